@@ -1,0 +1,166 @@
+/*
+ * quake_b200.h -- C ABI of the B200 (sm_100a) partitioned-IVF search hot path.
+ *
+ * This is the drop-in boundary for the Quake hot path. The reference has no
+ * FFI for this path: its seam is the pybind11 module `quake._bindings`
+ * (/root/reference/src/cpp/bindings/wrap.cpp:48), below which the functions listed here are plain C++
+ * calls. Each entry point cites the reference function it replaces. Signatures carry only plain
+ * pointers and sizes (device pointers unless stated otherwise) and a `cudaStream_t` passed as
+ * `void*`; no torch types. All calls are asynchronous on `stream` unless stated otherwise; they
+ * return 0 on success and a non-zero code on failure, in which case `qk_last_error()` describes
+ * the failure (same role as the reference's std::runtime_error / std::invalid_argument messages,
+ * src/cpp/include/common.h:154).
+ *
+ * There is NO CPU fallback behind any of these functions.
+ */
+#ifndef QUAKE_B200_H
+#define QUAKE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Same numeric values as faiss::MetricType, which the reference writes into metadata.txt
+ * (src/cpp/src/quake_index.cpp:187). */
+#define QK_METRIC_INNER_PRODUCT 0
+#define QK_METRIC_L2 1
+
+#define QK_OK 0
+#define QK_ERR_INVALID_ARGUMENT 1
+#define QK_ERR_CUDA 2
+#define QK_ERR_WORKSPACE 3
+#define QK_ERR_UNSUPPORTED 4
+
+/* Largest k (neighbours per query) the scan path accepts. */
+#define QK_MAX_K 2048
+
+/*
+ * Device-resident partition store: the B200 counterpart of faiss::DynamicInvertedLists +
+ * IndexPartition (src/cpp/include/dynamic_inverted_list.h:33, src/cpp/include/index_partition.h:24-29).
+ * Every partition ("list") is a contiguous run of rows in one arena; a list is cut into scan
+ * segments of at most `QK_SEGMENT_ROWS` rows so that oversized lists (a flat index is one list)
+ * still spread over the whole GPU.
+ */
+typedef struct qk_store {
+    const float*   vectors;      /* [rows x pitch] float32, row-major, 16-byte aligned rows          */
+    const int64_t* ids;          /* [rows] int64 vector ids; NULL => the arena row index is the id  */
+    int64_t        pitch;        /* floats per row, >= d, multiple of 4; padding must be zero       */
+    int32_t        d;            /* vector dimension                                                 */
+    int32_t        num_lists;    /* number of list slots                                             */
+    const int32_t* list_seg0;    /* [num_lists] first segment of each list                           */
+    const int32_t* list_nseg;    /* [num_lists] number of segments of each list (0 for an empty list)*/
+    int32_t        num_segments; /* total number of segments                                         */
+    int32_t        max_list_segments; /* max over lists of list_nseg (host-known)                    */
+    const int64_t* seg_row0;     /* [num_segments] first arena row of the segment                    */
+    const int32_t* seg_rows;     /* [num_segments] rows in the segment (1..QK_SEGMENT_ROWS)          */
+    float          max_row_norm; /* upper bound on the L2 norm of any stored row (see qk_max_row_norm)*/
+} qk_store_t;
+
+#define QK_SEGMENT_ROWS 4096
+
+/* ---- library info ------------------------------------------------------------------------- */
+const char* qk_version(void);
+const char* qk_last_error(void);
+/* Host call. Fails unless the current device is compute capability 10.x. */
+int qk_device_check(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---- partition scan + top-k ----------------------------------------------------------------
+ * Replaces QueryCoordinator::scan_partitions -> serial_scan / batched_serial_scan
+ * (src/cpp/src/query_coordinator.cpp:659-673, 471-611, 675-799), i.e. scan_list /
+ * batched_scan_list + TopkBuffer (src/cpp/include/list_scanning.h:241-366, 41-204) over the probed
+ * lists of every query, with the reference's output conventions: ids int64 / distances float32
+ * [Q x k], best first, L2 distances are Euclidean (sqrt) (list_scanning.h:260), missing slots are
+ * id -1 and +inf (l2) / -inf (ip) (query_coordinator.cpp:589-601).
+ *
+ * probe_lists: [Q x nprobe] int32 list slots in probe order, -1 = skip (query_coordinator.cpp:540).
+ * out_rows   : optional [Q x k] int64 arena row of each result (-1 where padded).
+ * stats      : optional device int32[4]: {queries that took the exact re-scan path, 0, 0, 0}.
+ */
+size_t qk_scan_workspace_bytes(const qk_store_t* store, int64_t num_queries, int nprobe, int k);
+int qk_scan_partitions(const qk_store_t* store,
+                       const float* queries, int64_t num_queries, int64_t query_pitch,
+                       const int32_t* probe_lists, int nprobe,
+                       int metric, int k,
+                       int64_t* out_ids, float* out_distances, int64_t* out_rows,
+                       void* workspace, size_t workspace_bytes,
+                       int32_t* stats, void* stream);
+
+/* Map the ids returned by the coarse (parent) scan -- partition ids -- to list slots of the child
+ * store. id_to_slot is a dense device table of `table_size` entries; ids outside it or mapped to
+ * a negative value become -1. Replaces the unordered_map lookup partitions_.at(pid)
+ * (src/cpp/src/dynamic_inverted_list.cpp) on the search path. */
+int qk_map_ids_to_slots(const int64_t* ids, int64_t n, const int32_t* id_to_slot, int64_t table_size,
+                        int32_t* out_slots, void* stream);
+
+/* Upper bound on the row norms of [n x pitch] rows, written to a device float (max-reduced into
+ * *out, which the caller initialises, e.g. to 0). Used for the filter/refine safety bound. */
+int qk_max_row_norm(const float* rows, int64_t n, int64_t pitch, int d, float* out, void* stream);
+
+/* Merge S partial results per query (multi-GPU shards, or APS rounds) into one top-k.
+ * Replaces the global TopkBuffer::batch_add merge of per-core partial results
+ * (src/cpp/src/query_coordinator.cpp:167-173, 752-758). parts are [S x Q x k]; padded entries have
+ * id -1. Order: by distance (ascending l2 / descending ip), ties by ascending id. */
+int qk_merge_topk(const float* part_distances, const int64_t* part_ids, int num_parts,
+                  int64_t num_queries, int k, int metric,
+                  int64_t* out_ids, float* out_distances, void* stream);
+
+/* ---- k-means assign / update / scatter ----------------------------------------------------
+ * Replaces faiss::IndexFlat::search(k=1) inside faiss::Clustering::train and the final assignment
+ * of kmeans() (src/cpp/src/clustering.cpp:65), and batched_scan_list(k=1) in
+ * kmeans_refine_partitions (clustering.cpp:152-159): nearest centroid per point, ties to the lowest
+ * centroid index. out_distances (optional): Euclidean distance / inner product to the chosen centroid.
+ * Runs on the partition-scan kernel (centroids as a flat store, points as queries, k = 1), so the
+ * argmin is decided in the reference's exact per-pair arithmetic. Host-synchronises once. */
+size_t qk_kmeans_assign_workspace_bytes(int64_t n, int64_t num_centroids, int d);
+int qk_kmeans_assign(const float* points, int64_t n, int64_t point_pitch, int d,
+                     const float* centroids, int64_t num_centroids, int64_t centroid_pitch,
+                     int metric, int32_t* out_assign, float* out_distances,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
+/* Replaces faiss compute_centroids (third_party/faiss/faiss/Clustering.cpp:123-192) and the scalar
+ * accumulation loop of kmeans_refine_partitions (clustering.cpp:162-175): per-centroid sum of
+ * assigned points and count. `order`/`offsets` come from qk_partition_by_assignment, so every
+ * centroid sums its members in ascending point index (deterministic). out_sums [K x out_pitch]. */
+int qk_kmeans_accumulate(const float* points, int64_t point_pitch, int d,
+                         const int64_t* order, const int64_t* offsets, int64_t num_centroids,
+                         float* out_sums, int64_t out_pitch, void* stream);
+
+/* Replaces torch::sort(assignments) + bincount + split (clustering.cpp:68-84): counting sort of
+ * point indices by assignment; within a centroid, ascending point index.
+ * counts [K] int64, offsets [K+1] int64, order [n] int64. */
+size_t qk_partition_workspace_bytes(int64_t n, int64_t num_centroids);
+int qk_partition_by_assignment(const int32_t* assign, int64_t n, int64_t num_centroids,
+                               int64_t* out_counts, int64_t* out_offsets, int64_t* out_order,
+                               void* workspace, size_t workspace_bytes, void* stream);
+
+/* dst[i] = src[order[i]] for rows (and ids when both id pointers are non-NULL): builds the CSR
+ * arena from the sorted order (replaces index_select + per-list add_entries,
+ * clustering.cpp:70-71, partition_manager.cpp:106-111). */
+int qk_gather_rows(const float* src, int64_t src_pitch, const int64_t* src_ids,
+                   const int64_t* order, int64_t n, int d,
+                   float* dst, int64_t dst_pitch, int64_t* dst_ids, void* stream);
+
+/* rows[i] /= ||rows[i]||_2 (in place). Replaces vectors / vectors.norm(2,1) (clustering.cpp:25-26). */
+int qk_normalize_rows(float* rows, int64_t n, int64_t pitch, int d, void* stream);
+
+/* dst[dst_rows[i]] = src[order ? order[i] : i] (rows, and ids when dst_ids != NULL): appends a batch
+ * into the lists of the arena. Replaces the per-vector add_entries loop of PartitionManager::add
+ * (src/cpp/src/partition_manager.cpp:245-258). */
+int qk_scatter_rows(const float* src, int64_t src_pitch, const int64_t* src_ids,
+                    const int64_t* order, const int64_t* dst_rows, int64_t n, int d,
+                    float* dst, int64_t dst_pitch, int64_t* dst_ids, void* stream);
+
+/* ---- host-side helpers (no GPU work): vendored-faiss control logic of Clustering::train ----------
+ * First m entries of faiss::rand_perm(n, seed) (third_party/faiss/faiss/utils/random.cpp:153-163). */
+int qk_host_rand_perm_prefix(int64_t n, int64_t seed, int64_t m, int64_t* out);
+/* faiss split_clusters (third_party/faiss/faiss/Clustering.cpp:204-251) on HOST arrays. */
+int qk_host_split_clusters(int64_t d, int64_t k, int64_t n, float* hassign, float* centroids,
+                           int64_t pitch, int64_t* nsplit_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QUAKE_B200_H */

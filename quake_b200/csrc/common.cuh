@@ -1,0 +1,162 @@
+// Shared device helpers for the quake_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+#include "../../include/quake_b200.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "quake_b200 kernels are written for sm_100a (B200) only"
+#endif
+
+namespace qk {
+
+// ---------------------------------------------------------------------------------------------
+// error plumbing (host)
+// ---------------------------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+#define QK_CUDA(call)                                              \
+    do {                                                           \
+        cudaError_t _e = (call);                                   \
+        if (_e != cudaSuccess) return ::qk::cuda_fail(_e, #call);  \
+    } while (0)
+#define QK_REQUIRE(cond, ...)                     \
+    do {                                          \
+        if (!(cond)) {                            \
+            ::qk::set_error(__VA_ARGS__);         \
+            return QK_ERR_INVALID_ARGUMENT;       \
+        }                                         \
+    } while (0)
+
+int sm_count();
+
+// ---------------------------------------------------------------------------------------------
+// order-preserving float <-> uint32 keys (ascending float order == ascending unsigned order)
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ uint32_t f2key(float f) {
+#ifdef __CUDA_ARCH__
+    uint32_t u = __float_as_uint(f);
+#else
+    uint32_t u;
+    memcpy(&u, &f, 4);
+#endif
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__host__ __device__ __forceinline__ float key2f(uint32_t k) {
+    uint32_t u = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(u);
+#else
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+#endif
+}
+static constexpr uint32_t KEY_MAX = 0xffffffffu;
+static constexpr uint64_t COMP_MAX = 0xffffffffffffffffull;
+
+// ---------------------------------------------------------------------------------------------
+// Pairwise distances in the REFERENCE'S summation order.
+//
+// The reference's per-pair arithmetic is faiss fvec_L2sqr / fvec_inner_product
+// (third_party/faiss/faiss/utils/distances_simd.cpp:188-224), plain loops that GCC -O3 (the reference's
+// Release flag, CMakeLists.txt:37) vectorises 8-wide for AVX2 without contracting the main loop to
+// FMA: lane j accumulates elements i == j (mod 8) with separately rounded sub, mul, add; the lanes
+// are folded as ((a0+a4)+(a2+a6)) + ((a1+a5)+(a3+a7)); a 4-wide FMA step and scalar FMA steps
+// absorb the remainder when d is not a multiple of 8. The functions below reproduce exactly that
+// evaluation order with IEEE round-to-nearest intrinsics, so the refined distances are
+// bit-identical to the reference build in oracle/_ref (checked in tests/).
+// ---------------------------------------------------------------------------------------------
+template <bool kIP>
+__device__ __forceinline__ float ref_term(float x, float y) {
+    if (kIP) return __fmul_rn(x, y);
+    float t = __fsub_rn(x, y);
+    return __fmul_rn(t, t);
+}
+template <bool kIP>
+__device__ __forceinline__ float ref_fma_term(float x, float y, float acc) {
+    if (kIP) return __fmaf_rn(x, y, acc);
+    float t = __fsub_rn(x, y);
+    return __fmaf_rn(t, t, acc);
+}
+
+template <bool kIP>
+__device__ float ref_pair_distance(const float* __restrict__ x, const float* __restrict__ y, int d) {
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, a4 = 0.f, a5 = 0.f, a6 = 0.f, a7 = 0.f;
+    const int nb = d >> 3;
+    for (int b = 0; b < nb; ++b) {
+        const float* xb = x + 8 * b;
+        const float* yb = y + 8 * b;
+        a0 = __fadd_rn(a0, ref_term<kIP>(xb[0], yb[0]));
+        a1 = __fadd_rn(a1, ref_term<kIP>(xb[1], yb[1]));
+        a2 = __fadd_rn(a2, ref_term<kIP>(xb[2], yb[2]));
+        a3 = __fadd_rn(a3, ref_term<kIP>(xb[3], yb[3]));
+        a4 = __fadd_rn(a4, ref_term<kIP>(xb[4], yb[4]));
+        a5 = __fadd_rn(a5, ref_term<kIP>(xb[5], yb[5]));
+        a6 = __fadd_rn(a6, ref_term<kIP>(xb[6], yb[6]));
+        a7 = __fadd_rn(a7, ref_term<kIP>(xb[7], yb[7]));
+    }
+    float s0 = __fadd_rn(a0, a4), s1 = __fadd_rn(a1, a5), s2 = __fadd_rn(a2, a6), s3 = __fadd_rn(a3, a7);
+    float res = __fadd_rn(__fadd_rn(s0, s2), __fadd_rn(s1, s3));
+    int o = nb << 3;
+    int r = d - o;
+    if (r >= 4) {
+        float f0 = ref_fma_term<kIP>(x[o + 0], y[o + 0], s0);
+        float f1 = ref_fma_term<kIP>(x[o + 1], y[o + 1], s1);
+        float f2 = ref_fma_term<kIP>(x[o + 2], y[o + 2], s2);
+        float f3 = ref_fma_term<kIP>(x[o + 3], y[o + 3], s3);
+        res = __fadd_rn(__fadd_rn(f0, f2), __fadd_rn(f1, f3));
+        o += 4;
+        r -= 4;
+    }
+    for (int i = 0; i < r; ++i) res = ref_fma_term<kIP>(x[o + i], y[o + i], res);
+    return res;
+}
+
+// ---------------------------------------------------------------------------------------------
+// mbarrier + bulk-copy (TMA, UBLKCP) wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done = 0;
+    const uint32_t a = smem_u32(bar);
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(a), "r"(parity)
+            : "memory");
+    }
+}
+// 1-D bulk copy global -> shared, completion signalled on an mbarrier (bytes % 16 == 0, 16B aligned).
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+
+__device__ __forceinline__ uint64_t shfl_u64(uint64_t v, int src) {
+    uint32_t lo = __shfl_sync(0xffffffffu, (uint32_t)v, src);
+    uint32_t hi = __shfl_sync(0xffffffffu, (uint32_t)(v >> 32), src);
+    return ((uint64_t)hi << 32) | lo;
+}
+
+}  // namespace qk

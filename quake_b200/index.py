@@ -1,0 +1,455 @@
+"""QuakeIndex: the reference's Python-facing index object, hosted on one B200.
+
+Mirrors ``QuakeIndex`` + ``QueryCoordinator`` + ``PartitionManager`` of the reference for the hot path
+(/root/reference/src/cpp/src/quake_index.cpp, query_coordinator.cpp:612-657, partition_manager.cpp) with
+the method names, argument meaning, output conventions and error classes of the pybind11 surface
+(/root/reference/src/cpp/bindings/wrap.cpp:57-128). Distance arithmetic and top-k run in the CUDA
+kernels behind include/quake_b200.h; nothing here falls back to the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import struct
+import time
+
+import numpy as np
+import torch
+
+from . import _lib, aps, clustering
+from ._lib import check, ptr
+from .params import (BuildTimingInfo, IndexBuildParams, MaintenancePolicyParams, MaintenanceTimingInfo,
+                     ModifyTimingInfo, SearchParams, SearchResult, SearchTimingInfo, str_to_metric)
+from .store import PartitionStore
+
+SERIALIZATION_MAGIC = 0x44494E4C  # common.h:66
+SERIALIZATION_VERSION = 3         # common.h:67
+_WORKSPACE_LIMIT = 6 << 30        # split query batches whose scan workspace would exceed this
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _device() -> torch.device:
+    _lib.require_device()
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def scan_partitions(store: PartitionStore, xq: torch.Tensor, probe_slots: torch.Tensor, k: int, metric: int,
+                    want_rows: bool = False):
+    """qk_scan_partitions over a device query batch xq [Q, pitch] and probe_slots [Q, nprobe] (int32).
+    Returns (ids [Q,k] int64, distances [Q,k] float32[, rows]) on the device."""
+    lib = _lib.load()
+    st, _ = store.tables()
+    Q, nprobe = int(probe_slots.shape[0]), int(probe_slots.shape[1])
+    dev = xq.device
+    out_ids = torch.empty((Q, k), dtype=torch.int64, device=dev)
+    out_dist = torch.empty((Q, k), dtype=torch.float32, device=dev)
+    out_rows = torch.empty((Q, k), dtype=torch.int64, device=dev) if want_rows else None
+    if st.num_segments == 0:
+        out_ids.fill_(-1)
+        out_dist.fill_(float("-inf") if metric == _lib.QK_METRIC_INNER_PRODUCT else float("inf"))
+        if want_rows:
+            out_rows.fill_(-1)
+        return (out_ids, out_dist, out_rows) if want_rows else (out_ids, out_dist)
+    probe_slots = probe_slots.to(torch.int32).contiguous()
+    # chunk the batch so that the workspace stays bounded
+    chunk = Q
+    while True:
+        wsb = lib.qk_scan_workspace_bytes(C.byref(st), chunk, nprobe, k)
+        if wsb == 0:
+            check(lib.qk_scan_partitions(C.byref(st), ptr(xq), chunk, xq.stride(0), ptr(probe_slots), nprobe, metric, k,
+                                         ptr(out_ids), ptr(out_dist), None, None, 0, None, _stream()))
+            raise _lib.QuakeB200Error("scan plan failed")
+        if wsb <= _WORKSPACE_LIMIT or chunk <= 32:
+            break
+        chunk = (chunk + 1) // 2
+    ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+    for b in range(0, Q, chunk):
+        n = min(chunk, Q - b)
+        check(lib.qk_scan_partitions(C.byref(st), ptr(xq[b:]), n, xq.stride(0), ptr(probe_slots[b:]), nprobe, metric, k,
+                                     ptr(out_ids[b:]), ptr(out_dist[b:]), ptr(out_rows[b:]) if want_rows else None,
+                                     ptr(ws), wsb, None, _stream()))
+    return (out_ids, out_dist, out_rows) if want_rows else (out_ids, out_dist)
+
+
+class QuakeIndex:
+    def __init__(self, current_level: int = 0):
+        self.parent: "QuakeIndex | None" = None
+        self.current_level = int(current_level)
+        self.store: PartitionStore | None = None
+        self.metric = 1
+        self.build_params: IndexBuildParams | None = None
+        self.maintenance_policy_params: MaintenancePolicyParams | None = None
+        self._hits: list[np.ndarray] = []  # per-query probed partitions (hit window)
+
+    # ------------------------------------------------------------------ build (quake_index.cpp:29-90)
+    def build(self, x: torch.Tensor, ids: torch.Tensor, build_params: IndexBuildParams) -> BuildTimingInfo:
+        t0 = time.perf_counter()
+        dev = _device()
+        self.build_params = build_params
+        self.metric = str_to_metric(build_params.metric)
+        if x.dim() != 2:
+            raise RuntimeError("[QuakeIndex::build] x must be 2D [N, dim]")
+        n, d = int(x.shape[0]), int(x.shape[1])
+        if ids.shape[0] != n:
+            raise RuntimeError("[QuakeIndex::build] x and ids must have the same number of rows")
+        info = BuildTimingInfo()
+        info.n_vectors, info.d = n, d
+        xd = clustering.pad_rows(x, dev)
+        if xd.data_ptr() == x.data_ptr():
+            xd = xd.clone()  # the reference deep-copies x (quake_index.cpp:33)
+        idd = ids.to(device=dev, dtype=torch.int64).contiguous()
+        self.store = PartitionStore(d, dev)
+        nlist = int(build_params.nlist)
+        if nlist > 1:
+            s1 = time.perf_counter()
+            centroids, counts, offsets, order = clustering.kmeans(xd, d, nlist, self.metric, int(build_params.niter))
+            torch.cuda.synchronize()
+            info.train_time_us = int((time.perf_counter() - s1) * 1e6)
+            s2 = time.perf_counter()
+            self.parent = QuakeIndex(self.current_level + 1)
+            pp = IndexBuildParams()
+            pp.metric = build_params.metric
+            pp.num_workers = build_params.num_workers
+            self.parent.build(centroids[:, :d], torch.arange(nlist, dtype=torch.int64), pp)
+            self.store.init_from_sorted(xd, idd, order, counts.cpu().numpy(), np.arange(nlist, dtype=np.int64))
+            torch.cuda.synchronize()
+            info.assign_time_us = int((time.perf_counter() - s2) * 1e6)
+        else:
+            # flat index: one partition with id 0 (quake_index.cpp:66-79)
+            self.parent = None
+            self.store.init_from_sorted(xd, idd, None, np.array([n], dtype=np.int64), np.array([0], dtype=np.int64))
+        info.n_clusters = self.nlist()
+        self.initialize_maintenance_policy(MaintenancePolicyParams())
+        torch.cuda.synchronize()
+        info.total_time_us = int((time.perf_counter() - t0) * 1e6)
+        return info
+
+    # ------------------------------------------------------------------ search (query_coordinator.cpp:612-657)
+    def _check_built(self, who: str):
+        if self.store is None:
+            raise RuntimeError(f"[QuakeIndex::{who}()] No query coordinator. Did you build the index?")
+
+    def search(self, x: torch.Tensor, search_params: SearchParams) -> SearchResult:
+        self._check_built("search")
+        t0 = time.perf_counter()
+        res = SearchResult()
+        tinfo = SearchTimingInfo()
+        tinfo.search_params = search_params
+        tinfo.n_clusters = self.nlist()
+        res.timing_info = tinfo
+        if x is None or x.numel() == 0 or x.shape[0] == 0:
+            # query_coordinator.cpp:476-482
+            res.ids = torch.empty((0,), dtype=torch.int64)
+            res.distances = torch.empty((0,), dtype=torch.float32)
+            tinfo.parent_info = SearchTimingInfo()
+            return res
+        if x.dim() != 2 or int(x.shape[1]) != self.store.d:
+            raise RuntimeError(f"[QuakeIndex::search] queries must be [Q, {self.store.d}]")
+        out_dev = x.device
+        xq = clustering.pad_rows(x, self.store.device)
+        ids, dist, parent_info = self._search_device(xq, search_params, tinfo)
+        res.ids = ids.to(out_dev)
+        res.distances = dist.to(out_dev)
+        tinfo.n_queries = int(x.shape[0])
+        tinfo.parent_info = parent_info
+        tinfo.total_time_ns = int((time.perf_counter() - t0) * 1e9)
+        return res
+
+    def _search_device(self, xq: torch.Tensor, sp: SearchParams, tinfo: SearchTimingInfo | None = None):
+        """Device-resident search: xq [Q, pitch] on the index's device -> (ids, distances) device tensors."""
+        Q = int(xq.shape[0])
+        k = int(sp.k) if sp is not None and int(sp.k) > 0 else 1
+        dev = xq.device
+        parent_info = SearchTimingInfo()
+        if self.parent is None:
+            # flat: every query scans all partitions (query_coordinator.cpp:624-626)
+            _, table = self.store.tables()
+            pids = self.store.partition_ids()
+            slots = torch.tensor([self.store.pid_slot[int(p)] for p in pids], dtype=torch.int32, device=dev)
+            probe = slots[None, :].expand(Q, -1).contiguous()
+            ids, dist = scan_partitions(self.store, xq, probe, k, self.metric)
+            return ids, dist, parent_info
+        nlist = self.nlist()
+        use_aps = float(sp.recall_target) > 0.0 and not bool(sp.batched_scan)
+        psp = SearchParams()
+        psp.batched_scan = True
+        psp.recall_target = sp.recall_target
+        if use_aps:
+            psp.k = max(int(nlist * float(sp.initial_search_fraction)), 1)  # query_coordinator.cpp:636-639
+        else:
+            psp.k = min(int(sp.nprobe), nlist)
+        t1 = time.perf_counter()
+        p_ids, _p_dist, _ = self.parent._search_device(xq, psp)
+        parent_info.n_queries = Q
+        parent_info.n_clusters = self.parent.nlist()
+        _, table = self.store.tables()
+        lib = _lib.load()
+        slots = torch.empty(p_ids.shape, dtype=torch.int32, device=dev)
+        check(lib.qk_map_ids_to_slots(ptr(p_ids), p_ids.numel(), ptr(table), table.numel(), ptr(slots), _stream()))
+        parent_info.total_time_ns = int((time.perf_counter() - t1) * 1e9)
+        if use_aps:
+            ids, dist, scanned = aps.adaptive_scan(self, xq, p_ids, slots, sp)
+            if tinfo is not None:
+                tinfo.partitions_scanned = int(scanned)
+        else:
+            ids, dist = scan_partitions(self.store, xq, slots, k, self.metric)
+        if self.maintenance_policy_params is not None and self.current_level == 0:
+            self._record_hits(p_ids)
+        return ids, dist, parent_info
+
+    def _record_hits(self, p_ids: torch.Tensor) -> None:
+        """Keep the last `window_size` queries' probed partitions (the reference's HitCountTracker,
+        hit_count_tracker.cpp:43-66; docs/architecture/architecture.rst:21). Kept on the device and only
+        materialised by maintenance()."""
+        w = int(self.maintenance_policy_params.window_size)
+        self._hits.append(p_ids[-w:].detach())
+        total = sum(int(h.shape[0]) for h in self._hits)
+        while len(self._hits) > 1 and total - int(self._hits[0].shape[0]) >= w:
+            total -= int(self._hits.pop(0).shape[0])
+
+    # ------------------------------------------------------------------ accessors
+    def get_ids(self) -> torch.Tensor:
+        if self.store is None:
+            raise RuntimeError("[QuakeIndex::get_ids()] No partition manager. Index not built?")
+        out = [self.store.get_list(int(p))[1] for p in self.store.partition_ids()]
+        return torch.cat(out).cpu() if out else torch.empty((0,), dtype=torch.int64)
+
+    def get(self, ids: torch.Tensor) -> torch.Tensor:
+        if self.store is None:
+            raise RuntimeError("[QuakeIndex::get()] No partition manager. Index not built?")
+        rows = self.store.find_rows(ids.to(torch.int64))
+        if bool((rows < 0).any()):
+            raise RuntimeError("ID not found in any partition")
+        return self.store.vectors[rows, : self.store.d].to(ids.device)
+
+    def ntotal(self) -> int:
+        return self.store.ntotal if self.store is not None else 0
+
+    def nlist(self) -> int:
+        return self.store.nlist if self.store is not None else 0
+
+    def d(self) -> int:
+        return self.store.d if self.store is not None else 0
+
+    # ------------------------------------------------------------------ add / remove (partition_manager.cpp:123-320)
+    def add(self, x: torch.Tensor, ids: torch.Tensor, assignments: torch.Tensor | None = None) -> ModifyTimingInfo:
+        if self.store is None:
+            raise RuntimeError("[QuakeIndex::add()] No partition manager. Build the index first.")
+        info = ModifyTimingInfo()
+        s1 = time.perf_counter()
+        if x is None or ids is None:
+            raise RuntimeError("[PartitionManager] add: vectors or vector_ids is undefined.")
+        if x.shape[0] != ids.shape[0]:
+            raise RuntimeError("[PartitionManager] add: mismatch in vectors.size(0) and vector_ids.size(0).")
+        n = int(x.shape[0])
+        info.modify_count = n
+        if n == 0:
+            return info
+        if x.dim() != 2:
+            raise RuntimeError("[PartitionManager] add: 'vectors' must be 2D [N, dim].")
+        if int(x.shape[1]) != self.store.d:
+            raise RuntimeError("[PartitionManager] add: dimension mismatch.")
+        dev = self.store.device
+        idd = ids.to(device=dev, dtype=torch.int64).contiguous()
+        if bool((idd > 2**31 - 1).any()):
+            raise RuntimeError("[PartitionManager] add: vector_ids must be less than INT_MAX.")
+        if int(torch.unique(idd).numel()) != n:
+            raise RuntimeError("[PartitionManager] add: vector_ids must be unique.")
+        if assignments is not None and bool((assignments >= self.store.curr_list_id).any()):
+            raise RuntimeError("[PartitionManager] add: assignments must be less than partition_store_->curr_list_id_.")
+        info.input_validation_time_us = int((time.perf_counter() - s1) * 1e6)
+        s2 = time.perf_counter()
+        xd = clustering.pad_rows(x, dev)
+        _, table = self.store.tables()
+        if self.parent is None:
+            slots = torch.full((n,), self.store.pid_slot[0] if 0 in self.store.pid_slot else -1, dtype=torch.int32,
+                               device=dev)
+        else:
+            if assignments is not None and assignments.numel() > 0:
+                if assignments.shape[0] != n:
+                    raise RuntimeError("[PartitionManager] add: assignments.size(0) != vectors.size(0).")
+                pid = assignments.to(device=dev, dtype=torch.int64).contiguous()
+            else:
+                psp = SearchParams()
+                psp.k = 1
+                psp.nprobe = self.parent.nlist()
+                psp.batched_scan = n > 10
+                pid, _, _ = self.parent._search_device(xd, psp)
+                pid = pid.reshape(-1).contiguous()
+            slots = torch.empty((n,), dtype=torch.int32, device=dev)
+            check(_lib.load().qk_map_ids_to_slots(ptr(pid), n, ptr(table), table.numel(), ptr(slots), _stream()))
+        torch.cuda.synchronize()
+        info.find_partition_time_us = int((time.perf_counter() - s2) * 1e6)
+        s3 = time.perf_counter()
+        if bool((slots < 0).any()):
+            raise RuntimeError("List does not exist in add_entries")
+        self.store.append(slots, xd, idd)
+        torch.cuda.synchronize()
+        info.modify_time_us = int((time.perf_counter() - s3) * 1e6)
+        return info
+
+    def remove(self, ids: torch.Tensor) -> ModifyTimingInfo:
+        if self.store is None:
+            raise RuntimeError("[QuakeIndex::remove()] No partition manager. Build the index first.")
+        info = ModifyTimingInfo()
+        if ids is None or ids.shape[0] == 0:
+            return info
+        info.modify_count = int(ids.shape[0])
+        s = time.perf_counter()
+        self.store.remove_ids(ids.to(device=self.store.device, dtype=torch.int64))
+        torch.cuda.synchronize()
+        info.modify_time_us = int((time.perf_counter() - s) * 1e6)
+        return info
+
+    def modify(self, ids: torch.Tensor, x: torch.Tensor) -> ModifyTimingInfo:
+        """quake_index.cpp:142-145: remove + add."""
+        self.remove(ids)
+        return self.add(x, ids)
+
+    # ------------------------------------------------------------------ maintenance
+    def initialize_maintenance_policy(self, maintenance_policy_params: MaintenancePolicyParams) -> None:
+        self.maintenance_policy_params = maintenance_policy_params
+        self._hits = []
+
+    def refine_partitions(self, partition_ids: torch.Tensor | None = None, iterations: int = 0) -> None:
+        """PartitionManager::refine_partitions (partition_manager.cpp:447-488): Lloyd refit restricted to
+        the given partitions; centroids in the parent are replaced (remove + add)."""
+        if self.parent is None:
+            raise RuntimeError("Index is not partitioned")
+        if partition_ids is None:
+            partition_ids = self.parent.get_ids()
+        pids = [int(p) for p in partition_ids.tolist()]
+        if not pids:
+            return
+        dev = self.store.device
+        d = self.store.d
+        pid_t = torch.tensor(pids, dtype=torch.int64)
+        cents = clustering.pad_rows(self.parent.get(pid_t.to(dev)), dev)
+        vecs, vids = [], []
+        for p in pids:
+            v, i = self.store.get_list(p, padded=True)
+            vecs.append(v)
+            vids.append(i)
+        allv = torch.cat(vecs).contiguous()
+        alli = torch.cat(vids).contiguous()
+        new_c, counts, nv, ni = clustering.kmeans_refine(cents, d, allv, alli, self.metric, int(iterations))
+        counts_h = counts.cpu().numpy()
+        offs = np.concatenate([[0], np.cumsum(counts_h)])
+        for j, p in enumerate(pids):
+            self.store.set_list(p, nv[offs[j]:offs[j + 1], :d], ni[offs[j]:offs[j + 1]])
+        self.parent.modify(pid_t, new_c[:, :d])
+
+    def maintenance(self) -> MaintenanceTimingInfo:
+        """QuakeIndex::maintenance (quake_index.cpp:157-163). Like the reference, nothing happens until the
+        hit window is full (maintenance_policies.cpp:36-41). Once it is, the partitions probed in the
+        window are refit with the k-means refit kernel path (refine_partitions with
+        `refinement_iterations`), which is the hot-path part of the reference's maintenance; the
+        cost-model split/delete policy is host control logic outside this build's scope."""
+        if self.maintenance_policy_params is None:
+            raise RuntimeError("[QuakeIndex::maintenance()] No maintenance policy set.")
+        info = MaintenanceTimingInfo()
+        p = self.maintenance_policy_params
+        recorded = sum(int(h.shape[0]) for h in self._hits)
+        if self.parent is None or recorded < int(p.window_size):
+            print(f"Window not full yet. {recorded} queries recorded and {p.window_size} queries required.")
+            return info
+        t0 = time.perf_counter()
+        hit = torch.unique(torch.cat([h.reshape(-1) for h in self._hits]))
+        hit = hit[hit >= 0].cpu()
+        live = set(int(x) for x in self.store.partition_ids())
+        hit = torch.tensor([int(x) for x in hit.tolist() if int(x) in live], dtype=torch.int64)
+        if hit.numel():
+            self.refine_partitions(hit, int(p.refinement_iterations))
+        torch.cuda.synchronize()
+        info.split_refine_time_us = int((time.perf_counter() - t0) * 1e6)
+        info.total_time_us = info.split_refine_time_us
+        self._hits = []
+        return info
+
+    # ------------------------------------------------------------------ save / load (quake_index.cpp:170-267)
+    def save(self, dir_path: str) -> None:
+        if os.path.exists(dir_path) and not os.path.isdir(dir_path):
+            raise RuntimeError("save path exists but is not a directory: " + dir_path)
+        os.makedirs(dir_path, exist_ok=True)
+        with open(os.path.join(dir_path, "metadata.txt"), "w") as f:
+            f.write(f"metric={self.metric}\nlevel={self.current_level}\nntotal={self.ntotal()}\nnlist={self.nlist()}\n")
+        self._save_partitions(os.path.join(dir_path, "partitions"))
+        if self.parent is not None:
+            self.parent.save(os.path.join(dir_path, "parent"))
+
+    def _save_partitions(self, path: str) -> None:
+        """DynamicInvertedLists::save, format v3 (dynamic_inverted_list.cpp:338-419): 32-byte header
+        {magic u32, version u32, nlist u64, code_size u64, num_partitions u64}, offsets u64[np+1],
+        partition ids u64[np], then per partition codes[n x code_size] followed by ids[n x 8]."""
+        st = self.store
+        pids = st.partition_ids()
+        code_size = st.d * 4
+        sizes = np.array([st.size_of(int(p)) for p in pids], dtype=np.uint64)
+        chunk = sizes * np.uint64(code_size + 8)
+        offsets = np.concatenate([[0], np.cumsum(chunk)]).astype(np.uint64)
+        with open(path, "wb") as f:
+            f.write(struct.pack("<IIQQQ", SERIALIZATION_MAGIC, SERIALIZATION_VERSION, len(pids), code_size, len(pids)))
+            f.write(offsets.tobytes())
+            f.write(pids.astype(np.uint64).tobytes())
+            for p in pids:
+                v, i = st.get_list(int(p))
+                f.write(v.contiguous().cpu().numpy().tobytes())
+                f.write(i.contiguous().cpu().numpy().tobytes())
+
+    def load(self, dir_path: str, n_workers: int = 0) -> None:
+        if not os.path.isdir(dir_path):
+            raise RuntimeError("Cannot load QuakeIndex, directory does not exist: " + dir_path)
+        dev = _device()
+        with open(os.path.join(dir_path, "metadata.txt")) as f:
+            for line in f:
+                if "=" not in line:
+                    continue
+                key, val = line.strip().split("=", 1)
+                if key == "metric":
+                    self.metric = int(val)
+                elif key == "level":
+                    self.current_level = int(val)
+        self._load_partitions(os.path.join(dir_path, "partitions"), dev)
+        pdir = os.path.join(dir_path, "parent")
+        if os.path.isdir(pdir):
+            self.parent = QuakeIndex()
+            self.parent.load(pdir, n_workers)
+        else:
+            self.parent = None
+        self.initialize_maintenance_policy(MaintenancePolicyParams())
+
+    def _load_partitions(self, path: str, dev) -> None:
+        with open(path, "rb") as f:
+            raw = f.read()
+        magic, version, _nlist, code_size, nparts = struct.unpack_from("<IIQQQ", raw, 0)
+        if magic != SERIALIZATION_MAGIC:
+            raise RuntimeError("Invalid file format (bad magic number).")
+        if version != SERIALIZATION_VERSION:
+            raise RuntimeError("Unsupported file version: " + str(version))
+        d = code_size // 4
+        offsets = np.frombuffer(raw, dtype=np.uint64, count=nparts + 1, offset=32)
+        pids = np.frombuffer(raw, dtype=np.uint64, count=nparts, offset=32 + 8 * (nparts + 1)).astype(np.int64)
+        start = 32 + 8 * (nparts + 1) + 8 * nparts
+        rec = code_size + 8
+        vec_parts, id_parts, counts = [], [], []
+        for i in range(nparts):
+            size = int(offsets[i + 1] - offsets[i])
+            if size % rec:
+                raise RuntimeError("Partition chunk size not divisible by (code_size+sizeof(idx_t))")
+            nv = size // rec
+            o = start + int(offsets[i])
+            vec_parts.append(np.frombuffer(raw, dtype=np.float32, count=nv * d, offset=o).reshape(nv, d))
+            id_parts.append(np.frombuffer(raw, dtype=np.int64, count=nv, offset=o + nv * code_size))
+            counts.append(nv)
+        self.store = PartitionStore(d, dev)
+        vecs = np.concatenate(vec_parts) if vec_parts else np.zeros((0, d), np.float32)
+        idv = np.concatenate(id_parts) if id_parts else np.zeros((0,), np.int64)
+        xd = clustering.pad_rows(torch.from_numpy(vecs.copy()), dev)
+        idd = torch.from_numpy(idv.copy()).to(dev)
+        self.store.init_from_sorted(xd, idd, None, np.array(counts, dtype=np.int64), pids)
+
+    def __repr__(self):
+        return '{"current_level": %d, }' % self.current_level

@@ -1,0 +1,353 @@
+"""Device-resident dynamic partition store.
+
+B200 counterpart of the reference's ``faiss::DynamicInvertedLists`` + ``IndexPartition``
+(/root/reference/src/cpp/include/dynamic_inverted_list.h:33, include/index_partition.h:24-29,
+src/index_partition.cpp:52-102, 247-255): every partition ("list") owns a contiguous run of rows
+``[row0, row0 + cap)`` of one HBM arena (vectors ``[rows, pitch]`` float32 + ids ``[rows]`` int64), of
+which the first ``size`` are live. Appends fill the slack; a list that outgrows its capacity is moved
+to the end of the arena with doubled capacity (the reference doubles per-list mallocs); removal is the
+reference's swap-with-last. Lists are cut into scan segments of <= QK_SEGMENT_ROWS rows.
+
+All bookkeeping (list table, id -> slot map) lives on the host, as it does in the reference; only the
+vector/id payload and the small lookup tables the kernels read live on the device.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import QK_SEGMENT_ROWS, QkStore, check, ptr
+
+
+def _round_up(x: int, a: int) -> int:
+    return (x + a - 1) // a * a
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class PartitionStore:
+    def __init__(self, d: int, device: torch.device):
+        self.d = int(d)
+        self.pitch = _round_up(self.d, 4)
+        self.device = device
+        self.vectors = torch.zeros((0, self.pitch), dtype=torch.float32, device=device)
+        self.ids = torch.zeros((0,), dtype=torch.int64, device=device)
+        self.rows_used = 0
+        self.list_row0 = np.zeros(0, dtype=np.int64)
+        self.list_size = np.zeros(0, dtype=np.int64)
+        self.list_cap = np.zeros(0, dtype=np.int64)
+        self.slot_pid = np.zeros(0, dtype=np.int64)
+        self.pid_slot: dict[int, int] = {}
+        self.free_slots: list[int] = []
+        self.curr_list_id = 0
+        self.max_row_norm = 0.0
+        self._dirty = True
+        self._tables = None
+        self._struct = None
+        self._id_to_slot = None
+
+    # ------------------------------------------------------------------ basic queries
+    @property
+    def nlist(self) -> int:
+        return len(self.pid_slot)
+
+    @property
+    def ntotal(self) -> int:
+        return int(self.list_size.sum()) if self.list_size.size else 0
+
+    def partition_ids(self) -> np.ndarray:
+        return np.array(sorted(self.pid_slot.keys()), dtype=np.int64)
+
+    def size_of(self, pid: int) -> int:
+        return int(self.list_size[self.pid_slot[int(pid)]])
+
+    # ------------------------------------------------------------------ arena management
+    def _reserve_rows(self, rows: int) -> None:
+        if rows <= self.vectors.shape[0]:
+            return
+        new_cap = max(rows, int(self.vectors.shape[0] * 1.5) + 1024)
+        nv = torch.zeros((new_cap, self.pitch), dtype=torch.float32, device=self.device)
+        ni = torch.full((new_cap,), -1, dtype=torch.int64, device=self.device)
+        if self.rows_used:
+            nv[: self.rows_used].copy_(self.vectors[: self.rows_used])
+            ni[: self.rows_used].copy_(self.ids[: self.rows_used])
+        self.vectors, self.ids = nv, ni
+        self._dirty = True
+
+    def _new_slot(self) -> int:
+        if self.free_slots:
+            return self.free_slots.pop()
+        s = self.slot_pid.size
+        for name in ("list_row0", "list_size", "list_cap"):
+            setattr(self, name, np.append(getattr(self, name), 0))
+        self.slot_pid = np.append(self.slot_pid, -1)
+        return s
+
+    def add_list(self, pid: int, capacity: int = 0) -> int:
+        """DynamicInvertedLists::add_list: a new empty partition."""
+        pid = int(pid)
+        if pid in self.pid_slot:
+            raise RuntimeError("List already exists in add_list")
+        s = self._new_slot()
+        cap = int(capacity)
+        self.list_row0[s] = self.rows_used
+        self.list_size[s] = 0
+        self.list_cap[s] = cap
+        self.slot_pid[s] = pid
+        self.pid_slot[pid] = s
+        self._reserve_rows(self.rows_used + cap)
+        self.rows_used += cap
+        self.curr_list_id = max(self.curr_list_id, pid + 1)
+        self._dirty = True
+        return s
+
+    def remove_list(self, pid: int) -> None:
+        pid = int(pid)
+        s = self.pid_slot.pop(pid, None)
+        if s is None:
+            raise RuntimeError("List does not exist in remove_list")
+        self.list_size[s] = 0
+        self.list_cap[s] = 0  # the rows become dead space until compact()
+        self.slot_pid[s] = -1
+        self.free_slots.append(s)
+        self._dirty = True
+
+    def _grow_list(self, s: int, need: int) -> None:
+        """Move list `s` to the end of the arena with capacity >= need (doubling)."""
+        new_cap = max(need, 2 * int(self.list_cap[s]), 32)
+        old0, n = int(self.list_row0[s]), int(self.list_size[s])
+        self._reserve_rows(self.rows_used + new_cap)
+        new0 = self.rows_used
+        if n:
+            self.vectors[new0:new0 + n].copy_(self.vectors[old0:old0 + n])
+            self.ids[new0:new0 + n].copy_(self.ids[old0:old0 + n])
+        self.list_row0[s] = new0
+        self.list_cap[s] = new_cap
+        self.rows_used += new_cap
+        self._dirty = True
+
+    # ------------------------------------------------------------------ bulk build
+    def init_from_sorted(self, src: torch.Tensor, src_ids: torch.Tensor, order: torch.Tensor | None,
+                         counts: np.ndarray, pids: np.ndarray, slack: bool = True) -> None:
+        """Lay out len(counts) lists; list i receives rows src[order[offs[i]:offs[i+1]]]
+        (PartitionManager::init_partitions, partition_manager.cpp:33-121)."""
+        lib = _lib.load()
+        counts = np.asarray(counts, dtype=np.int64)
+        n = int(counts.sum())
+        caps = counts + np.maximum(16, counts // 8) if slack else counts.copy()
+        caps = (caps + 3) // 4 * 4
+        row0 = np.concatenate([[0], np.cumsum(caps)[:-1]]).astype(np.int64) if len(caps) else np.zeros(0, np.int64)
+        total = int(caps.sum())
+        self.vectors = torch.zeros((total, self.pitch), dtype=torch.float32, device=self.device)
+        self.ids = torch.full((total,), -1, dtype=torch.int64, device=self.device)
+        self.rows_used = total
+        nl = len(counts)
+        self.list_row0 = row0.copy()
+        self.list_size = counts.copy()
+        self.list_cap = caps.astype(np.int64)
+        self.slot_pid = np.asarray(pids, dtype=np.int64).copy()
+        self.pid_slot = {int(p): i for i, p in enumerate(self.slot_pid)}
+        self.free_slots = []
+        self.curr_list_id = int(self.slot_pid.max()) + 1 if nl else 0
+        if n:
+            offs = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+            shift = torch.from_numpy(row0 - offs[:-1]).to(self.device)
+            dst_rows = torch.arange(n, dtype=torch.int64, device=self.device) + torch.repeat_interleave(
+                shift, torch.from_numpy(counts).to(self.device))
+            check(lib.qk_scatter_rows(ptr(src), src.stride(0), ptr(src_ids), ptr(order), ptr(dst_rows), n, self.d,
+                                      ptr(self.vectors), self.pitch, ptr(self.ids), _stream()))
+        self._dirty = True
+        self.refresh_max_norm()
+
+    def refresh_max_norm(self) -> None:
+        lib = _lib.load()
+        if self.rows_used == 0:
+            self.max_row_norm = 0.0
+            return
+        out = torch.zeros(1, dtype=torch.float32, device=self.device)
+        # dead rows are zero or stale copies of live rows: both are safe for an upper bound
+        check(lib.qk_max_row_norm(ptr(self.vectors), self.rows_used, self.pitch, self.d, ptr(out), _stream()))
+        self.max_row_norm = float(out.item())
+        self._dirty = True
+
+    # ------------------------------------------------------------------ append / remove
+    def append(self, slots: torch.Tensor, x: torch.Tensor, x_ids: torch.Tensor) -> None:
+        """Append x[i] to list slot slots[i], input order preserved inside every list
+        (PartitionManager::add, partition_manager.cpp:245-258)."""
+        lib = _lib.load()
+        n = int(x.shape[0])
+        if n == 0:
+            return
+        nslots = self.slot_pid.size
+        slots32 = slots.to(torch.int32).contiguous()
+        counts_d = torch.zeros(nslots, dtype=torch.int64, device=self.device)
+        offsets_d = torch.zeros(nslots + 1, dtype=torch.int64, device=self.device)
+        order_d = torch.empty(n, dtype=torch.int64, device=self.device)
+        wsb = lib.qk_partition_workspace_bytes(n, nslots)
+        ws = torch.empty(wsb, dtype=torch.uint8, device=self.device)
+        check(lib.qk_partition_by_assignment(ptr(slots32), n, nslots, ptr(counts_d), ptr(offsets_d), ptr(order_d),
+                                             ptr(ws), wsb, _stream()))
+        counts = counts_d.cpu().numpy()
+        if int(counts.sum()) != n:
+            raise RuntimeError("List does not exist in add_entries")
+        for s in np.nonzero(counts)[0]:
+            need = int(self.list_size[s] + counts[s])
+            if need > self.list_cap[s]:
+                self._grow_list(int(s), need)
+        base = torch.from_numpy(self.list_row0 + self.list_size).to(self.device) - offsets_d[:-1]
+        dst_rows = torch.arange(n, dtype=torch.int64, device=self.device) + torch.repeat_interleave(base, counts_d)
+        x = x.contiguous()
+        check(lib.qk_scatter_rows(ptr(x), x.stride(0), ptr(x_ids.contiguous()), ptr(order_d), ptr(dst_rows), n, self.d,
+                                  ptr(self.vectors), self.pitch, ptr(self.ids), _stream()))
+        self.list_size = self.list_size + counts
+        out = torch.tensor([self.max_row_norm], dtype=torch.float32, device=self.device)
+        check(lib.qk_max_row_norm(ptr(x), n, x.stride(0), self.d, ptr(out), _stream()))
+        self.max_row_norm = float(out.item())
+        self._dirty = True
+
+    def live_rows(self) -> torch.Tensor:
+        """Arena rows of all live vectors, list slot by list slot."""
+        sz = torch.from_numpy(self.list_size).to(self.device)
+        r0 = torch.from_numpy(self.list_row0).to(self.device)
+        n = int(self.list_size.sum())
+        if n == 0:
+            return torch.zeros(0, dtype=torch.int64, device=self.device)
+        starts = torch.cumsum(sz, 0) - sz
+        return torch.arange(n, dtype=torch.int64, device=self.device) + torch.repeat_interleave(r0 - starts, sz)
+
+    def find_rows(self, ids: torch.Tensor) -> torch.Tensor:
+        """Arena row of each id (-1 if absent). The reference searches every list linearly
+        (dynamic_inverted_list.cpp:302-321, index_partition.cpp:129-145)."""
+        rows = self.live_rows()
+        ids = ids.to(self.device)
+        if rows.numel() == 0:
+            return torch.full_like(ids, -1)
+        live_ids = self.ids[rows]
+        sorted_ids, perm = torch.sort(live_ids)
+        pos = torch.searchsorted(sorted_ids, ids).clamp(max=sorted_ids.numel() - 1)
+        hit = sorted_ids[pos] == ids
+        return torch.where(hit, rows[perm[pos]], torch.full_like(ids, -1))
+
+    def remove_ids(self, ids: torch.Tensor) -> int:
+        """DynamicInvertedLists::remove_vectors (dynamic_inverted_list.cpp:137-149): every list drops its
+        members found in `ids`, filling each hole with the list's current last element."""
+        rows = self.find_rows(ids)
+        rows = rows[rows >= 0]
+        if rows.numel() == 0:
+            return 0
+        rows_h = np.sort(rows.cpu().numpy())
+        order = np.argsort(self.list_row0, kind="stable")
+        starts = self.list_row0[order]
+        li = order[np.searchsorted(starts, rows_h, side="right") - 1]
+        src_l, dst_l = [], []
+        # group by list and replay the reference's swap-with-last loop on positions only
+        cuts = np.nonzero(np.diff(li))[0] + 1
+        for grp_rows, s in zip(np.split(rows_h, cuts), li[np.concatenate([[0], cuts])]):
+            s = int(s)
+            r0, n = int(self.list_row0[s]), int(self.list_size[s])
+            pos = (grp_rows - r0).tolist()
+            removed = set(pos)
+            tail = n - 1
+            for p in pos:
+                if p > tail:
+                    break
+                while tail > p and tail in removed:
+                    tail -= 1
+                if tail > p:
+                    src_l.append(r0 + tail)
+                    dst_l.append(r0 + p)
+                tail -= 1
+            self.list_size[s] = n - len(pos)
+        if src_l:
+            src = torch.tensor(src_l, dtype=torch.int64, device=self.device)
+            dst = torch.tensor(dst_l, dtype=torch.int64, device=self.device)
+            self.vectors[dst] = self.vectors[src]
+            self.ids[dst] = self.ids[src]
+        self._dirty = True
+        return int(rows_h.size)
+
+    def get_list(self, pid: int, padded: bool = False):
+        s = self.pid_slot[int(pid)]
+        r0, n = int(self.list_row0[s]), int(self.list_size[s])
+        v = self.vectors[r0:r0 + n]
+        return (v if padded else v[:, : self.d]), self.ids[r0:r0 + n]
+
+    def set_list(self, pid: int, vecs: torch.Tensor, ids: torch.Tensor) -> None:
+        """Replace the content of a list (kmeans_refine_partitions hands back rebuilt partitions)."""
+        s = self.pid_slot[int(pid)]
+        n = int(vecs.shape[0])
+        if n > self.list_cap[s]:
+            self.list_size[s] = 0
+            self._grow_list(s, n + max(16, n // 8))
+        r0 = int(self.list_row0[s])
+        if n:
+            self.vectors[r0:r0 + n, : self.d] = vecs
+            if self.pitch > self.d:
+                self.vectors[r0:r0 + n, self.d:] = 0
+            self.ids[r0:r0 + n] = ids
+        self.list_size[s] = n
+        self._dirty = True
+
+    def compact(self) -> None:
+        """Rewrite the arena without dead space (lists keep their content order)."""
+        pids = self.partition_ids()
+        slots = np.array([self.pid_slot[int(p)] for p in pids], dtype=np.int64)
+        counts = self.list_size[slots]
+        rows = []
+        for s in slots:
+            r0, n = int(self.list_row0[s]), int(self.list_size[s])
+            rows.append(torch.arange(r0, r0 + n, dtype=torch.int64, device=self.device))
+        order = torch.cat(rows) if rows else torch.zeros(0, dtype=torch.int64, device=self.device)
+        old_v, old_i = self.vectors, self.ids
+        norm = self.max_row_norm
+        self.init_from_sorted(old_v, old_i, order, counts, pids)
+        self.max_row_norm = max(norm, self.max_row_norm)
+
+    # ------------------------------------------------------------------ device tables for the kernels
+    def tables(self):
+        """(QkStore struct, id_to_slot tensor); rebuilt lazily after any mutation."""
+        if not self._dirty and self._struct is not None:
+            return self._struct, self._id_to_slot
+        nslots = self.slot_pid.size
+        size = self.list_size
+        nseg = (size + QK_SEGMENT_ROWS - 1) // QK_SEGMENT_ROWS
+        seg0 = np.concatenate([[0], np.cumsum(nseg)[:-1]]) if nslots else np.zeros(0, np.int64)
+        S = int(nseg.sum())
+        seg_list = np.repeat(np.arange(nslots), nseg)
+        seg_idx = np.arange(S) - np.repeat(seg0, nseg)
+        seg_row0 = self.list_row0[seg_list] + seg_idx * QK_SEGMENT_ROWS
+        seg_rows = np.minimum(QK_SEGMENT_ROWS, size[seg_list] - seg_idx * QK_SEGMENT_ROWS)
+        dev = self.device
+        t = {
+            "list_seg0": torch.from_numpy(seg0.astype(np.int32)).to(dev),
+            "list_nseg": torch.from_numpy(nseg.astype(np.int32)).to(dev),
+            "seg_row0": torch.from_numpy(seg_row0.astype(np.int64)).to(dev),
+            "seg_rows": torch.from_numpy(seg_rows.astype(np.int32)).to(dev),
+        }
+        table_size = max(self.curr_list_id, 1)
+        id_to_slot = np.full(table_size, -1, dtype=np.int32)
+        for pid, s in self.pid_slot.items():
+            id_to_slot[pid] = s
+        self._id_to_slot = torch.from_numpy(id_to_slot).to(dev)
+        st = QkStore()
+        st.vectors = self.vectors.data_ptr()
+        st.ids = self.ids.data_ptr()
+        st.pitch = self.pitch
+        st.d = self.d
+        st.num_lists = nslots
+        st.list_seg0 = t["list_seg0"].data_ptr()
+        st.list_nseg = t["list_nseg"].data_ptr()
+        st.num_segments = S
+        st.max_list_segments = int(nseg.max()) if nslots else 0
+        st.seg_row0 = t["seg_row0"].data_ptr()
+        st.seg_rows = t["seg_rows"].data_ptr()
+        st.max_row_norm = float(self.max_row_norm)
+        self._tables = t
+        self._struct = st
+        self._dirty = False
+        return st, self._id_to_slot
