@@ -262,12 +262,48 @@ def index_lists(idx):
     return pids, lists, None, None
 
 
-def search_index_like(idx, q, k, nprobe, metric=None, recall_target=-1.0, initial_search_fraction=0.02,
-                      recompute_threshold=0.001, use_precomputed=True):
-    """QueryCoordinator::search restated on the CPU over the CONTENT of a quake_b200 index: coarse scan of
-    the parent's centroid list, then serial_scan of the probed lists. Returns torch (ids, distances)."""
-    metric = idx.metric if metric is None else metric
-    pids, lists, cv, ci = index_lists(idx)
+def read_index_dir(path):
+    """Parse an index directory in the reference's on-disk format (quake_index.cpp:170-267,
+    dynamic_inverted_list.cpp:338-419) -> (metric, pids, [(vecs, ids)], centroids | None, centroid ids | None)."""
+    import struct
+
+    def read_partitions(fn):
+        raw = open(fn, "rb").read()
+        magic, version, _nl, code_size, nparts = struct.unpack_from("<IIQQQ", raw, 0)
+        assert magic == 0x44494E4C and version == 3
+        d = code_size // 4
+        offs = np.frombuffer(raw, np.uint64, nparts + 1, 32)
+        pids = np.frombuffer(raw, np.uint64, nparts, 32 + 8 * (nparts + 1)).astype(np.int64)
+        start = 32 + 8 * (nparts + 1) + 8 * nparts
+        lists = []
+        for i in range(nparts):
+            nv = int(offs[i + 1] - offs[i]) // (code_size + 8)
+            o = start + int(offs[i])
+            v = np.frombuffer(raw, np.float32, nv * d, o).reshape(nv, d).copy()
+            ids = np.frombuffer(raw, np.int64, nv, o + nv * code_size).copy()
+            lists.append((v, ids))
+        return pids, lists
+
+    metric = 1
+    for line in open(os.path.join(path, "metadata.txt")):
+        if line.startswith("metric="):
+            metric = int(line.strip().split("=")[1])
+    pids, lists = read_partitions(os.path.join(path, "partitions"))
+    order = np.argsort(pids)
+    pids, lists = pids[order], [lists[i] for i in order]
+    cv = ci = None
+    pp = os.path.join(path, "parent", "partitions")
+    if os.path.exists(pp):
+        _, pl = read_partitions(pp)
+        cv, ci = pl[0]
+    return metric, pids, lists, cv, ci
+
+
+def search_lists(pids, lists, cv, ci, q, k, nprobe, metric, recall_target=-1.0, initial_search_fraction=0.02,
+                 recompute_threshold=0.001, use_precomputed=True, blas=None, return_probe=False):
+    """QueryCoordinator::search (query_coordinator.cpp:612-657) restated over explicit lists: coarse scan of
+    the centroid list (cv, ci), then serial_scan of the probed lists. `blas` selects the coarse-scan
+    arithmetic (None = the reference's rule: sgemm form for >= 20 queries). Returns torch (ids, distances)."""
     qn = _f32(_np(q))
     Q = qn.shape[0]
     if cv is None:
@@ -277,7 +313,7 @@ def search_index_like(idx, q, k, nprobe, metric=None, recall_target=-1.0, initia
     nlist = len(lists)
     use_aps = recall_target > 0
     kp = max(int(nlist * initial_search_fraction), 1) if use_aps else min(nprobe, nlist)
-    cid, _ = coarse_topk(qn, cv, ci, kp, metric)
+    cid, _ = coarse_topk(qn, cv, ci, kp, metric, blas=blas)
     slot_of = {int(p): s for s, p in enumerate(pids)}
     probe = np.vectorize(lambda p: slot_of.get(int(p), -1))(cid).astype(np.int64)
     cents = None
@@ -286,4 +322,13 @@ def search_index_like(idx, q, k, nprobe, metric=None, recall_target=-1.0, initia
         rows = np.vectorize(lambda p: row_of[int(p)])(cid)
         cents = cv[rows]
     oi, od, sc = serial_scan(qn, lists, probe, k, metric, recall_target, recompute_threshold, use_precomputed, cents)
+    if return_probe:
+        return torch.from_numpy(oi), torch.from_numpy(od), cid, sc
     return torch.from_numpy(oi), torch.from_numpy(od)
+
+
+def search_index_like(idx, q, k, nprobe, metric=None, **kw):
+    """search_lists over the CONTENT of a quake_b200.QuakeIndex (same centroids + list membership)."""
+    metric = idx.metric if metric is None else metric
+    pids, lists, cv, ci = index_lists(idx)
+    return search_lists(pids, lists, cv, ci, q, k, nprobe, metric, **kw)

@@ -31,6 +31,13 @@ int cuda_fail(cudaError_t e, const char* what);
 
 int sm_count();
 
+// qk_scan_partitions with one more knob: rank_squared != 0 orders l2 results by the squared distance
+// (used by the k-means assign, where faiss's Top1 handler compares squared distances).
+int scan_partitions_impl(const qk_store_t* st, const float* queries, int64_t Q, int64_t q_pitch,
+                         const int32_t* probe_lists, int nprobe, int metric, int k, int64_t* out_ids, float* out_dist,
+                         int64_t* out_rows, void* workspace, size_t workspace_bytes, int32_t* stats, void* stream,
+                         int rank_squared);
+
 // ---------------------------------------------------------------------------------------------
 // order-preserving float <-> uint32 keys (ascending float order == ascending unsigned order)
 // ---------------------------------------------------------------------------------------------

@@ -544,8 +544,8 @@ extern "C" int qk_kmeans_assign(const float* points, int64_t n, int64_t point_pi
     st.max_row_norm = h_norm;
     for (int64_t b = 0; b < n; b += B) {
         const int64_t cnt = (n - b) < B ? (n - b) : B;
-        rc = qk_scan_partitions(&st, points + b * point_pitch, cnt, point_pitch, probe, 1, metric, 1, ids, dist, rows,
-                                ws + L.off_scan, L.scan_bytes, nullptr, stream);
+        rc = scan_partitions_impl(&st, points + b * point_pitch, cnt, point_pitch, probe, 1, metric, 1, ids, dist, rows,
+                                  ws + L.off_scan, L.scan_bytes, nullptr, stream, 1);
         if (rc) return rc;
         assign_finish_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, stream>>>(rows, dist, cnt, out_assign + b,
                                                                                 out_distances ? out_distances + b : nullptr);

@@ -310,6 +310,7 @@ __device__ __forceinline__ void select_tile(uint64_t* top_g, int kc, const uint3
     }
     uint64_t thr = warp_element<E>(a, kc - 1);
     const uint64_t thr_in = thr;
+    bool changed = false;  // warp-uniform
 #pragma unroll 1
     for (int j = 0; j < SCAN_TV / 32; ++j) {
         const int r = j * 32 + lane;
@@ -324,16 +325,17 @@ __device__ __forceinline__ void select_tile(uint64_t* top_g, int kc, const uint3
             if (c < thr) {
                 warp_insert<E>(a, c, lane);
                 thr = warp_element<E>(a, kc - 1);
+                changed = true;
             }
         }
     }
-    if (thr != thr_in) {
+    if (changed) {
 #pragma unroll
         for (int e = 0; e < E; ++e) {
             int i = lane * E + e;
             if (i < kc) top_g[i] = a[e];
         }
-        if (thr != COMP_MAX) {
+        if (thr != thr_in && thr != COMP_MAX) {
             const uint32_t tk = (uint32_t)(thr >> 32);
             if (tk < gthr_q) {
                 uint32_t old = 0;
@@ -620,6 +622,7 @@ struct MergeArgs {
     float* out_dist;
     int64_t* out_rows;
     int force_rescan;
+    int rank_squared;  // l2 only: order by the squared distance (k-means assign: faiss Top1 on squared l2)
 };
 
 template <bool kIP>
@@ -679,7 +682,8 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_refine_kernel(const Merge
             if (i < nc) {
                 const uint32_t row = (uint32_t)sbuf[i];
                 const float dist = ref_pair_distance<kIP>(qs, a.vecs + (int64_t)row * a.pitch, a.d);
-                const uint32_t dk = f2key(kIP ? -dist : dist);
+                // order by the value the reference orders by: sqrt'ed for l2 (list_scanning.h:260)
+                const uint32_t dk = f2key(kIP ? -dist : (a.rank_squared ? dist : __fsqrt_rn(dist)));
                 rkey[i] = ((uint64_t)dk << 32) | (uint32_t)i;
                 rid[i] = a.ids ? a.ids[row] : (int64_t)row;
                 rrow[i] = row;
@@ -699,7 +703,7 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_refine_kernel(const Merge
             if (tid == 0) {
                 const int kk = a.k < nc ? a.k : nc;
                 const float a_score = key2f((uint32_t)(sbuf[a.kc - 1] >> 32));  // filter score of the kc-th candidate
-                const float rk = key2f((uint32_t)(rkey[kk - 1] >> 32));         // exact k-th (l2: sqr dist, ip: -ip)
+                const float rk = key2f((uint32_t)(rkey[kk - 1] >> 32));         // exact k-th (l2: distance, ip: -ip)
                 const double qn = s_qn, qnorm = sqrt(qn), U = (double)a.max_row_norm;
                 const double eps = 5.960464477539063e-08;  // 2^-24
                 const double gam = (a.d + 8) * eps;
@@ -707,8 +711,12 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_refine_kernel(const Merge
                 bool ok;
                 if (!kIP) {
                     const double e1 = gam * (U * U + 2.0 * qnorm * U) + 4.0 * eps * fabs((double)a_score);
+                    // lb bounds the reference-order SQUARED distance of every rejected row from below; the
+                    // reference compares sqrt'ed values, and sqrt_rn is monotone, so a rejected row cannot
+                    // tie or beat the k-th as soon as sqrt_rn(round_down(lb)) is strictly above it.
                     const double lb = (qn * (1.0 - gam) + (double)a_score - e1) * (1.0 - e2);
-                    ok = lb > (double)rk;
+                    const float lbf = __double2float_rd(lb);
+                    ok = a.rank_squared ? (lb > (double)rk) : (lbf > 0.f && __fsqrt_rn(lbf) > rk);
                 } else {
                     // scores are -<q,v>: any rejected v has ip <= -a_score + err; need that below the k-th exact ip
                     const double err = (gam + e2) * qnorm * U + 4.0 * eps * fabs((double)a_score);
@@ -735,7 +743,7 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_refine_kernel(const Merge
             const uint64_t rk = rkey[i];
             const uint32_t slot = (uint32_t)rk;
             const float v = key2f((uint32_t)(rk >> 32));
-            dist = kIP ? -v : __fsqrt_rn(v);
+            dist = kIP ? -v : (a.rank_squared ? __fsqrt_rn(v) : v);
             id = rid[slot];
             row = rrow[slot];
         }
@@ -760,7 +768,8 @@ __global__ void __launch_bounds__(256) exact_rescan_kernel(const MergeArgs a, co
     int64_t* rid = reinterpret_cast<int64_t*>(rkey + kp);                       // [kp]
     uint32_t* rrow = reinterpret_cast<uint32_t*>(rid + kp);                     // [kp]
     __shared__ unsigned hist[256];
-    __shared__ unsigned s_prefix, s_need, s_less, s_take_eq;
+    __shared__ unsigned s_prefix, s_need, s_less, s_eq_total;
+    __shared__ unsigned long long s_prefix64;
     __shared__ int s_scan[256];
     __shared__ int s_base_lt, s_base_eq;
     const int tid = threadIdx.x;
@@ -778,7 +787,11 @@ __global__ void __launch_bounds__(256) exact_rescan_kernel(const MergeArgs a, co
 
     auto dist_key = [&](int64_t row) {
         const float dist = ref_pair_distance<kIP>(qs, a.vecs + row * a.pitch, a.d);
-        return f2key(kIP ? -dist : dist);
+        return f2key(kIP ? -dist : (a.rank_squared ? dist : __fsqrt_rn(dist)));
+    };
+    auto id_key = [&](int64_t row) {  // ascending signed id order as unsigned
+        const int64_t id = a.ids ? a.ids[row] : row;
+        return (uint64_t)id ^ 0x8000000000000000ull;
     };
 
     if (kk > 0) {
@@ -809,12 +822,53 @@ __global__ void __launch_bounds__(256) exact_rescan_kernel(const MergeArgs a, co
                 s_prefix = prefix | ((unsigned)b << (8 * pass));
                 s_need = need - cum;
                 s_less += cum;
+                s_eq_total = b < 256 ? hist[b] : 0u;
             }
             __syncthreads();
         }
         const uint32_t T = s_prefix;
         const unsigned n_less = s_less;        // keys strictly below T
-        const unsigned take_eq = s_need;       // how many keys equal to T to take (scan order)
+        const unsigned take_eq = s_need;       // how many keys equal to T to take
+        const unsigned eq_total = s_eq_total;  // how many keys equal T
+        __syncthreads();
+        // A distance tie that straddles the k-th boundary is resolved by ascending id (the order the
+        // oracle fixes for the reference's distance-only comparator): radix-select the take_eq-th
+        // smallest id among the rows whose key equals T.
+        uint64_t id_thr = ~0ull;
+        if (eq_total > take_eq) {
+            if (tid == 0) { s_prefix64 = 0ull; s_need = take_eq; }
+            __syncthreads();
+            for (int pass = 7; pass >= 0; --pass) {
+                hist[tid] = 0;
+                __syncthreads();
+                const uint64_t prefix = s_prefix64;
+                for (int j = 0; j < a.P; ++j) {
+                    const int seg = a.pair_seg[q * a.P + j];
+                    if (seg < 0) continue;
+                    const int64_t r0 = a.seg_row0[seg];
+                    const int n = seg_rows[seg];
+                    for (int r = tid; r < n; r += blockDim.x) {
+                        if (dist_key(r0 + r) != T) continue;
+                        const uint64_t ik = id_key(r0 + r);
+                        const bool match = (pass == 7) || ((ik >> (8 * (pass + 1))) == (prefix >> (8 * (pass + 1))));
+                        if (match) atomicAdd(&hist[(unsigned)(ik >> (8 * pass)) & 255u], 1u);
+                    }
+                }
+                __syncthreads();
+                if (tid == 0) {
+                    unsigned need = s_need, cum = 0;
+                    int b = 0;
+                    for (; b < 256; ++b) {
+                        if (cum + hist[b] >= need) break;
+                        cum += hist[b];
+                    }
+                    s_prefix64 = prefix | ((unsigned long long)(b & 255) << (8 * pass));
+                    s_need = need - cum;
+                }
+                __syncthreads();
+            }
+            id_thr = s_prefix64;
+        }
         if (tid == 0) { s_base_lt = 0; s_base_eq = 0; }
         __syncthreads();
         // deterministic ordered collection
@@ -830,7 +884,7 @@ __global__ void __launch_bounds__(256) exact_rescan_kernel(const MergeArgs a, co
                 if (r < n) {
                     dk = dist_key(r0 + r);
                     lt = dk < T;
-                    eq = dk == T;
+                    eq = (dk == T) && (id_key(r0 + r) <= id_thr);
                 }
                 // block exclusive scan of (lt, eq) packed
                 int v = (lt ? 1 : 0) | (eq ? (1 << 16) : 0);
@@ -881,7 +935,7 @@ __global__ void __launch_bounds__(256) exact_rescan_kernel(const MergeArgs a, co
             const uint64_t rk = rkey[i];
             const uint32_t slot = (uint32_t)rk;
             const float v = key2f((uint32_t)(rk >> 32));
-            dist = kIP ? -v : __fsqrt_rn(v);
+            dist = kIP ? -v : (a.rank_squared ? __fsqrt_rn(v) : v);
             id = rid[slot];
             row = rrow[slot];
         }
@@ -929,6 +983,14 @@ extern "C" int qk_scan_partitions(const qk_store_t* st, const float* queries, in
                                   const int32_t* probe_lists, int nprobe, int metric, int k, int64_t* out_ids,
                                   float* out_dist, int64_t* out_rows, void* workspace, size_t workspace_bytes,
                                   int32_t* stats, void* stream_v) {
+    return qk::scan_partitions_impl(st, queries, Q, q_pitch, probe_lists, nprobe, metric, k, out_ids, out_dist, out_rows,
+                                    workspace, workspace_bytes, stats, stream_v, 0);
+}
+
+int qk::scan_partitions_impl(const qk_store_t* st, const float* queries, int64_t Q, int64_t q_pitch,
+                             const int32_t* probe_lists, int nprobe, int metric, int k, int64_t* out_ids,
+                             float* out_dist, int64_t* out_rows, void* workspace, size_t workspace_bytes,
+                             int32_t* stats, void* stream_v, int rank_squared) {
     cudaStream_t stream = (cudaStream_t)stream_v;
     QK_REQUIRE(st && queries && probe_lists && out_ids && out_dist, "null argument");
     QK_REQUIRE(metric == QK_METRIC_L2 || metric == QK_METRIC_INNER_PRODUCT, "metric %d not supported", metric);
@@ -1011,6 +1073,7 @@ extern "C" int qk_scan_partitions(const qk_store_t* st, const float* queries, in
     ma.max_row_norm = st->max_row_norm;
     ma.out_ids = out_ids; ma.out_dist = out_dist; ma.out_rows = out_rows;
     ma.force_rescan = g_force_rescan;
+    ma.rank_squared = rank_squared;
     {
         int kcp = 1;
         while (kcp < p.kc) kcp <<= 1;
