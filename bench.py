@@ -1,0 +1,417 @@
+#!/usr/bin/env python
+"""bench.py -- the Quake search hot path on B200 (BASELINE.json metric: QPS, k=10, d=128).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo (CUDA kernels behind the C ABI)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's own CPU search, same workload
+
+Workload at every N: BASELINE.json configs[1] -- 1M x 128 float32 (torch.randn, seed 1234), nlist=4096,
+Q=1024 queries (seed 4321), k=10, l2, nprobe=64 (the headline nprobe of SURVEY.md 8d). A "step" is one
+search of the 1024-query batch: coarse centroid scan -> partition scan -> top-k. Multi-GPU (N>1): one
+replica of the index per rank and an independent 1024-query batch per rank ("replicas only" for this
+config; weak scaling), no data-path collective.
+
+value   = queries/s with the queries already resident in HBM (CUDA events, max over ranks)
+e2e     = queries/s through QuakeIndex.search with pinned HOST query tensors in and host results out
+roofline= the partition-scan filter kernel: algorithmic bytes (every distinct probed list read once,
+          n_p * d * 4 B) / its CUDA-event duration, against MEASURED_PEAKS.json hbm_gbs
+cpu_baseline = the compiled reference (oracle/_ref) searching the same index on the host cores
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = {"name": "C2: 1M x 128 f32 randn, nlist=4096, Q=1024, k=10, l2, nprobe=64",
+            "N": 1_000_000, "d": 128, "nlist": 4096, "Q": 1024, "k": 10, "nprobe": 64, "metric": "l2", "niter": 5}
+METRIC = "search_qps_k10_d128"
+UNIT = "queries/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--nprobe", type=int, default=WORKLOAD["nprobe"])
+    ap.add_argument("--n", type=int, default=WORKLOAD["N"], help="override N (debug only; the line says so)")
+    ap.add_argument("--nlist", type=int, default=WORKLOAD["nlist"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(W):
+    tag = "C2" if (W["N"], W["nlist"]) == (1_000_000, 4096) else "reduced (debug)"
+    return (f"{tag}: {W['N']} x {W['d']} f32 randn, nlist={W['nlist']}, Q={W['Q']}, k={W['k']}, {W['metric']}, "
+            f"nprobe={W['nprobe']}")
+
+
+def make_data(n, d, q, rank=0):
+    import torch
+    g = torch.Generator().manual_seed(1234)
+    x = torch.randn(n, d, generator=g)
+    g2 = torch.Generator().manual_seed(4321 + rank)
+    xq = torch.randn(q, d, generator=g2)
+    return x, xq
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [t.strip() for t in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for nme, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------ reference (CPU)
+def import_reference():
+    p = os.path.join(ROOT, "oracle", "_ref")
+    if p not in sys.path:
+        sys.path.insert(0, p)
+    import quake_ref  # the compiled, unmodified reference (built by oracle/build_ref.sh)
+    return quake_ref
+
+
+def time_reference_search(ref_idx, quake_ref, xq, k, nprobe, cores, budget_s, steps=None, warmup=1):
+    """Times the reference's CPU search (num_workers=0) in its two deterministic modes and returns the
+    faster: serial_scan parallel over queries (num_threads=cores) and batched_serial_scan."""
+    import torch
+    torch.set_num_threads(cores)
+    best = None
+    for mode, batched in (("serial_scan", False), ("batched_serial_scan", True)):
+        sp = quake_ref.SearchParams()
+        sp.k, sp.nprobe, sp.batched_scan, sp.num_threads = k, nprobe, batched, cores
+        t0 = time.perf_counter()
+        ref_idx.search(xq, sp)  # warm-up + cost probe
+        one = time.perf_counter() - t0
+        reps = steps if steps is not None else max(1, min(10, int(budget_s / 2 / max(one, 1e-3))))
+        for _ in range(max(0, warmup - 1)):
+            ref_idx.search(xq, sp)
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            ref_idx.search(xq, sp)
+        dt = (time.perf_counter() - t0) / reps
+        qps = xq.shape[0] / dt
+        if best is None or qps > best["value"]:
+            best = {"value": qps, "mode": mode, "ms_per_step": dt * 1e3, "reps": reps}
+    return best
+
+
+def run_reference_arm(args):
+    """--impl reference: the reference's own CPU implementation of the path, all host threads, same config."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import torch
+    W = dict(WORKLOAD, N=args.n, nlist=args.nlist, nprobe=args.nprobe)
+    W["name"] = workload_name(W)
+    cores = host_cores()
+    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    line = {"impl": "reference", "metric": METRIC, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic"}
+    try:
+        quake_ref = import_reference()
+        kind = "reference"
+    except Exception as e:  # the compiled reference did not travel / load: fall back to the oracle port
+        quake_ref, kind, why = None, "port", repr(e)
+    x, xq = make_data(W["N"], W["d"], W["Q"])
+    ids = torch.arange(W["N"], dtype=torch.int64)
+    if kind == "reference":
+        torch.set_num_threads(cores)
+        bp = quake_ref.IndexBuildParams()
+        bp.nlist, bp.metric, bp.niter = W["nlist"], W["metric"], W["niter"]
+        idx = quake_ref.QuakeIndex()
+        t0 = time.perf_counter()
+        idx.build(x, ids, bp)
+        build_s = time.perf_counter() - t0
+        # bound the run: probe one step, shrink the per-step sample if K+W steps would not end in ~3 min
+        sp = quake_ref.SearchParams()
+        sp.k, sp.nprobe, sp.num_threads = W["k"], W["nprobe"], cores
+        t0 = time.perf_counter(); idx.search(xq, sp); one = time.perf_counter() - t0
+        total_steps = args.steps + args.warmup
+        qn = W["Q"]
+        while qn > 32 and one * (qn / W["Q"]) * total_steps * 2 > 180:
+            qn //= 2
+        best = time_reference_search(idx, quake_ref, xq[:qn], W["k"], W["nprobe"], cores, 0, steps=args.steps,
+                                     warmup=max(args.warmup, 1))
+        sample = f"{qn} of {W['Q']} queries per step, {best['mode']}, num_threads={cores}, index built by the reference in {build_s:.1f}s"
+    else:
+        from oracle import oracle as orc
+        import numpy as np
+        # scalar port on a small index slice (bounded): 64 queries, lists from a 100k subset
+        n_small = min(W["N"], 100_000)
+        xs = x[:n_small].numpy()
+        cents = xs[: max(W["nlist"] // 10, 1)]
+        a = orc.assign(xs, cents, W["metric"])
+        lists = [(xs[a == c], np.nonzero(a == c)[0].astype(np.int64)) for c in range(cents.shape[0])]
+        qn = 64
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            orc.search_lists(np.arange(len(lists)), lists, cents, np.arange(len(lists)), xq[:qn].numpy(), W["k"],
+                             min(W["nprobe"], len(lists)), W["metric"])
+        dt = (time.perf_counter() - t0) / args.steps
+        best = {"value": qn / dt, "ms_per_step": dt * 1e3, "mode": "oracle port"}
+        cores = 1
+        sample = f"oracle port (compiled reference unavailable: {why}); {qn} queries, {n_small} vectors"
+    line.update({"value": best["value"], "ms_per_step": best["ms_per_step"],
+                 "config": {"workload": W["name"], "N": W["N"], "nlist": W["nlist"], "nprobe": W["nprobe"],
+                            "Q": W["Q"], "k": W["k"], "metric": W["metric"]},
+                 "cpu_baseline": {"value": best["value"], "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+                 "e2e": {"value": best["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                 "gpu_launches": 0})
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------ this repo (GPU)
+def run_b200(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; quake_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    import quake_b200 as qb
+    from quake_b200 import _lib
+    import ctypes as C
+    lib = _lib.load()
+
+    W = dict(WORKLOAD, N=args.n, nlist=args.nlist, nprobe=args.nprobe)
+    W["name"] = workload_name(W)
+    x, xq_h = make_data(W["N"], W["d"], W["Q"], rank)
+    ids = torch.arange(W["N"], dtype=torch.int64)
+    bp = qb.IndexBuildParams()
+    bp.nlist, bp.metric, bp.niter = W["nlist"], W["metric"], W["niter"]
+    idx = qb.QuakeIndex()
+    t0 = time.perf_counter()
+    idx.build(x, ids, bp)
+    torch.cuda.synchronize()
+    build_s = time.perf_counter() - t0
+
+    sp = qb.SearchParams()
+    sp.k, sp.nprobe = W["k"], W["nprobe"]
+    xq_pinned = xq_h.pin_memory()
+    xq_d = xq_h.to(dev)
+
+    # ---- parity gate (oracle = checker only) + recall
+    parity = {}
+    if rank == 0:
+        from oracle import oracle as orc
+        res = idx.search(xq_h[:16], sp)
+        oi, od = orc.search_index_like(idx, xq_h[:16], k=W["k"], nprobe=W["nprobe"])
+        parity["ids_equal_oracle_16q"] = bool(torch.equal(res.ids, oi))
+        parity["dist_bit_equal_16q"] = bool(torch.equal(res.distances, od))
+        full = idx.search(xq_h, sp)
+        xd = x.to(dev)
+        gt = torch.cdist(xq_d, xd).topk(W["k"], largest=False).indices.cpu()
+        hit = sum(len(set(a.tolist()) & set(b.tolist())) for a, b in zip(full.ids, gt))
+        parity["recall_at_k_vs_bruteforce"] = hit / float(gt.numel())
+        del xd, gt
+
+    # ---- algorithmic bytes of the partition-scan filter kernel for this batch (grouped mode: every
+    #      distinct probed list read once)
+    psp = qb.SearchParams(); psp.k = min(W["nprobe"], idx.nlist()); psp.batched_scan = True
+    p_ids, _, _ = idx.parent._search_device(xq_d, psp)
+    uniq = torch.unique(p_ids[p_ids >= 0]).cpu().numpy()
+    sizes = np.array([idx.store.size_of(int(p)) for p in uniq], dtype=np.int64)
+    alg_bytes = int(sizes.sum()) * W["d"] * 4
+    pair_bytes = int(sum(idx.store.size_of(int(p)) for p in p_ids.cpu().numpy().reshape(-1) if p >= 0)) * W["d"] * 4
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing (value)
+    for _ in range(args.warmup):
+        idx._search_device(xq_d, sp)
+    lib.qk_profile_begin(4 * args.steps + 8)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    cuprof = os.environ.get("QK_BENCH_CUPROF") == "1"  # ncu --profile-from-start off: capture the timed steps only
+    if cuprof:
+        torch.cuda.cudart().cudaProfilerStart()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        out = idx._search_device(xq_d, sp)
+    e1.record()
+    barrier()
+    if cuprof:
+        torch.cuda.cudart().cudaProfilerStop()
+    clocks = sampler.stop()
+    dev_ms = e0.elapsed_time(e1) / args.steps
+    # filter-kernel records: 2 scan calls per step (coarse scan of the centroid list, then the partition scan)
+    scan_ms = []
+    for i in range(lib.qk_profile_count()):
+        ms, qn, npb, kk = C.c_float(), C.c_int64(), C.c_int32(), C.c_int32()
+        lib.qk_profile_read(i, C.byref(ms), C.byref(qn), C.byref(npb), C.byref(kk))
+        if npb.value == W["nprobe"] and kk.value == W["k"]:
+            scan_ms.append(ms.value)
+    lib.qk_profile_end()
+    scan_ms_avg = sum(scan_ms) / max(len(scan_ms), 1)
+
+    # ---- end to end through the public API with host tensors (e2e)
+    for _ in range(max(args.warmup, 3)):
+        idx.search(xq_pinned, sp)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        r = idx.search(xq_pinned, sp)
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+    h2d = xq_pinned.numel() * 4
+    d2h = r.ids.numel() * 8 + r.distances.numel() * 4
+
+    # ---- max over ranks
+    t = torch.tensor([dev_ms, e2e_ms, scan_ms_avg], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms, scan_ms_avg = [float(v) for v in t.cpu()]
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+        achieved = alg_bytes / (scan_ms_avg * 1e-3) / 1e9 if scan_ms_avg > 0 else 0.0
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "scan_kernel_traffic.json"))).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+        line = {
+            "metric": METRIC, "value": world * W["Q"] / (dev_ms * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": W["name"], "N": W["N"], "nlist": W["nlist"], "nprobe": W["nprobe"], "Q": W["Q"],
+                       "k": W["k"], "metric": W["metric"], "parallelism": f"replicas x{world}" if world > 1 else "1 gpu",
+                       "l2_policy": "index (512 MB of lists) larger than L2; no flush between steps",
+                       "build_s": round(build_s, 2), "parity": parity},
+            "roofline": {"bound": "hbm", "kernel": "scan_kernel (partition-scan filter)", "achieved": achieved,
+                         "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None, "traffic": traffic,
+                         "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
+                         "per_query_list_bytes_per_launch": pair_bytes, "kernel_ms": scan_ms_avg,
+                         "kernel_share_of_step": scan_ms_avg / dev_ms if dev_ms else None},
+            "e2e": {"value": world * W["Q"] / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": 14 * args.steps,
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(idx, xq_h, W)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def cpu_baseline(idx, xq_h, W):
+    """The compiled reference (oracle/_ref) searching THE SAME index (saved by us in the reference's format,
+    loaded by the reference) on the host cores; bounded sample."""
+    cores = host_cores()
+    try:
+        quake_ref = import_reference()
+        with tempfile.TemporaryDirectory() as tmp:
+            p = os.path.join(tmp, "idx")
+            idx.save(p)
+            ref = quake_ref.QuakeIndex()
+            ref.load(p, 0)
+        best = time_reference_search(ref, quake_ref, xq_h, W["k"], W["nprobe"], cores, budget_s=20.0)
+        return {"value": best["value"], "unit": UNIT, "cores": cores, "kind": "reference",
+                "sample": f"all {W['Q']} queries x {best['reps']} reps, same index (loaded from our save), "
+                          f"{best['mode']}, num_threads={cores}"}
+    except Exception as e:
+        from oracle import oracle as orc
+        qn = 16
+        t0 = time.perf_counter()
+        orc.search_index_like(idx, xq_h[:qn], k=W["k"], nprobe=W["nprobe"])
+        dt = time.perf_counter() - t0
+        return {"value": qn / dt, "unit": UNIT, "cores": 1, "kind": "port",
+                "sample": f"{qn} queries, scalar oracle port (compiled reference unavailable: {e!r}); includes list export"}
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    return run_b200(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -57,6 +57,7 @@ typedef struct qk_store {
     const int64_t* seg_row0;     /* [num_segments] first arena row of the segment                    */
     const int32_t* seg_rows;     /* [num_segments] rows in the segment (1..QK_SEGMENT_ROWS)          */
     float          max_row_norm; /* upper bound on the L2 norm of any stored row (see qk_max_row_norm)*/
+    const float*   row_norms;    /* [rows] squared L2 norm of every row (see qk_row_sqnorms); l2 only */
 } qk_store_t;
 
 #define QK_SEGMENT_ROWS 4096
@@ -88,6 +89,14 @@ int qk_scan_partitions(const qk_store_t* store,
                        void* workspace, size_t workspace_bytes,
                        int32_t* stats, void* stream);
 
+/* Measurement aid (bench.py): while profiling is on, every qk_scan_partitions call records a CUDA-event
+ * pair on its stream right around the filter ("scan") kernel -- the dominant kernel of the path. Read the
+ * records after synchronising. Not thread-safe; off by default. */
+int qk_profile_begin(int max_records);
+int qk_profile_count(void);
+int qk_profile_read(int index, float* ms, int64_t* queries, int* nprobe, int* k);
+int qk_profile_end(void);
+
 /* Map the ids returned by the coarse (parent) scan -- partition ids -- to list slots of the child
  * store. id_to_slot is a dense device table of `table_size` entries; ids outside it or mapped to
  * a negative value become -1. Replaces the unordered_map lookup partitions_.at(pid)
@@ -98,6 +107,10 @@ int qk_map_ids_to_slots(const int64_t* ids, int64_t n, const int32_t* id_to_slot
 /* Upper bound on the row norms of [n x pitch] rows, written to a device float (max-reduced into
  * *out, which the caller initialises, e.g. to 0). Used for the filter/refine safety bound. */
 int qk_max_row_norm(const float* rows, int64_t n, int64_t pitch, int d, float* out, void* stream);
+
+/* out[i] = ||rows[i]||^2 (fp32): the per-row term of the l2 filter score ||v||^2 - 2<q,v>. The store keeps it
+ * beside the vectors (4 B per row) so that the scan kernel streams each vector exactly once. */
+int qk_row_sqnorms(const float* rows, int64_t n, int64_t pitch, int d, float* out, void* stream);
 
 /* Merge S partial results per query (multi-GPU shards, or APS rounds) into one top-k.
  * Replaces the global TopkBuffer::batch_add merge of per-core partial results

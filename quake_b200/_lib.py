@@ -39,6 +39,7 @@ class QkStore(C.Structure):
         ("seg_row0", vp),
         ("seg_rows", vp),
         ("max_row_norm", C.c_float),
+        ("row_norms", vp),
     ]
 
 
@@ -52,8 +53,13 @@ PROTOTYPES = {
         C.c_int,
         [C.POINTER(QkStore), vp, C.c_int64, C.c_int64, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, C.c_size_t, vp, vp],
     ),
+    "qk_profile_begin": (C.c_int, [C.c_int]),
+    "qk_profile_count": (C.c_int, []),
+    "qk_profile_read": (C.c_int, [C.c_int, c_f32p, c_i64p, c_i32p, c_i32p]),
+    "qk_profile_end": (C.c_int, []),
     "qk_map_ids_to_slots": (C.c_int, [vp, C.c_int64, vp, C.c_int64, vp, vp]),
     "qk_max_row_norm": (C.c_int, [vp, C.c_int64, C.c_int64, C.c_int, vp, vp]),
+    "qk_row_sqnorms": (C.c_int, [vp, C.c_int64, C.c_int64, C.c_int, vp, vp]),
     "qk_merge_topk": (C.c_int, [vp, vp, C.c_int, C.c_int64, C.c_int, C.c_int, vp, vp, vp]),
     "qk_kmeans_assign_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int64, C.c_int]),
     "qk_kmeans_assign": (

@@ -48,6 +48,10 @@ __host__ __device__ __forceinline__ uint32_t f2key(float f) {
     uint32_t u;
     memcpy(&u, &f, 4);
 #endif
+    // NaN (either sign) never wins a comparison in the reference (faiss result handlers use strict
+    // comparisons; a NaN centroid comes out of kmeans_refine_partitions for an emptied cluster,
+    // clustering.cpp:122-124): it maps to the "invalid" key.
+    if ((u & 0x7fffffffu) > 0x7f800000u) return 0xffffffffu;
     return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
 __host__ __device__ __forceinline__ float key2f(uint32_t k) {

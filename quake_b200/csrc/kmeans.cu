@@ -210,6 +210,19 @@ __global__ void normalize_rows_kernel(float* __restrict__ rows, int64_t n, int64
     for (int j = lane; j < d; j += 32) r[j] = __fdiv_rn(r[j], nrm);
 }
 
+__global__ void row_sqnorms_kernel(const float* __restrict__ rows, int64_t n, int64_t pitch, int d,
+                                   float* __restrict__ out) {
+    const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= n) return;
+    const float* r = rows + row * pitch;
+    float s = 0.f;
+    for (int j = lane; j < d; j += 32) s = fmaf(r[j], r[j], s);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) out[row] = s;
+}
+
 __global__ void max_row_norm_kernel(const float* __restrict__ rows, int64_t n, int64_t pitch, int d,
                                     float* __restrict__ out) {
     const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -399,6 +412,16 @@ extern "C" int qk_normalize_rows(float* rows, int64_t n, int64_t pitch, int d, v
     return QK_OK;
 }
 
+extern "C" int qk_row_sqnorms(const float* rows, int64_t n, int64_t pitch, int d, float* out, void* stream_v) {
+    cudaStream_t stream = (cudaStream_t)stream_v;
+    QK_REQUIRE(rows && out && d > 0, "bad argument");
+    if (n == 0) return QK_OK;
+    int64_t threads = n * 32;
+    row_sqnorms_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(rows, n, pitch, d, out);
+    QK_CUDA(cudaGetLastError());
+    return QK_OK;
+}
+
 extern "C" int qk_max_row_norm(const float* rows, int64_t n, int64_t pitch, int d, float* out, void* stream_v) {
     cudaStream_t stream = (cudaStream_t)stream_v;
     QK_REQUIRE(rows && out && d > 0, "bad argument");
@@ -443,7 +466,7 @@ extern "C" int qk_merge_topk(const float* part_distances, const int64_t* part_id
 namespace {
 struct AssignLayout {
     size_t off_seg_row0, off_seg_rows, off_list_seg0, off_list_nseg, off_probe, off_rows, off_dist, off_ids, off_norm,
-        off_scan, scan_bytes, total;
+        off_cnorms, off_scan, scan_bytes, total;
     int nseg;
 };
 int64_t assign_batch(int64_t n) { return n < 65536 ? n : 65536; }
@@ -470,6 +493,7 @@ int assign_layout(int64_t n, int64_t K, int d, AssignLayout* L) {
     L->off_ids = take((size_t)B * 8);
     L->off_dist = take((size_t)B * 4);
     L->off_norm = take(4);
+    L->off_cnorms = take((size_t)K * 4);
     L->off_scan = take(L->scan_bytes);
     L->total = o;
     return QK_OK;
@@ -525,6 +549,9 @@ extern "C" int qk_kmeans_assign(const float* points, int64_t n, int64_t point_pi
     }
     rc = qk_max_row_norm(centroids, K, centroid_pitch, d, norm, stream);
     if (rc) return rc;
+    float* cnorms = (float*)(ws + L.off_cnorms);
+    rc = qk_row_sqnorms(centroids, K, centroid_pitch, d, cnorms, stream);
+    if (rc) return rc;
     float h_norm = 0.f;  // the bound is a host-side field of the store
     QK_CUDA(cudaMemcpyAsync(&h_norm, norm, 4, cudaMemcpyDeviceToHost, stream));
     QK_CUDA(cudaStreamSynchronize(stream));
@@ -542,6 +569,7 @@ extern "C" int qk_kmeans_assign(const float* points, int64_t n, int64_t point_pi
     st.seg_row0 = seg_row0;
     st.seg_rows = seg_rows;
     st.max_row_norm = h_norm;
+    st.row_norms = cnorms;
     for (int64_t b = 0; b < n; b += B) {
         const int64_t cnt = (n - b) < B ? (n - b) : B;
         rc = scan_partitions_impl(&st, points + b * point_pitch, cnt, point_pitch, probe, 1, metric, 1, ids, dist, rows,

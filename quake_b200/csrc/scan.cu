@@ -10,11 +10,15 @@
 //   2. prefix_segments   exclusive scan -> per-segment group offsets and the work-item list size
 //   3. scatter_pairs     group the pairs by segment (the reference's batched_serial_scan grouping,
 //                        query_coordinator.cpp:708-721) and emit work items (segment, query chunk)
-//   4. scan_kernel       FILTER: every segment is streamed once per chunk of <=32 queries through
-//                        shared memory (TMA bulk copies, mbarrier pipeline); fp32 FFMA2 scores
-//                        ||v||^2 - 2<q,v> (l2) or -<q,v> (ip); per (query, segment) running top-kc in
-//                        a warp-resident sorted array; a per-query global threshold (atomicMin)
-//                        prunes later segments.
+//   4. scan_kernel       FILTER: persistent, warp-specialised CTAs (one per SM). A producer warp pulls work
+//                        items (segment, chunk of <= 32 queries) from an atomic counter and streams the
+//                        segment's rows through a 4-stage shared-memory ring with TMA bulk copies
+//                        (mbarrier full/empty pipeline); two compute groups of 4 warps take alternate
+//                        64-row tiles and score them against the staged query chunk with fp32 FFMA2
+//                        (||v||^2 - 2<q,v> for l2 with precomputed row norms, -<q,v> for ip), writing
+//                        order-preserving keys to shared memory; four select warps keep, per (query,
+//                        segment), a running top-kc in a warp-resident sorted array, pruned by a per-query
+//                        global threshold (atomicMin). No CTA-wide barrier inside the loop.
 //   5. merge_refine      REFINE: per query, the kc best candidates by filter score are re-evaluated in
 //                        the reference's exact summation order (common.cuh: ref_pair_distance), sorted
 //                        by (distance, id), and a rigorous rounding-error bound proves no rejected
@@ -32,8 +36,8 @@ struct ScanPlan {
     int P;        // (query, segment) pair slots per query
     int kc;       // candidates kept per (query, segment) and refined per query
     int gq;       // queries per work item
+    int nq;       // query-chunk ring depth
     int dp;       // padded dimension (multiple of 4)
-    int variant;  // kernel shape
     size_t smem;  // dynamic shared memory of scan_kernel
     // workspace offsets (bytes)
     size_t off_pair_seg, off_seg_count, off_seg_fill, off_seg_start, off_item_start, off_seg_pairs, off_items,
@@ -41,23 +45,36 @@ struct ScanPlan {
 };
 
 static constexpr int SCAN_DC = 128;     // floats of a row staged per pipeline unit
-static constexpr int SCAN_STAGES = 2;
+static constexpr int SCAN_VP = SCAN_DC + 4;  // padded smem row stride (floats): 8 rows x 16 B hit 32 distinct banks
+static constexpr int SCAN_STAGES = 4;
 static constexpr int SCAN_GQ = 32;      // max queries per work item
-static constexpr int SCAN_TV = 128;     // rows per tile
+static constexpr int SCAN_TV = 64;      // rows per tile
+static constexpr int SCAN_KP = SCAN_TV + 4;  // padded key row stride (u32)
+static constexpr int SCAN_COMPUTE_WARPS = 8;  // two groups of four
+static constexpr int SCAN_SELECT_WARPS = 4;
+static constexpr int SCAN_THREADS = 32 * (SCAN_COMPUTE_WARPS + SCAN_SELECT_WARPS + 1);
+static constexpr int SCAN_MAX_NQ = 4;   // query-chunk ring depth
 static constexpr int MERGE_THREADS = 256;
 static constexpr int MERGE_SORT_CAP = 4096;
+static constexpr size_t SCAN_SMEM_LIMIT = 227 * 1024;
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 static int candidate_count(int k) { return k + (k / 16 > 6 ? k / 16 : 6); }
 
-static size_t scan_smem_bytes(int dp, int kc, int gq) {
-    size_t b = 128;                                                        // mbarriers
-    b += (size_t)SCAN_STAGES * SCAN_TV * (SCAN_DC + 4) * sizeof(float);    // V stages
-    b += (size_t)gq * dp * sizeof(float);                                  // Q chunk
-    b += (size_t)SCAN_GQ * SCAN_TV * sizeof(uint32_t);                     // score keys
-    b += (size_t)gq * kc * sizeof(uint64_t);                               // sorted candidate arrays
-    b += (size_t)SCAN_GQ * 4 * sizeof(int);                                // per-query meta
+struct ItemDesc {  // published by the producer warp for every work item
+    int seg;     // -1: no more work
+    int g_begin, g_cnt;
+    int nrows;
+    long long row0;
+};
+
+static size_t scan_smem_bytes(int dp, int kc, int gq, int nq) {
+    size_t b = 512;                                                          // mbarriers + item descriptors
+    b += (size_t)SCAN_STAGES * SCAN_TV * SCAN_VP * sizeof(float);            // V ring
+    b += (size_t)nq * gq * (dp + 4) * sizeof(float);                         // query-chunk ring
+    b += (size_t)4 * gq * SCAN_KP * sizeof(uint32_t);                        // score keys: 2 groups x 2 buffers
+    b += (size_t)gq * kc * sizeof(uint64_t);                                 // sorted candidate arrays
     return b;
 }
 
@@ -72,13 +89,15 @@ static int make_plan(const qk_store_t* st, int64_t Q, int nprobe, int k, ScanPla
     if (extra > st->num_segments) extra = st->num_segments;
     p->P = nprobe + (int)extra;
     p->kc = candidate_count(k);
-    // queries per work item: bounded by the sorted-array state and the staged query rows
+    // queries per work item: bounded by shared memory (candidate arrays + staged query rows)
     int gq = SCAN_GQ;
-    while (gq > 1 && ((size_t)gq * p->kc * 8 > 40 * 1024 || (size_t)gq * p->dp * 4 > 64 * 1024)) gq >>= 1;
-    QK_REQUIRE((size_t)gq * p->dp * 4 <= 64 * 1024, "dimension %d too large for the scan kernel", st->d);
+    while (gq > 1 && scan_smem_bytes(p->dp, p->kc, gq, 2) > SCAN_SMEM_LIMIT) gq >>= 1;
+    QK_REQUIRE(scan_smem_bytes(p->dp, p->kc, gq, 2) <= SCAN_SMEM_LIMIT,
+               "scan kernel shared memory exceeds 227 KB (k=%d d=%d)", k, st->d);
     p->gq = gq;
-    p->smem = scan_smem_bytes(p->dp, p->kc, gq);
-    QK_REQUIRE(p->smem <= 227 * 1024, "scan kernel shared memory %zu exceeds 227 KB (k=%d d=%d)", p->smem, k, st->d);
+    p->nq = 2;
+    while (p->nq < SCAN_MAX_NQ && scan_smem_bytes(p->dp, p->kc, gq, p->nq + 1) <= SCAN_SMEM_LIMIT) p->nq++;
+    p->smem = scan_smem_bytes(p->dp, p->kc, gq, p->nq);
     QK_REQUIRE(Q * (int64_t)p->P < (int64_t)1 << 30, "too many (query, segment) pairs; split the query batch");
     const size_t QP = (size_t)Q * p->P;
     const size_t S = (size_t)st->num_segments;
@@ -282,6 +301,7 @@ __device__ __forceinline__ void smem_insert(uint64_t* arr, int n, uint64_t c, in
 // ------------------------------------------------------------------------------------------------
 struct ScanArgs {
     const float* vecs;
+    const float* norms;  // squared row norms (l2 only)
     int64_t pitch;
     int dp;
     const int64_t* seg_row0;
@@ -295,10 +315,10 @@ struct ScanArgs {
     uint32_t* gthr;
     uint64_t* cand;
     int32_t* cand_n;
-    int P, kc, gq;
+    int P, kc, gq, nq;
 };
 
-// process the scores of one tile for one query with a register-resident sorted array
+// process the keys of one tile for one query with a register-resident sorted array
 template <int E>
 __device__ __forceinline__ void select_tile(uint64_t* top_g, int kc, const uint32_t* keys, int tile_row0, int lane,
                                             uint32_t& gthr_q, uint32_t* gthr_global) {
@@ -311,7 +331,7 @@ __device__ __forceinline__ void select_tile(uint64_t* top_g, int kc, const uint3
     uint64_t thr = warp_element<E>(a, kc - 1);
     const uint64_t thr_in = thr;
     bool changed = false;  // warp-uniform
-#pragma unroll 1
+#pragma unroll
     for (int j = 0; j < SCAN_TV / 32; ++j) {
         const int r = j * 32 + lane;
         const uint32_t key = keys[r];
@@ -344,6 +364,7 @@ __device__ __forceinline__ void select_tile(uint64_t* top_g, int kc, const uint3
                 gthr_q = old < tk ? old : tk;
             }
         }
+        __syncwarp();
     }
 }
 
@@ -378,197 +399,265 @@ __device__ __forceinline__ void select_tile_generic(uint64_t* top_g, int kc, con
     }
 }
 
-// RV rows per thread, WR warps along rows (TV = 32*RV*WR), QT queries per thread, WQ warps along
-// queries (QT*WQ == SCAN_GQ). Queries are interleaved over the WQ groups: g = t*WQ + wq.
-template <int RV, int WR, int QT, int WQ, bool kIP>
-__global__ void __launch_bounds__(32 * WR * WQ, 1) scan_kernel(const ScanArgs a) {
-    constexpr int NT = 32 * WR * WQ;
-    constexpr int NW = WR * WQ;
-    constexpr int TV = SCAN_TV;
-    constexpr int DC = SCAN_DC;
-    constexpr int VP = DC + 4;
-    static_assert(32 * RV * WR == TV, "tile rows");
-    static_assert(QT * WQ == SCAN_GQ, "queries per item");
-    static_assert(QT % 4 == 0, "QT");
-
+// Shared-memory map (dynamic):
+//   [0, 512)        mbarriers: full[4] empty[4] qfull[4] qempty[4] kfull[2][2] kempty[2][2]; ItemDesc[4] at +256
+//   Vs   [STAGES][TV][VP] f32      row ring, one stage = one tile x one d-chunk
+//   Qs   [nq][gq][dp+4]   f32      query-chunk ring, one slot per work item in flight
+//   Ks   [2 groups][2][gq][KP] u32 score keys
+//   top  [gq][kc] u64              per-query sorted candidate arrays of the current item (select warps only)
+//
+// Roles: warps 0-3 compute group 0 (even tiles), warps 4-7 compute group 1 (odd tiles), warps 8-11 select,
+// warp 12 producer. Inside a compute group, warp gw covers rows rb*32.. (rb = gw & 1) x query half qh = gw >> 1;
+// lane (lr = lane & 7, lq = lane >> 3) owns rows rb*32 + lr + 8i (i < 4) and queries qh + 2*(lq + 4t) (t < 4), so
+// every shared-memory load is one wavefront (8 distinct rows or 4 distinct queries, the rest broadcast).
+template <bool kIP>
+__global__ void __launch_bounds__(SCAN_THREADS, 1) scan_kernel(const ScanArgs a) {
+    constexpr int TV = SCAN_TV, DC = SCAN_DC, VP = SCAN_VP, KP = SCAN_KP, NS = SCAN_STAGES;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);  // full[STAGES], qbar
-    float* Vs = reinterpret_cast<float*>(smem_raw + 128);
-    float* Qs = Vs + SCAN_STAGES * TV * VP;
-    uint32_t* Ss = reinterpret_cast<uint32_t*>(Qs + (size_t)a.gq * a.dp);
-    uint64_t* top = reinterpret_cast<uint64_t*>(Ss + SCAN_GQ * TV);
-    int* meta_pair = reinterpret_cast<int*>(top + (size_t)a.gq * a.kc);
-    uint32_t* meta_gthr = reinterpret_cast<uint32_t*>(meta_pair + SCAN_GQ);
-    __shared__ int s_item;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
+    uint64_t* full = bars;             // [NS]   producer -> compute (tx)
+    uint64_t* empty = bars + 4;        // [NS]   compute  -> producer (4 warps of the owning group)
+    uint64_t* qfull = bars + 8;        // [nq]   producer -> all consumers (tx + descriptor)
+    uint64_t* qempty = bars + 12;      // [nq]   12 consumer warps -> producer
+    uint64_t* kfull = bars + 16;       // [2][2] compute group -> select (4 warps)
+    uint64_t* kempty = bars + 20;      // [2][2] select (4 warps) -> compute group
+    ItemDesc* descs = reinterpret_cast<ItemDesc*>(smem_raw + 256);  // [SCAN_MAX_NQ]
+    float* Vs = reinterpret_cast<float*>(smem_raw + 512);
+    const int dp = a.dp, kc = a.kc, gq = a.gq, nq = a.nq;
+    const int QP = dp + 4;
+    float* Qs = Vs + (size_t)NS * TV * VP;
+    uint32_t* Ks = reinterpret_cast<uint32_t*>(Qs + (size_t)nq * gq * QP);
+    uint64_t* top = reinterpret_cast<uint64_t*>(Ks + (size_t)4 * gq * KP);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int wr = warp % WR, wq = warp / WR;
-    uint64_t* qbar = bars + SCAN_STAGES;
     if (tid == 0) {
-        for (int s = 0; s < SCAN_STAGES; ++s) mbar_init(bars + s, 1);
-        mbar_init(qbar, 1);
+        for (int s = 0; s < NS; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 4); }
+        for (int s = 0; s < SCAN_MAX_NQ; ++s) {
+            mbar_init(qfull + s, 1);
+            mbar_init(qempty + s, SCAN_COMPUTE_WARPS + SCAN_SELECT_WARPS);
+        }
+        for (int s = 0; s < 4; ++s) { mbar_init(kfull + s, 4); mbar_init(kempty + s, SCAN_SELECT_WARPS); }
         mbar_fence_init();
     }
     __syncthreads();
-    uint32_t full_parity = 0;  // bit s = parity to wait for on stage s
-    uint32_t q_parity = 0;
-    const int dp = a.dp, kc = a.kc;
     const int ndc = (dp + DC - 1) / DC;
-    const int n_items = a.ctrl[1];
 
-    for (;;) {
-        if (tid == 0) s_item = atomicAdd(&a.ctrl[0], 1);
-        __syncthreads();
-        const int it = s_item;
-        if (it >= n_items) break;
-        const int2 item = a.items[it];
-        const int seg = item.x;
-        const int g_begin = a.seg_start[seg] + item.y * a.gq;
-        int g_cnt = a.seg_start[seg + 1] - g_begin;
-        g_cnt = g_cnt < a.gq ? g_cnt : a.gq;
-        const int64_t row0 = a.seg_row0[seg];
-        const int nrows = a.seg_rows[seg];
-        const int ntiles = (nrows + TV - 1) / TV;
-        const int nunits = ntiles * ndc;
-
-        // ---- per-item setup: query rows -> smem (bulk copies), candidate arrays, thresholds
-        fence_proxy_async();
-        if (tid == 0) mbar_expect_tx(qbar, (uint32_t)(g_cnt * dp * 4));
-        if (tid < SCAN_GQ) {
-            int pair = -1;
-            if (tid < g_cnt) {
-                pair = a.seg_pairs[g_begin + tid];
+    if (warp == SCAN_COMPUTE_WARPS + SCAN_SELECT_WARPS) {
+        // ===================================================================== producer warp
+        const int n_items = a.ctrl[1];
+        uint32_t U = 0;
+        for (uint32_t n = 0;; ++n) {
+            const int ib = n % nq;
+            mbar_wait(qempty + ib, ((n / nq) & 1u) ^ 1u);
+            int it = 0;
+            if (lane == 0) it = atomicAdd(&a.ctrl[0], 1);
+            it = __shfl_sync(0xffffffffu, it, 0);
+            if (it >= n_items) {
+                if (lane == 0) {
+                    descs[ib].seg = -1;
+                    mbar_arrive(qfull + ib);
+                }
+                break;
+            }
+            const int2 item = a.items[it];
+            const int seg = item.x;
+            const int g_begin = a.seg_start[seg] + item.y * gq;
+            int g_cnt = a.seg_start[seg + 1] - g_begin;
+            g_cnt = g_cnt < gq ? g_cnt : gq;
+            const int64_t row0 = a.seg_row0[seg];
+            const int nrows = a.seg_rows[seg];
+            if (lane == 0) {
+                ItemDesc d;
+                d.seg = seg; d.g_begin = g_begin; d.g_cnt = g_cnt; d.nrows = nrows; d.row0 = row0;
+                descs[ib] = d;
+                mbar_expect_tx(qfull + ib, (uint32_t)(g_cnt * dp * 4));
+            }
+            __syncwarp();
+            if (lane < g_cnt) {
+                const int pair = a.seg_pairs[g_begin + lane];
                 const int64_t q = pair / a.P;
-                meta_gthr[tid] = a.gthr[q];
-                bulk_g2s(Qs + (size_t)tid * dp, a.queries + q * a.q_pitch, (uint32_t)(dp * 4), qbar);
+                bulk_g2s(Qs + ((size_t)ib * gq + lane) * QP, a.queries + q * a.q_pitch, (uint32_t)(dp * 4), qfull + ib);
             }
-            meta_pair[tid] = pair;
-        }
-        for (int i = tid; i < g_cnt * kc; i += NT) top[i] = COMP_MAX;
-
-        auto issue_unit = [&](int u) {
-            const int stage = u % SCAN_STAGES;
-            const int tile = u / ndc, dc = u - tile * ndc;
-            const int tr = min(TV, nrows - tile * TV);
-            const int dcur = min(DC, dp - dc * DC);
-            if (tid == 0) mbar_expect_tx(bars + stage, (uint32_t)(tr * dcur * 4));
-            for (int r = tid; r < tr; r += NT)
-                bulk_g2s(Vs + ((size_t)stage * TV + r) * VP, a.vecs + (row0 + (int64_t)tile * TV + r) * a.pitch + dc * DC,
-                         (uint32_t)(dcur * 4), bars + stage);
-        };
-        issue_unit(0);
-        mbar_wait(qbar, q_parity);
-        q_parity ^= 1;
-        __syncthreads();  // meta + top visible
-
-        // number of queries this thread serves: g = t*WQ + wq < g_cnt
-        const int my_q = (g_cnt - wq + WQ - 1) / WQ;
-
-        float2 acc[RV][QT];
-        float nrm[RV];
-#pragma unroll 1
-        for (int u = 0; u < nunits; ++u) {
-            const int stage = u % SCAN_STAGES;
-            const int tile = u / ndc, dc = u - tile * ndc;
-            if (u + 1 < nunits) {
-                fence_proxy_async();
-                issue_unit(u + 1);
-            }
-            if (dc == 0) {
-#pragma unroll
-                for (int i = 0; i < RV; ++i) {
-                    nrm[i] = 0.f;
-#pragma unroll
-                    for (int t = 0; t < QT; ++t) acc[i][t] = make_float2(0.f, 0.f);
+            const int ntiles = (nrows + TV - 1) / TV;
+            for (int tile = 0; tile < ntiles; ++tile) {
+                const int tr = min(TV, nrows - tile * TV);
+                for (int dc = 0; dc < ndc; ++dc, ++U) {
+                    const int st = U % NS;
+                    mbar_wait(empty + st, ((U / NS) & 1u) ^ 1u);
+                    const int dcur = min(DC, dp - dc * DC);
+                    if (lane == 0) mbar_expect_tx(full + st, (uint32_t)(tr * dcur * 4));
+                    __syncwarp();
+                    for (int r = lane; r < tr; r += 32)
+                        bulk_g2s(Vs + ((size_t)st * TV + r) * VP,
+                                 a.vecs + (row0 + (int64_t)tile * TV + r) * a.pitch + dc * DC, (uint32_t)(dcur * 4),
+                                 full + st);
                 }
             }
-            mbar_wait(bars + stage, (full_parity >> stage) & 1u);
-            full_parity ^= (1u << stage);
-
-            const int dcur4 = min(DC, dp - dc * DC) >> 2;
-            const float4* vrow[RV];
+        }
+    } else if (warp >= SCAN_COMPUTE_WARPS) {
+        // ===================================================================== select warps
+        const int sw = warp - SCAN_COMPUTE_WARPS;
+        uint32_t T = 0;
+        for (uint32_t n = 0;; ++n) {
+            const int ib = n % nq;
+            mbar_wait(qfull + ib, (n / nq) & 1u);
+            const ItemDesc d = descs[ib];
+            if (d.seg < 0) break;
+            // lane j < 8 keeps the (pair, threshold) of query g = sw + 4j
+            int my_pair = -1;
+            uint32_t my_gthr = KEY_MAX;
+            {
+                const int g = sw + 4 * lane;
+                if (lane < 8 && g < d.g_cnt) {
+                    my_pair = a.seg_pairs[d.g_begin + g];
+                    my_gthr = a.gthr[my_pair / a.P];
+                }
+            }
+            for (int g = sw; g < d.g_cnt; g += 4)
+                for (int i = lane; i < kc; i += 32) top[(size_t)g * kc + i] = COMP_MAX;
+            __syncwarp();
+            const int ntiles = (d.nrows + TV - 1) / TV;
+            for (int tile = 0; tile < ntiles; ++tile, ++T) {
+                const int grp = T & 1u, kb = (T >> 1) & 1u;
+                mbar_wait(kfull + grp * 2 + kb, (T >> 2) & 1u);
+                const uint32_t* kbase = Ks + (size_t)(grp * 2 + kb) * gq * KP;
+                for (int j = 0; sw + 4 * j < d.g_cnt; ++j) {
+                    const int g = sw + 4 * j;
+                    uint32_t gthr_q = __shfl_sync(0xffffffffu, my_gthr, j);
+                    const int pair = __shfl_sync(0xffffffffu, my_pair, j);
+                    uint32_t* gthr_global = a.gthr + pair / a.P;
+                    if (kc <= 32)
+                        select_tile<1>(top + (size_t)g * kc, kc, kbase + g * KP, tile * TV, lane, gthr_q, gthr_global);
+                    else if (kc <= 128)
+                        select_tile<4>(top + (size_t)g * kc, kc, kbase + g * KP, tile * TV, lane, gthr_q, gthr_global);
+                    else
+                        select_tile_generic(top + (size_t)g * kc, kc, kbase + g * KP, tile * TV, lane, gthr_q, gthr_global);
+                    if (lane == j) my_gthr = gthr_q;
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(kempty + grp * 2 + kb);
+            }
+            // emit the per-(query, segment) candidates
+            for (int j = 0; sw + 4 * j < d.g_cnt; ++j) {
+                const int g = sw + 4 * j;
+                const int pair = __shfl_sync(0xffffffffu, my_pair, j);
+                const uint64_t* tg = top + (size_t)g * kc;
+                uint64_t* out = a.cand + (size_t)pair * kc;
+                int cnt = 0;
+                for (int base = 0; base < kc; base += 32) {
+                    int i = base + lane;
+                    uint64_t v = (i < kc) ? tg[i] : COMP_MAX;
+                    if (v != COMP_MAX) out[i] = v;
+                    cnt += __popc(__ballot_sync(0xffffffffu, v != COMP_MAX));
+                }
+                if (lane == 0) a.cand_n[pair] = cnt;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(qempty + ib);
+        }
+    } else {
+        // ===================================================================== compute warps
+        const int grp = warp >> 2, gw = warp & 3;
+        const int rb = gw & 1, qh = gw >> 1;
+        const int lr = lane & 7, lq = lane >> 3;
+        uint32_t T = 0, U = 0;
+        for (uint32_t n = 0;; ++n) {
+            const int ib = n % nq;
+            mbar_wait(qfull + ib, (n / nq) & 1u);
+            const ItemDesc d = descs[ib];
+            if (d.seg < 0) break;
+            const int g_cnt = d.g_cnt;
+            // queries of this lane: g = qh + 2*(lq + 4t); t < nt is warp-uniform
+            const int jmax = (g_cnt - qh + 1) >> 1;            // number of j = lq + 4t with g < g_cnt
+            const int nt = (jmax + 3) >> 2;                    // 0..4
+            const float* qbase = Qs + ((size_t)ib * gq + qh + 2 * lq) * QP;
+            const int ntiles = (d.nrows + TV - 1) / TV;
+            for (int tile = 0; tile < ntiles; ++tile, ++T, U += ndc) {
+                if ((int)(T & 1u) != grp) continue;
+                const int tr = min(TV, d.nrows - tile * TV);
+                float nrm[4];
+                if (!kIP) {
 #pragma unroll
-            for (int i = 0; i < RV; ++i)
-                vrow[i] = reinterpret_cast<const float4*>(Vs + ((size_t)stage * TV + wr * (32 * RV) + i * 32 + lane) * VP);
-            const float4* qrow = reinterpret_cast<const float4*>(Qs + (size_t)wq * dp + dc * DC);
-            const int qstride4 = (WQ * dp) >> 2;
-#pragma unroll 2
-            for (int c = 0; c < dcur4; ++c) {
-                float4 v[RV];
-#pragma unroll
-                for (int i = 0; i < RV; ++i) {
-                    v[i] = vrow[i][c];
-                    if (!kIP) {
-                        nrm[i] = fmaf(v[i].x, v[i].x, nrm[i]);
-                        nrm[i] = fmaf(v[i].y, v[i].y, nrm[i]);
-                        nrm[i] = fmaf(v[i].z, v[i].z, nrm[i]);
-                        nrm[i] = fmaf(v[i].w, v[i].w, nrm[i]);
+                    for (int i = 0; i < 4; ++i) {
+                        const int r = rb * 32 + lr + 8 * i;
+                        nrm[i] = (r < tr) ? __ldg(a.norms + d.row0 + (int64_t)tile * TV + r) : 0.f;
                     }
                 }
+                float2 acc[4][4];
 #pragma unroll
-                for (int tb = 0; tb < QT / 4; ++tb) {
-                    if (tb * 4 < my_q) {
+                for (int i = 0; i < 4; ++i)
 #pragma unroll
-                        for (int tt = 0; tt < 4; ++tt) {
-                            const int t = tb * 4 + tt;
-                            const float4 q4 = qrow[(size_t)t * qstride4 + c];
+                    for (int t = 0; t < 4; ++t) acc[i][t] = make_float2(0.f, 0.f);
+                for (int dc = 0; dc < ndc; ++dc) {
+                    const uint32_t u = U + dc;
+                    const int st = u % NS;
+                    mbar_wait(full + st, (u / NS) & 1u);
+                    const int dcur4 = min(DC, dp - dc * DC) >> 2;
+                    const float4* vrow = reinterpret_cast<const float4*>(Vs + ((size_t)st * TV + rb * 32 + lr) * VP);
+                    const float4* qrow = reinterpret_cast<const float4*>(qbase + dc * DC);
+                    constexpr int VSTEP = 8 * VP / 4;          // float4 stride between this lane's rows
+                    const int qstep = 8 * QP / 4;              // float4 stride between this lane's queries
+                    if (nt == 4) {
+#pragma unroll 4
+                        for (int c = 0; c < dcur4; ++c) {
+                            float4 v[4], q[4];
 #pragma unroll
-                            for (int i = 0; i < RV; ++i) {
-                                acc[i][t] = ffma2(make_float2(v[i].x, v[i].y), make_float2(q4.x, q4.y), acc[i][t]);
-                                acc[i][t] = ffma2(make_float2(v[i].z, v[i].w), make_float2(q4.z, q4.w), acc[i][t]);
+                            for (int i = 0; i < 4; ++i) v[i] = vrow[i * VSTEP + c];
+#pragma unroll
+                            for (int t = 0; t < 4; ++t) q[t] = qrow[t * qstep + c];
+#pragma unroll
+                            for (int t = 0; t < 4; ++t)
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) {
+                                    acc[i][t] = ffma2(make_float2(v[i].x, v[i].y), make_float2(q[t].x, q[t].y), acc[i][t]);
+                                    acc[i][t] = ffma2(make_float2(v[i].z, v[i].w), make_float2(q[t].z, q[t].w), acc[i][t]);
+                                }
+                        }
+                    } else if (nt >= 1) {
+#pragma unroll 2
+                        for (int c = 0; c < dcur4; ++c) {
+                            float4 v[4];
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) v[i] = vrow[i * VSTEP + c];
+#pragma unroll
+                            for (int t = 0; t < 3; ++t) {
+                                if (t < nt) {
+                                    const float4 q4 = qrow[t * qstep + c];
+#pragma unroll
+                                    for (int i = 0; i < 4; ++i) {
+                                        acc[i][t] = ffma2(make_float2(v[i].x, v[i].y), make_float2(q4.x, q4.y), acc[i][t]);
+                                        acc[i][t] = ffma2(make_float2(v[i].z, v[i].w), make_float2(q4.z, q4.w), acc[i][t]);
+                                    }
+                                }
                             }
                         }
                     }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(empty + st);
                 }
-            }
-
-            if (dc == ndc - 1) {
-                // ---- tile epilogue: scores -> keys -> smem; then warp-per-query selection
-                const int tr = min(TV, nrows - tile * TV);
+                // ---- tile epilogue: scores -> order-preserving keys -> Ks[grp][kb]
+                const int kb = (T >> 1) & 1u;
+                mbar_wait(kempty + grp * 2 + kb, ((T >> 2) & 1u) ^ 1u);
+                uint32_t* kbase = Ks + (size_t)(grp * 2 + kb) * gq * KP;
 #pragma unroll
-                for (int i = 0; i < RV; ++i) {
-                    const int r = wr * (32 * RV) + i * 32 + lane;
+                for (int t = 0; t < 4; ++t) {
+                    const int g = qh + 2 * (lq + 4 * t);
+                    if (g < g_cnt) {
 #pragma unroll
-                    for (int t = 0; t < QT; ++t) {
-                        const int g = t * WQ + wq;
-                        if (g < g_cnt) {
+                        for (int i = 0; i < 4; ++i) {
+                            const int r = rb * 32 + lr + 8 * i;
                             const float dot = acc[i][t].x + acc[i][t].y;
-                            const float s = kIP ? -dot : fmaf(-2.f, dot, nrm[i]);
-                            Ss[g * TV + r] = (r < tr) ? f2key(s) : KEY_MAX;
+                            const float sc = kIP ? -dot : fmaf(-2.f, dot, nrm[i]);
+                            kbase[g * KP + r] = (r < tr) ? f2key(sc) : KEY_MAX;
                         }
                     }
                 }
-                __syncthreads();
-                for (int g = warp; g < g_cnt; g += NW) {
-                    uint32_t gthr_q = meta_gthr[g];
-                    uint32_t* gthr_global = a.gthr + meta_pair[g] / a.P;
-                    if (kc <= 32)
-                        select_tile<1>(top + (size_t)g * kc, kc, Ss + g * TV, tile * TV, lane, gthr_q, gthr_global);
-                    else if (kc <= 128)
-                        select_tile<4>(top + (size_t)g * kc, kc, Ss + g * TV, tile * TV, lane, gthr_q, gthr_global);
-                    else
-                        select_tile_generic(top + (size_t)g * kc, kc, Ss + g * TV, tile * TV, lane, gthr_q, gthr_global);
-                    if (lane == 0) meta_gthr[g] = gthr_q;
-                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(kfull + grp * 2 + kb);
             }
-            __syncthreads();  // stage consumed (and, after an epilogue, Ss free again)
+            __syncwarp();
+            if (lane == 0) mbar_arrive(qempty + ib);
         }
-
-        // ---- emit the per-(query, segment) candidates
-        for (int g = warp; g < g_cnt; g += NW) {
-            const int pair = meta_pair[g];
-            const uint64_t* tg = top + (size_t)g * kc;
-            uint64_t* out = a.cand + (size_t)pair * kc;
-            int n = 0;
-            for (int base = 0; base < kc; base += 32) {
-                int i = base + lane;
-                uint64_t v = (i < kc) ? tg[i] : COMP_MAX;
-                if (v != COMP_MAX) out[i] = v;
-                n += __popc(__ballot_sync(0xffffffffu, v != COMP_MAX));
-            }
-            if (lane == 0) a.cand_n[pair] = n;
-        }
-        __syncthreads();  // protects s_item, meta, top before the next item
     }
 }
 
@@ -951,18 +1040,26 @@ __global__ void __launch_bounds__(256) exact_rescan_kernel(const MergeArgs a, co
 static int g_scan_variant = -1;
 static int g_force_rescan = 0;
 
-template <int RV, int WR, int QT, int WQ>
+// optional per-launch timing of the filter kernel (qk_profile_*): CUDA events recorded on the launch
+// stream right around scan_kernel, read back by the caller after it has synchronised.
+struct ProfileRecord {
+    cudaEvent_t start, stop;
+    int64_t queries;
+    int nprobe, k, used;
+};
+static ProfileRecord* g_prof = nullptr;
+static int g_prof_cap = 0, g_prof_n = 0;
+
 static int launch_scan(const ScanArgs& sa, int metric, size_t smem, cudaStream_t stream) {
-    const int nt = 32 * WR * WQ;
     const int grid = sm_count();
     if (metric == QK_METRIC_INNER_PRODUCT) {
-        auto kern = scan_kernel<RV, WR, QT, WQ, true>;
+        auto kern = scan_kernel<true>;
         QK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, nt, smem, stream>>>(sa);
+        kern<<<grid, SCAN_THREADS, smem, stream>>>(sa);
     } else {
-        auto kern = scan_kernel<RV, WR, QT, WQ, false>;
+        auto kern = scan_kernel<false>;
         QK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, nt, smem, stream>>>(sa);
+        kern<<<grid, SCAN_THREADS, smem, stream>>>(sa);
     }
     QK_CUDA(cudaGetLastError());
     return QK_OK;
@@ -1007,8 +1104,7 @@ int qk::scan_partitions_impl(const qk_store_t* st, const float* queries, int64_t
         return QK_ERR_WORKSPACE;
     }
     if (g_scan_variant < 0) {
-        const char* e = getenv("QK_SCAN_VARIANT");
-        g_scan_variant = e ? atoi(e) : 0;
+        g_scan_variant = 0;
         const char* f = getenv("QK_FORCE_RESCAN");
         g_force_rescan = f ? atoi(f) : 0;
     }
@@ -1056,14 +1152,17 @@ int qk::scan_partitions_impl(const qk_store_t* st, const float* queries, int64_t
     sa.queries = queries; sa.q_pitch = q_pitch;
     sa.seg_start = seg_start; sa.seg_pairs = seg_pairs; sa.items = items; sa.ctrl = ctrl;
     sa.gthr = gthr; sa.cand = cand; sa.cand_n = cand_n;
-    sa.P = p.P; sa.kc = p.kc; sa.gq = p.gq;
-    switch (g_scan_variant) {
-        case 1: rc = launch_scan<1, 4, 16, 2>(sa, metric, p.smem, stream); break;
-        case 2: rc = launch_scan<4, 1, 8, 4>(sa, metric, p.smem, stream); break;
-        case 3: rc = launch_scan<2, 2, 8, 4>(sa, metric, p.smem, stream); break;
-        default: rc = launch_scan<2, 2, 16, 2>(sa, metric, p.smem, stream); break;
+    sa.P = p.P; sa.kc = p.kc; sa.gq = p.gq; sa.nq = p.nq;
+    sa.norms = st->row_norms;
+    ProfileRecord* rec = nullptr;
+    if (g_prof && g_prof_n < g_prof_cap) {
+        rec = &g_prof[g_prof_n++];
+        rec->queries = Q; rec->nprobe = nprobe; rec->k = k; rec->used = 1;
+        QK_CUDA(cudaEventRecord(rec->start, stream));
     }
+    rc = launch_scan(sa, metric, p.smem, stream);
     if (rc) return rc;
+    if (rec) QK_CUDA(cudaEventRecord(rec->stop, stream));
 
     MergeArgs ma;
     ma.vecs = st->vectors; ma.pitch = st->pitch; ma.ids = st->ids; ma.d = st->d;
@@ -1099,5 +1198,49 @@ int qk::scan_partitions_impl(const qk_store_t* st, const float* queries, int64_t
         QK_CUDA(cudaGetLastError());
     }
     if (stats) QK_CUDA(cudaMemcpyAsync(stats, ctrl + 2, sizeof(int32_t), cudaMemcpyDeviceToDevice, stream));
+    return QK_OK;
+}
+
+// ---- per-launch timing of the filter kernel ------------------------------------------------------
+extern "C" int qk_profile_begin(int max_records) {
+    QK_REQUIRE(max_records > 0 && max_records <= (1 << 20), "bad max_records");
+    if (g_prof) {
+        for (int i = 0; i < g_prof_cap; ++i) { cudaEventDestroy(g_prof[i].start); cudaEventDestroy(g_prof[i].stop); }
+        delete[] g_prof;
+        g_prof = nullptr;
+    }
+    g_prof = new ProfileRecord[max_records];
+    g_prof_cap = max_records;
+    g_prof_n = 0;
+    for (int i = 0; i < max_records; ++i) {
+        QK_CUDA(cudaEventCreate(&g_prof[i].start));
+        QK_CUDA(cudaEventCreate(&g_prof[i].stop));
+        g_prof[i].used = 0;
+    }
+    return QK_OK;
+}
+
+extern "C" int qk_profile_count(void) { return g_prof ? g_prof_n : 0; }
+
+extern "C" int qk_profile_read(int index, float* ms, int64_t* queries, int* nprobe, int* k) {
+    QK_REQUIRE(g_prof && index >= 0 && index < g_prof_n, "profile record %d out of range", index);
+    ProfileRecord& r = g_prof[index];
+    QK_CUDA(cudaEventSynchronize(r.stop));
+    float t = 0.f;
+    QK_CUDA(cudaEventElapsedTime(&t, r.start, r.stop));
+    if (ms) *ms = t;
+    if (queries) *queries = r.queries;
+    if (nprobe) *nprobe = r.nprobe;
+    if (k) *k = r.k;
+    return QK_OK;
+}
+
+extern "C" int qk_profile_end(void) {
+    if (g_prof) {
+        for (int i = 0; i < g_prof_cap; ++i) { cudaEventDestroy(g_prof[i].start); cudaEventDestroy(g_prof[i].stop); }
+        delete[] g_prof;
+    }
+    g_prof = nullptr;
+    g_prof_cap = g_prof_n = 0;
     return QK_OK;
 }

@@ -19,7 +19,8 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import QK_SEGMENT_ROWS, QkStore, check, ptr
+from ._lib import QkStore, check, ptr
+from ._lib import QK_SEGMENT_ROWS as _MAX_SEGMENT_ROWS
 
 
 def _round_up(x: int, a: int) -> int:
@@ -37,6 +38,7 @@ class PartitionStore:
         self.device = device
         self.vectors = torch.zeros((0, self.pitch), dtype=torch.float32, device=device)
         self.ids = torch.zeros((0,), dtype=torch.int64, device=device)
+        self.norms = torch.zeros((0,), dtype=torch.float32, device=device)  # squared row norms
         self.rows_used = 0
         self.list_row0 = np.zeros(0, dtype=np.int64)
         self.list_size = np.zeros(0, dtype=np.int64)
@@ -73,10 +75,12 @@ class PartitionStore:
         new_cap = max(rows, int(self.vectors.shape[0] * 1.5) + 1024)
         nv = torch.zeros((new_cap, self.pitch), dtype=torch.float32, device=self.device)
         ni = torch.full((new_cap,), -1, dtype=torch.int64, device=self.device)
+        nn = torch.zeros((new_cap,), dtype=torch.float32, device=self.device)
         if self.rows_used:
             nv[: self.rows_used].copy_(self.vectors[: self.rows_used])
             ni[: self.rows_used].copy_(self.ids[: self.rows_used])
-        self.vectors, self.ids = nv, ni
+            nn[: self.rows_used].copy_(self.norms[: self.rows_used])
+        self.vectors, self.ids, self.norms = nv, ni, nn
         self._dirty = True
 
     def _new_slot(self) -> int:
@@ -126,6 +130,7 @@ class PartitionStore:
         if n:
             self.vectors[new0:new0 + n].copy_(self.vectors[old0:old0 + n])
             self.ids[new0:new0 + n].copy_(self.ids[old0:old0 + n])
+            self.norms[new0:new0 + n].copy_(self.norms[old0:old0 + n])
         self.list_row0[s] = new0
         self.list_cap[s] = new_cap
         self.rows_used += new_cap
@@ -145,6 +150,7 @@ class PartitionStore:
         total = int(caps.sum())
         self.vectors = torch.zeros((total, self.pitch), dtype=torch.float32, device=self.device)
         self.ids = torch.full((total,), -1, dtype=torch.int64, device=self.device)
+        self.norms = torch.zeros((total,), dtype=torch.float32, device=self.device)
         self.rows_used = total
         nl = len(counts)
         self.list_row0 = row0.copy()
@@ -173,7 +179,15 @@ class PartitionStore:
         # dead rows are zero or stale copies of live rows: both are safe for an upper bound
         check(lib.qk_max_row_norm(ptr(self.vectors), self.rows_used, self.pitch, self.d, ptr(out), _stream()))
         self.max_row_norm = float(out.item())
+        self._refresh_norms(0, self.rows_used)
         self._dirty = True
+
+    def _refresh_norms(self, row0: int, n: int) -> None:
+        """Recompute the squared norms of arena rows [row0, row0 + n)."""
+        if n <= 0:
+            return
+        check(_lib.load().qk_row_sqnorms(ptr(self.vectors[row0:]), n, self.pitch, self.d, ptr(self.norms[row0:]),
+                                         _stream()))
 
     # ------------------------------------------------------------------ append / remove
     def append(self, slots: torch.Tensor, x: torch.Tensor, x_ids: torch.Tensor) -> None:
@@ -204,6 +218,9 @@ class PartitionStore:
         x = x.contiguous()
         check(lib.qk_scatter_rows(ptr(x), x.stride(0), ptr(x_ids.contiguous()), ptr(order_d), ptr(dst_rows), n, self.d,
                                   ptr(self.vectors), self.pitch, ptr(self.ids), _stream()))
+        xn = torch.empty(n, dtype=torch.float32, device=self.device)
+        check(lib.qk_row_sqnorms(ptr(x), n, x.stride(0), self.d, ptr(xn), _stream()))
+        self.norms[dst_rows] = xn[order_d]
         self.list_size = self.list_size + counts
         out = torch.tensor([self.max_row_norm], dtype=torch.float32, device=self.device)
         check(lib.qk_max_row_norm(ptr(x), n, x.stride(0), self.d, ptr(out), _stream()))
@@ -268,6 +285,7 @@ class PartitionStore:
             dst = torch.tensor(dst_l, dtype=torch.int64, device=self.device)
             self.vectors[dst] = self.vectors[src]
             self.ids[dst] = self.ids[src]
+            self.norms[dst] = self.norms[src]
         self._dirty = True
         return int(rows_h.size)
 
@@ -290,6 +308,10 @@ class PartitionStore:
             if self.pitch > self.d:
                 self.vectors[r0:r0 + n, self.d:] = 0
             self.ids[r0:r0 + n] = ids
+            self._refresh_norms(r0, n)
+            out = torch.tensor([self.max_row_norm], dtype=torch.float32, device=self.device)
+            check(_lib.load().qk_max_row_norm(ptr(self.vectors[r0:]), n, self.pitch, self.d, ptr(out), _stream()))
+            self.max_row_norm = float(out.item())
         self.list_size[s] = n
         self._dirty = True
 
@@ -315,6 +337,12 @@ class PartitionStore:
             return self._struct, self._id_to_slot
         nslots = self.slot_pid.size
         size = self.list_size
+        # scan-segment length: long lists (a flat index is ONE list) are cut so that the whole GPU gets work
+        # items even for a small query batch; IVF lists are far shorter than this and stay whole.
+        total = int(size.sum()) if nslots else 0
+        seg_len = min(_MAX_SEGMENT_ROWS, max(256, -(-total // 1024)))
+        seg_len = (seg_len + 63) // 64 * 64
+        QK_SEGMENT_ROWS = seg_len  # noqa: F841 (shadows the module constant below on purpose)
         nseg = (size + QK_SEGMENT_ROWS - 1) // QK_SEGMENT_ROWS
         seg0 = np.concatenate([[0], np.cumsum(nseg)[:-1]]) if nslots else np.zeros(0, np.int64)
         S = int(nseg.sum())
@@ -347,6 +375,7 @@ class PartitionStore:
         st.seg_row0 = t["seg_row0"].data_ptr()
         st.seg_rows = t["seg_rows"].data_ptr()
         st.max_row_norm = float(self.max_row_norm)
+        st.row_norms = self.norms.data_ptr()
         self._tables = t
         self._struct = st
         self._dirty = False
