@@ -287,6 +287,16 @@ def run_b200(args):
     alg_bytes = int(sizes.sum()) * W["d"] * 4
     pair_bytes = int(sum(idx.store.size_of(int(p)) for p in p_ids.cpu().numpy().reshape(-1) if p >= 0)) * W["d"] * 4
 
+    # ---- selection statistics of one partition scan (how many candidates the filter appended)
+    os.environ["QK_SCAN_STATS"] = "1"
+    idx._search_device(xq_d, sp)
+    torch.cuda.synchronize()
+    from quake_b200 import index as _qi
+    st4 = _qi.LAST_SCAN_STATS.cpu().tolist()
+    os.environ.pop("QK_SCAN_STATS")
+    scan_stats = {"queries_rescanned": st4[0], "max_appended_per_query": st4[1],
+                  "mean_appended_per_query": ((st4[3] << 32) | (st4[2] & 0xffffffff)) / W["Q"]}
+
     def barrier():
         if world > 1:
             dist.barrier()
@@ -361,7 +371,7 @@ def run_b200(args):
             "config": {"workload": W["name"], "N": W["N"], "nlist": W["nlist"], "nprobe": W["nprobe"], "Q": W["Q"],
                        "k": W["k"], "metric": W["metric"], "parallelism": f"replicas x{world}" if world > 1 else "1 gpu",
                        "l2_policy": "index (512 MB of lists) larger than L2; no flush between steps",
-                       "build_s": round(build_s, 2), "parity": parity},
+                       "build_s": round(build_s, 2), "parity": parity, "scan_stats": scan_stats},
             "roofline": {"bound": "hbm", "kernel": "scan_kernel (partition-scan filter)", "achieved": achieved,
                          "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None, "traffic": traffic,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,

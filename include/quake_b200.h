@@ -58,6 +58,7 @@ typedef struct qk_store {
     const int32_t* seg_rows;     /* [num_segments] rows in the segment (1..QK_SEGMENT_ROWS)          */
     float          max_row_norm; /* upper bound on the L2 norm of any stored row (see qk_max_row_norm)*/
     const float*   row_norms;    /* [rows] squared L2 norm of every row (see qk_row_sqnorms); l2 only */
+    int64_t        num_rows;     /* rows allocated behind `vectors` (bounds of the TMA tensor map)       */
 } qk_store_t;
 
 #define QK_SEGMENT_ROWS 4096
@@ -78,7 +79,8 @@ int qk_device_check(int* sm_count, int* cc_major, int* cc_minor);
  *
  * probe_lists: [Q x nprobe] int32 list slots in probe order, -1 = skip (query_coordinator.cpp:540).
  * out_rows   : optional [Q x k] int64 arena row of each result (-1 where padded).
- * stats      : optional device int32[4]: {queries that took the exact re-scan path, 0, 0, 0}.
+ * stats      : optional device int32[4]: {queries that took the exact re-scan path, largest number of
+ *              candidates any query appended, total candidates appended (low, high 32 bits)}.
  */
 size_t qk_scan_workspace_bytes(const qk_store_t* store, int64_t num_queries, int nprobe, int k);
 int qk_scan_partitions(const qk_store_t* store,

@@ -40,6 +40,7 @@ class QkStore(C.Structure):
         ("seg_rows", vp),
         ("max_row_norm", C.c_float),
         ("row_norms", vp),
+        ("num_rows", C.c_int64),
     ]
 
 

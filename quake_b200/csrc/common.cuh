@@ -1,5 +1,6 @@
 // Shared device helpers for the quake_b200 kernels (sm_100a only).
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <math.h>
@@ -125,6 +126,33 @@ __device__ float ref_pair_distance(const float* __restrict__ x, const float* __r
     return res;
 }
 
+// The same evaluation spread over an aligned group of 8 lanes: lane j (= lane & 7) carries accumulator
+// a_j; the fold uses shuffles inside the group. Every lane of the group must call it; the result is valid
+// on the group's lane 0. Bit-identical to ref_pair_distance (float addition is commutative).
+template <bool kIP>
+__device__ __forceinline__ float ref_pair_distance_g8(const float* __restrict__ x, const float* __restrict__ y, int d,
+                                                      int j) {
+    const unsigned gmask = 0xffu << ((threadIdx.x & 31u) & 24u);  // the group may sit in a divergent branch
+    float a = 0.f;
+    const int nb = d >> 3;
+    for (int b = 0; b < nb; ++b) a = __fadd_rn(a, ref_term<kIP>(x[8 * b + j], y[8 * b + j]));
+    // s_j = a_j + a_{j+4} on lanes j < 4
+    float s = __fadd_rn(a, __shfl_down_sync(gmask, a, 4, 8));
+    int o = nb << 3;
+    int r = d - o;
+    float f = s;
+    if (r >= 4) {
+        if (j < 4) f = ref_fma_term<kIP>(x[o + j], y[o + j], s);
+        o += 4;
+        r -= 4;
+    }
+    // (f0 + f2) on lane 0, (f1 + f3) on lane 1, then their sum on lane 0
+    float t = __fadd_rn(f, __shfl_down_sync(gmask, f, 2, 8));
+    float res = __fadd_rn(t, __shfl_down_sync(gmask, t, 1, 8));
+    for (int i = 0; i < r; ++i) res = ref_fma_term<kIP>(x[o + i], y[o + i], res);
+    return res;
+}
+
 // ---------------------------------------------------------------------------------------------
 // mbarrier + bulk-copy (TMA, UBLKCP) wrappers
 // ---------------------------------------------------------------------------------------------
@@ -159,6 +187,22 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint3
                      smem_u32(smem_dst)),
                  "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
+}
+// 2-D tiled TMA load (tensor map in kernel parameter space), completion on an mbarrier.
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tmap, int x, int y, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(x), "r"(y)
+        : "memory");
+}
+// 16-byte asynchronous copy global -> shared that bypasses L1 (LDGSTS)
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+// one (pre-counted) arrival on `bar` once all cp.async of this thread issued so far have landed
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t* bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 

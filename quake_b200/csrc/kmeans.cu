@@ -570,6 +570,7 @@ extern "C" int qk_kmeans_assign(const float* points, int64_t n, int64_t point_pi
     st.seg_rows = seg_rows;
     st.max_row_norm = h_norm;
     st.row_norms = cnorms;
+    st.num_rows = K;
     for (int64_t b = 0; b < n; b += B) {
         const int64_t cnt = (n - b) < B ? (n - b) : B;
         rc = scan_partitions_impl(&st, points + b * point_pitch, cnt, point_pitch, probe, 1, metric, 1, ids, dist, rows,

@@ -41,17 +41,17 @@ struct ScanPlan {
     size_t smem;  // dynamic shared memory of scan_kernel
     // workspace offsets (bytes)
     size_t off_pair_seg, off_seg_count, off_seg_fill, off_seg_start, off_item_start, off_seg_pairs, off_items,
-        off_ctrl, off_gthr, off_flags, off_cand_n, off_cand, total;
+        off_ctrl, off_gthr, off_flags, off_qcount, off_qbuf, total;
+    int qcap;     // entries of the per-query candidate buffer
 };
 
 static constexpr int SCAN_DC = 128;     // floats of a row staged per pipeline unit
-static constexpr int SCAN_VP = SCAN_DC + 4;  // padded smem row stride (floats): 8 rows x 16 B hit 32 distinct banks
 static constexpr int SCAN_STAGES = 4;
 static constexpr int SCAN_GQ = 32;      // max queries per work item
 static constexpr int SCAN_TV = 64;      // rows per tile
 static constexpr int SCAN_KP = SCAN_TV + 4;  // padded key row stride (u32)
 static constexpr int SCAN_COMPUTE_WARPS = 8;  // two groups of four
-static constexpr int SCAN_SELECT_WARPS = 4;
+static constexpr int SCAN_SELECT_WARPS = 7;   // 8 + 7 + 1 producer = 16 warps: 128 registers per thread
 static constexpr int SCAN_THREADS = 32 * (SCAN_COMPUTE_WARPS + SCAN_SELECT_WARPS + 1);
 static constexpr int SCAN_MAX_NQ = 4;   // query-chunk ring depth
 static constexpr int MERGE_THREADS = 256;
@@ -62,20 +62,42 @@ static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; 
 
 static int candidate_count(int k) { return k + (k / 16 > 6 ? k / 16 : 6); }
 
-struct ItemDesc {  // published by the producer warp for every work item
-    int seg;     // -1: no more work
+struct WorkItem {  // one (segment, query chunk) unit of work; written by scatter_pairs_kernel
+    int seg;     // -1: no more work (only in shared memory)
     int g_begin, g_cnt;
     int nrows;
     long long row0;
+    long long pad_;
 };
+static_assert(sizeof(WorkItem) == 32, "WorkItem layout");
+
+struct ItemDesc {  // published in shared memory by the producer warp for every work item in flight
+    WorkItem w;
+    int pair[SCAN_GQ];        // (query, segment) pair index of every query slot
+    uint32_t gthr[SCAN_GQ];   // the queries' global filter-key thresholds when the item was issued
+};
+static constexpr int SCAN_SMEM_HEADER = 2048;  // mbarriers (256 B) + SCAN_MAX_NQ descriptors
+static_assert(256 + SCAN_MAX_NQ * sizeof(ItemDesc) <= SCAN_SMEM_HEADER, "header");
+
+// Entries of the per-query candidate buffer in global memory. With an exact running threshold a query appends
+// about kc * (1 + ln(rows / kc)) rows over a whole scan; the threshold is refreshed every SCAN_REFRESH_STEP-ish
+// appends and several pairs of one query can be in flight, hence the slack. Overflow is not an error: the query
+// is handed to the exact re-scan.
+static int candidate_buffer_cap(int kc) {
+    int c = 32 * kc;
+    if (c < 1024) c = 1024;
+    if (c > 65536) c = 65536;
+    return c;
+}
 
 static size_t scan_smem_bytes(int dp, int kc, int gq, int nq) {
-    size_t b = 512;                                                          // mbarriers + item descriptors
-    b += (size_t)SCAN_STAGES * SCAN_TV * SCAN_VP * sizeof(float);            // V ring
+    size_t b = SCAN_SMEM_HEADER;                                             // mbarriers + item descriptors
+    b += (size_t)SCAN_STAGES * SCAN_TV * SCAN_DC * sizeof(float);            // row ring (TMA, swizzled)
     b += (size_t)nq * gq * (dp + 4) * sizeof(float);                         // query-chunk ring
     b += (size_t)4 * gq * SCAN_KP * sizeof(uint32_t);                        // score keys: 2 groups x 2 buffers
-    b += (size_t)gq * kc * sizeof(uint64_t);                                 // sorted candidate arrays
-    return b;
+    b += (size_t)SCAN_SELECT_WARPS * 256 * sizeof(uint32_t);                 // radix-select histograms
+    (void)kc;
+    return b + 1024;                                                         // slack to align the base to 1 KB
 }
 
 static int make_plan(const qk_store_t* st, int64_t Q, int nprobe, int k, ScanPlan* p) {
@@ -94,6 +116,12 @@ static int make_plan(const qk_store_t* st, int64_t Q, int nprobe, int k, ScanPla
     while (gq > 1 && scan_smem_bytes(p->dp, p->kc, gq, 2) > SCAN_SMEM_LIMIT) gq >>= 1;
     QK_REQUIRE(scan_smem_bytes(p->dp, p->kc, gq, 2) <= SCAN_SMEM_LIMIT,
                "scan kernel shared memory exceeds 227 KB (k=%d d=%d)", k, st->d);
+    // enough work items for every SM: shrink the query chunk (down to 8) while the batch yields fewer than
+    // two items per SM (a coarse scan has one pair per query)
+    {
+        const int64_t est_pairs = Q * (int64_t)p->P;
+        while (gq > 8 && (est_pairs + gq - 1) / gq < 2 * (int64_t)sm_count()) gq >>= 1;
+    }
     p->gq = gq;
     p->nq = 2;
     while (p->nq < SCAN_MAX_NQ && scan_smem_bytes(p->dp, p->kc, gq, p->nq + 1) <= SCAN_SMEM_LIMIT) p->nq++;
@@ -106,15 +134,16 @@ static int make_plan(const qk_store_t* st, int64_t Q, int nprobe, int k, ScanPla
     p->off_seg_count = o;  o = align_up(o + (S + 1) * 4, 256);
     p->off_seg_fill = o;   o = align_up(o + (S + 1) * 4, 256);
     p->off_flags = o;      o = align_up(o + (size_t)Q * 4, 256);
+    p->off_qcount = o;     o = align_up(o + (size_t)Q * 4, 256);
     p->off_ctrl = o;       o = align_up(o + 64, 256);
     p->off_seg_start = o;  o = align_up(o + (S + 1) * 4, 256);
     p->off_item_start = o; o = align_up(o + (S + 1) * 4, 256);
     p->off_seg_pairs = o;  o = align_up(o + QP * 4, 256);
     size_t max_items = QP / gq + (QP < S ? QP : S) + 1;
-    p->off_items = o;      o = align_up(o + max_items * 8, 256);
+    p->off_items = o;      o = align_up(o + max_items * sizeof(WorkItem), 256);
     p->off_gthr = o;       o = align_up(o + (size_t)Q * 4, 256);
-    p->off_cand_n = o;     o = align_up(o + QP * 4, 256);
-    p->off_cand = o;       o = align_up(o + QP * p->kc * 8, 256);
+    p->qcap = candidate_buffer_cap(p->kc);
+    p->off_qbuf = o;       o = align_up(o + (size_t)Q * p->qcap * 8, 256);
     p->total = o;
     return QK_OK;
 }
@@ -219,7 +248,8 @@ __global__ void __launch_bounds__(1024) prefix_segments_kernel(const int32_t* __
 __global__ void scatter_pairs_kernel(const int32_t* __restrict__ pair_seg, int64_t QP, int S,
                                      const int32_t* __restrict__ seg_start, int32_t* __restrict__ seg_fill,
                                      int32_t* __restrict__ seg_pairs, const int32_t* __restrict__ item_start,
-                                     int2* __restrict__ items) {
+                                     const int64_t* __restrict__ seg_row0, const int32_t* __restrict__ seg_rows, int gq,
+                                     WorkItem* __restrict__ items) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < QP) {
         int seg = pair_seg[i];
@@ -229,211 +259,164 @@ __global__ void scatter_pairs_kernel(const int32_t* __restrict__ pair_seg, int64
         }
     }
     if (i < S) {
-        int b = item_start[i], e = item_start[i + 1];
-        for (int c = b; c < e; ++c) items[c] = make_int2((int)i, c - b);
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// warp-resident sorted arrays (ascending composite keys), blocked layout: lane holds E consecutive
-// elements. insert() requires c < current maximum.
-// ------------------------------------------------------------------------------------------------
-template <int E>
-__device__ __forceinline__ void warp_insert(uint64_t (&a)[E], uint64_t c, int lane) {
-    int cnt = 0;
-#pragma unroll
-    for (int e = 0; e < E; ++e) cnt += (a[e] < c) ? 1 : 0;
-    unsigned open = __ballot_sync(0xffffffffu, cnt < E);
-    uint64_t carry = a[E - 1];
-    {
-        uint32_t lo = __shfl_up_sync(0xffffffffu, (uint32_t)carry, 1);
-        uint32_t hi = __shfl_up_sync(0xffffffffu, (uint32_t)(carry >> 32), 1);
-        carry = ((uint64_t)hi << 32) | lo;
-    }
-    if (open == 0) return;
-    const int li = __ffs(open) - 1;
-    if (lane > li) {
-#pragma unroll
-        for (int e = E - 1; e >= 1; --e) a[e] = a[e - 1];
-        a[0] = carry;
-    } else if (lane == li) {
-#pragma unroll
-        for (int e = E - 1; e >= 0; --e) {
-            if (e > cnt) a[e] = a[e - 1 < 0 ? 0 : e - 1];
-            else if (e == cnt) a[e] = c;
+        const int b = item_start[i], e = item_start[i + 1];
+        if (e > b) {
+            const int p0 = seg_start[i], p1 = seg_start[i + 1];
+            WorkItem w;
+            w.seg = (int)i;
+            w.nrows = seg_rows[i];
+            w.row0 = seg_row0[i];
+            w.pad_ = 0;
+            for (int c = b; c < e; ++c) {
+                w.g_begin = p0 + (c - b) * gq;
+                w.g_cnt = min(gq, p1 - w.g_begin);
+                items[c] = w;
+            }
         }
     }
 }
 
-template <int E>
-__device__ __forceinline__ uint64_t warp_element(const uint64_t (&a)[E], int idx) {
-    const int src = idx / E, slot = idx % E;
-    uint64_t v = a[0];
+// ------------------------------------------------------------------------------------------------
+// running per-query filter threshold
+// ------------------------------------------------------------------------------------------------
+// kc-th smallest 32-bit filter key among buf[0..n) (composite entries key << 32 | row, read past L1), by a
+// warp-level radix select: 4 passes, 256-bin histogram in shared memory. Slots that were reserved but not
+// yet written hold 0xff..ff and count as +inf, so the result is always a valid upper bound on the kc-th
+// smallest key of everything appended so far. Returns KEY_MAX while fewer than kc entries are visible.
+template <typename KeyAt>
+__device__ __forceinline__ uint32_t radix_select(KeyAt key_at, int n, int kc, uint32_t* hist, int lane) {
+    if (n < kc) return KEY_MAX;
+    uint32_t prefix = 0;
+    int need = kc;  // rank (1-based) of the wanted key among the keys matching `prefix` so far
+    for (int pass = 3; pass >= 0; --pass) {
 #pragma unroll
-    for (int e = 1; e < E; ++e)
-        if (slot == e) v = a[e];
-    return shfl_u64(v, src);
-}
-
-// generic (any n) insertion into a shared-memory sorted array, warp-cooperative
-__device__ __forceinline__ void smem_insert(uint64_t* arr, int n, uint64_t c, int lane) {
-    int lo = 0, hi = n - 1;  // arr[n-1] > c guaranteed
-    while (lo < hi) {
-        int mid = (lo + hi) >> 1;
-        if (arr[mid] > c) hi = mid; else lo = mid + 1;
-    }
-    const int p = lo;
-    for (int base = n - 1; base > p; base -= 32) {
-        int i = base - lane;
-        uint64_t v = 0;
-        bool act = i > p;
-        if (act) v = arr[i - 1];
+        for (int b = 0; b < 8; ++b) hist[lane * 8 + b] = 0;
         __syncwarp();
-        if (act) arr[i] = v;
+        const int sh = 8 * pass;
+        for (int i = lane; i < n; i += 32) {
+            const uint32_t key = key_at(i);
+            const bool match = (pass == 3) || ((key >> (sh + 8)) == (prefix >> (sh + 8)));
+            if (match) atomicAdd(&hist[(key >> sh) & 255u], 1u);
+        }
+        __syncwarp();
+        uint32_t h[8], sum = 0;  // lane l owns bins 8l..8l+7
+#pragma unroll
+        for (int b = 0; b < 8; ++b) { h[b] = hist[lane * 8 + b]; sum += h[b]; }
+        uint32_t incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += y;
+        }
+        const uint32_t excl = incl - sum;
+        const unsigned owner = __ballot_sync(0xffffffffu, incl >= (uint32_t)need);
+        const int ol = __ffs(owner) - 1;  // first lane whose cumulative count reaches `need`
+        int bin = 0;
+        uint32_t before = excl;
+        if (lane == ol) {
+#pragma unroll
+            for (int b = 0; b < 8; ++b) {
+                if (before + h[b] >= (uint32_t)need) { bin = lane * 8 + b; break; }
+                before += h[b];
+            }
+        }
+        bin = __shfl_sync(0xffffffffu, bin, ol);
+        before = __shfl_sync(0xffffffffu, before, ol);
+        prefix |= (uint32_t)bin << sh;
+        need -= (int)before;
         __syncwarp();
     }
-    if (lane == 0) arr[p] = c;
-    __syncwarp();
+    return prefix;
 }
 
 // ------------------------------------------------------------------------------------------------
 // 4. the scan (filter) kernel
 // ------------------------------------------------------------------------------------------------
 struct ScanArgs {
-    const float* vecs;
     const float* norms;  // squared row norms (l2 only)
-    int64_t pitch;
     int dp;
-    const int64_t* seg_row0;
-    const int32_t* seg_rows;
     const float* queries;
     int64_t q_pitch;
-    const int32_t* seg_start;
     const int32_t* seg_pairs;
-    const int2* items;
+    const WorkItem* items;
     int32_t* ctrl;
-    uint32_t* gthr;
-    uint64_t* cand;
-    int32_t* cand_n;
+    uint32_t* gthr;    // [Q] running filter-key threshold of every query (upper bound on its kc-th best key)
+    int32_t* qcount;   // [Q] entries appended to the query's candidate buffer (may exceed qcap: overflow)
+    uint64_t* qbuf;    // [Q][qcap] candidates: key << 32 | arena row; unwritten slots are 0xff..ff
     int P, kc, gq, nq;
+    int qcap;
 };
 
-// process the keys of one tile for one query with a register-resident sorted array
-template <int E>
-__device__ __forceinline__ void select_tile(uint64_t* top_g, int kc, const uint32_t* keys, int tile_row0, int lane,
-                                            uint32_t& gthr_q, uint32_t* gthr_global) {
-    uint64_t a[E];
+// One d-chunk (<= 128 floats) of one 64-row tile for NT query slots per lane: 4 rows x NT queries x float4
+// per step. The rows sit in shared memory as the TMA engine wrote them with the 128-byte swizzle: sub-tile b
+// (32 floats = 128 B of every row) at b * 8 KB, row r at r * 128 B inside it, 16-byte chunk cc stored at
+// position cc ^ (r & 7). This lane's rows all have r & 7 == lr, so `lrx` = lr << 4 un-swizzles them.
+template <int NT>
+__device__ __forceinline__ void fma_chunk(float2 (&acc)[4][4], const unsigned char* __restrict__ vbase, uint32_t lrx,
+                                          const float4* __restrict__ qrow, int qstep, int dcur4) {
+    auto step = [&](int c, uint32_t off) {
+        float4 v[4], q[NT];
 #pragma unroll
-    for (int e = 0; e < E; ++e) {
-        int i = lane * E + e;
-        a[e] = (i < kc) ? top_g[i] : COMP_MAX;
-    }
-    uint64_t thr = warp_element<E>(a, kc - 1);
-    const uint64_t thr_in = thr;
-    bool changed = false;  // warp-uniform
+        for (int i = 0; i < 4; ++i) v[i] = *reinterpret_cast<const float4*>(vbase + i * 1024 + off);
 #pragma unroll
-    for (int j = 0; j < SCAN_TV / 32; ++j) {
-        const int r = j * 32 + lane;
-        const uint32_t key = keys[r];
-        const uint64_t comp = ((uint64_t)key << 32) | (uint32_t)(tile_row0 + r);
-        bool pass = (key != KEY_MAX) && (key <= gthr_q) && (comp < thr);
-        unsigned m = __ballot_sync(0xffffffffu, pass);
-        while (m) {
-            const int src = __ffs(m) - 1;
-            m &= m - 1;
-            const uint64_t c = shfl_u64(comp, src);
-            if (c < thr) {
-                warp_insert<E>(a, c, lane);
-                thr = warp_element<E>(a, kc - 1);
-                changed = true;
+        for (int t = 0; t < NT; ++t) q[t] = qrow[t * qstep + c];
+#pragma unroll
+        for (int t = 0; t < NT; ++t)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                acc[i][t] = ffma2(make_float2(v[i].x, v[i].y), make_float2(q[t].x, q[t].y), acc[i][t]);
+                acc[i][t] = ffma2(make_float2(v[i].z, v[i].w), make_float2(q[t].z, q[t].w), acc[i][t]);
             }
-        }
-    }
-    if (changed) {
+    };
+    int c = 0;
+    for (; c + 8 <= dcur4; c += 8) {
+        const uint32_t sub = (uint32_t)(c >> 3) * 8192u;
 #pragma unroll
-        for (int e = 0; e < E; ++e) {
-            int i = lane * E + e;
-            if (i < kc) top_g[i] = a[e];
-        }
-        if (thr != thr_in && thr != COMP_MAX) {
-            const uint32_t tk = (uint32_t)(thr >> 32);
-            if (tk < gthr_q) {
-                uint32_t old = 0;
-                if (lane == 0) old = atomicMin(gthr_global, tk);
-                old = __shfl_sync(0xffffffffu, old, 0);
-                gthr_q = old < tk ? old : tk;
-            }
-        }
-        __syncwarp();
+        for (int u = 0; u < 8; ++u) step(c + u, sub + (((uint32_t)u << 4) ^ lrx));
     }
+    for (; c < dcur4; ++c) step(c, (uint32_t)(c >> 3) * 8192u + ((((uint32_t)c & 7u) << 4) ^ lrx));
 }
 
-__device__ __forceinline__ void select_tile_generic(uint64_t* top_g, int kc, const uint32_t* keys, int tile_row0,
-                                                    int lane, uint32_t& gthr_q, uint32_t* gthr_global) {
-    uint64_t thr = top_g[kc - 1];
-    const uint64_t thr_in = thr;
-    for (int j = 0; j < SCAN_TV / 32; ++j) {
-        const int r = j * 32 + lane;
-        const uint32_t key = keys[r];
-        const uint64_t comp = ((uint64_t)key << 32) | (uint32_t)(tile_row0 + r);
-        bool pass = (key != KEY_MAX) && (key <= gthr_q) && (comp < thr);
-        unsigned m = __ballot_sync(0xffffffffu, pass);
-        while (m) {
-            const int src = __ffs(m) - 1;
-            m &= m - 1;
-            const uint64_t c = shfl_u64(comp, src);
-            if (c < thr) {
-                smem_insert(top_g, kc, c, lane);
-                thr = top_g[kc - 1];
-            }
-        }
-    }
-    if (thr != thr_in && thr != COMP_MAX) {
-        const uint32_t tk = (uint32_t)(thr >> 32);
-        if (tk < gthr_q) {
-            uint32_t old = 0;
-            if (lane == 0) old = atomicMin(gthr_global, tk);
-            old = __shfl_sync(0xffffffffu, old, 0);
-            gthr_q = old < tk ? old : tk;
-        }
-    }
-}
-
-// Shared-memory map (dynamic):
-//   [0, 512)        mbarriers: full[4] empty[4] qfull[4] qempty[4] kfull[2][2] kempty[2][2]; ItemDesc[4] at +256
-//   Vs   [STAGES][TV][VP] f32      row ring, one stage = one tile x one d-chunk
-//   Qs   [nq][gq][dp+4]   f32      query-chunk ring, one slot per work item in flight
+// Shared-memory map (dynamic, 1 KB aligned):
+//   [0, 2048)       mbarriers: full[4] empty[4] qfull[4] qempty[4] kfull[2][2] kempty[2][2]; ItemDesc[4] at +256
+//   Vs   [STAGES][4][TV][32] f32   row ring, one stage = one 64-row tile x one d-chunk of <= 128 floats, written
+//                                  by TMA tensor copies (box 64 rows x 128 B, 128-byte swizzle)
+//   Qs   [nq][gq][dp+4]   f32      query-chunk ring, one slot per work item in flight (cp.async gathers)
 //   Ks   [2 groups][2][gq][KP] u32 score keys
-//   top  [gq][kc] u64              per-query sorted candidate arrays of the current item (select warps only)
+//   hist [select warps][256] u32   radix-select histograms
 //
-// Roles: warps 0-3 compute group 0 (even tiles), warps 4-7 compute group 1 (odd tiles), warps 8-11 select,
-// warp 12 producer. Inside a compute group, warp gw covers rows rb*32.. (rb = gw & 1) x query half qh = gw >> 1;
-// lane (lr = lane & 7, lq = lane >> 3) owns rows rb*32 + lr + 8i (i < 4) and queries qh + 2*(lq + 4t) (t < 4), so
-// every shared-memory load is one wavefront (8 distinct rows or 4 distinct queries, the rest broadcast).
+// Roles: warps 0-3 compute group 0 (even tiles), warps 4-7 compute group 1 (odd tiles), warps 8-14 select
+// (warp sw owns queries sw, sw+7, ...), warp 15 producer. Inside a compute group, warp gw covers rows rb*32..
+// (rb = gw & 1) x query half qh = gw >> 1; lane (lr = lane & 7, lq = lane >> 3) owns rows rb*32 + lr + 8i (i < 4)
+// and queries qh + 2*(lq + 4t) (t < 4), so every shared-memory load is one wavefront (8 distinct rows or 4
+// distinct queries, the rest broadcast).
 template <bool kIP>
-__global__ void __launch_bounds__(SCAN_THREADS, 1) scan_kernel(const ScanArgs a) {
-    constexpr int TV = SCAN_TV, DC = SCAN_DC, VP = SCAN_VP, KP = SCAN_KP, NS = SCAN_STAGES;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
+__global__ void __launch_bounds__(SCAN_THREADS, 1) scan_kernel(const ScanArgs a, const __grid_constant__ CUtensorMap vmap) {
+    constexpr int TV = SCAN_TV, DC = SCAN_DC, KP = SCAN_KP, NS = SCAN_STAGES;
+    constexpr int STAGE_BYTES = TV * DC * 4;  // 32 KB
+    extern __shared__ __align__(16) unsigned char smem_dyn[];
+    // the 128-byte TMA swizzle is a function of the shared-memory address: align the map to 1 KB
+    unsigned char* smem_raw = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
     uint64_t* full = bars;             // [NS]   producer -> compute (tx)
     uint64_t* empty = bars + 4;        // [NS]   compute  -> producer (4 warps of the owning group)
-    uint64_t* qfull = bars + 8;        // [nq]   producer -> all consumers (tx + descriptor)
-    uint64_t* qempty = bars + 12;      // [nq]   12 consumer warps -> producer
-    uint64_t* kfull = bars + 16;       // [2][2] compute group -> select (4 warps)
-    uint64_t* kempty = bars + 20;      // [2][2] select (4 warps) -> compute group
+    uint64_t* qfull = bars + 8;        // [nq]   producer (32 lanes, after their cp.async landed) -> consumers
+    uint64_t* qempty = bars + 12;      // [nq]   15 consumer warps -> producer
+    uint64_t* kfull = bars + 16;       // [2][2] compute group (4 warps) -> select
+    uint64_t* kempty = bars + 20;      // [2][2] select (7 warps) -> compute group
     ItemDesc* descs = reinterpret_cast<ItemDesc*>(smem_raw + 256);  // [SCAN_MAX_NQ]
-    float* Vs = reinterpret_cast<float*>(smem_raw + 512);
+    unsigned char* Vs = smem_raw + SCAN_SMEM_HEADER;
     const int dp = a.dp, kc = a.kc, gq = a.gq, nq = a.nq;
     const int QP = dp + 4;
-    float* Qs = Vs + (size_t)NS * TV * VP;
+    float* Qs = reinterpret_cast<float*>(Vs + (size_t)NS * STAGE_BYTES);
     uint32_t* Ks = reinterpret_cast<uint32_t*>(Qs + (size_t)nq * gq * QP);
-    uint64_t* top = reinterpret_cast<uint64_t*>(Ks + (size_t)4 * gq * KP);
+    uint32_t* hists = Ks + (size_t)4 * gq * KP;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) {
         for (int s = 0; s < NS; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 4); }
         for (int s = 0; s < SCAN_MAX_NQ; ++s) {
-            mbar_init(qfull + s, 1);
+            mbar_init(qfull + s, 32);
             mbar_init(qempty + s, SCAN_COMPUTE_WARPS + SCAN_SELECT_WARPS);
         }
         for (int s = 0; s < 4; ++s) { mbar_init(kfull + s, 4); mbar_init(kempty + s, SCAN_SELECT_WARPS); }
@@ -444,113 +427,187 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) scan_kernel(const ScanArgs a)
 
     if (warp == SCAN_COMPUTE_WARPS + SCAN_SELECT_WARPS) {
         // ===================================================================== producer warp
+        // Software-pipelined over work items so that the dependent metadata loads (work counter -> item ->
+        // pair ids -> thresholds) of the next items are in flight while the current item is issued:
+        //   it3: index reserved for item n+3      m2: WorkItem of item n+2
+        //   m1 + pair1: item n+1 and its pair ids  m0 + pair0 + gthr0: item n, complete
         const int n_items = a.ctrl[1];
-        uint32_t U = 0;
-        for (uint32_t n = 0;; ++n) {
-            const int ib = n % nq;
-            mbar_wait(qempty + ib, ((n / nq) & 1u) ^ 1u);
+        auto fetch_index = [&]() {
             int it = 0;
             if (lane == 0) it = atomicAdd(&a.ctrl[0], 1);
-            it = __shfl_sync(0xffffffffu, it, 0);
-            if (it >= n_items) {
-                if (lane == 0) {
-                    descs[ib].seg = -1;
-                    mbar_arrive(qfull + ib);
-                }
+            return __shfl_sync(0xffffffffu, it, 0);
+        };
+        auto fetch_item = [&](int it) {
+            WorkItem w;
+            w.seg = -1; w.g_begin = 0; w.g_cnt = 0; w.nrows = 0; w.row0 = 0; w.pad_ = 0;
+            if (it < n_items) w = a.items[it];
+            return w;
+        };
+        auto fetch_pair = [&](const WorkItem& w) { return (w.seg >= 0 && lane < w.g_cnt) ? a.seg_pairs[w.g_begin + lane] : -1; };
+        // thresholds move during the kernel (atomicMin from every SM): read them past the non-coherent L1
+        auto fetch_gthr = [&](int pair) { return pair >= 0 ? __ldcg(a.gthr + pair / a.P) : KEY_MAX; };
+        WorkItem m0 = fetch_item(fetch_index());
+        WorkItem m1 = fetch_item(fetch_index());
+        WorkItem m2 = fetch_item(fetch_index());
+        int pair0 = fetch_pair(m0);
+        int pair1 = fetch_pair(m1);
+        uint32_t gthr0 = fetch_gthr(pair0);
+        uint32_t U = 0;
+        const int dp4 = dp >> 2;
+        for (uint32_t n = 0;; ++n) {
+            const int ib = n % nq;
+            const int it3 = fetch_index();
+            mbar_wait(qempty + ib, ((n / nq) & 1u) ^ 1u);
+            if (m0.seg < 0) {
+                if (lane == 0) descs[ib].w.seg = -1;
+                __syncwarp();
+                mbar_arrive(qfull + ib);  // all 32 lanes
                 break;
             }
-            const int2 item = a.items[it];
-            const int seg = item.x;
-            const int g_begin = a.seg_start[seg] + item.y * gq;
-            int g_cnt = a.seg_start[seg + 1] - g_begin;
-            g_cnt = g_cnt < gq ? g_cnt : gq;
-            const int64_t row0 = a.seg_row0[seg];
-            const int nrows = a.seg_rows[seg];
-            if (lane == 0) {
-                ItemDesc d;
-                d.seg = seg; d.g_begin = g_begin; d.g_cnt = g_cnt; d.nrows = nrows; d.row0 = row0;
-                descs[ib] = d;
-                mbar_expect_tx(qfull + ib, (uint32_t)(g_cnt * dp * 4));
-            }
-            __syncwarp();
-            if (lane < g_cnt) {
-                const int pair = a.seg_pairs[g_begin + lane];
-                const int64_t q = pair / a.P;
-                bulk_g2s(Qs + ((size_t)ib * gq + lane) * QP, a.queries + q * a.q_pitch, (uint32_t)(dp * 4), qfull + ib);
+            const int g_cnt = m0.g_cnt, nrows = m0.nrows;
+            const int64_t row0 = m0.row0;
+            descs[ib].pair[lane] = pair0;
+            descs[ib].gthr[lane] = gthr0;
+            if (lane == 0) descs[ib].w = m0;
+            __threadfence_block();  // the descriptor is published by the (asynchronous) arrivals below
+            // gather the item's query rows (16-byte cp.async, L2 only); the slot's barrier counts one arrival
+            // per lane, delivered when that lane's copies have landed
+            {
+                float* qdst = Qs + (size_t)ib * gq * QP;
+                for (int g = 0; g < g_cnt; ++g) {
+                    const int64_t q = __shfl_sync(0xffffffffu, pair0, g) / a.P;
+                    const float* src = a.queries + q * a.q_pitch;
+                    for (int c = lane; c < dp4; c += 32) cp_async16(qdst + (size_t)g * QP + 4 * c, src + 4 * c);
+                }
+                cp_async_mbar_arrive_noinc(qfull + ib);
             }
             const int ntiles = (nrows + TV - 1) / TV;
             for (int tile = 0; tile < ntiles; ++tile) {
-                const int tr = min(TV, nrows - tile * TV);
                 for (int dc = 0; dc < ndc; ++dc, ++U) {
                     const int st = U % NS;
                     mbar_wait(empty + st, ((U / NS) & 1u) ^ 1u);
-                    const int dcur = min(DC, dp - dc * DC);
-                    if (lane == 0) mbar_expect_tx(full + st, (uint32_t)(tr * dcur * 4));
+                    if (lane == 0) {
+                        const int dcur = min(DC, dp - dc * DC);
+                        const int nbox = (dcur + 31) >> 5;
+                        mbar_expect_tx(full + st, (uint32_t)(nbox * TV * 128));
+                        for (int b = 0; b < nbox; ++b)
+                            tma_load_2d(Vs + (size_t)st * STAGE_BYTES + (size_t)b * (TV * 128), &vmap, dc * DC + b * 32,
+                                        (int)(row0 + (int64_t)tile * TV), full + st);
+                    }
                     __syncwarp();
-                    for (int r = lane; r < tr; r += 32)
-                        bulk_g2s(Vs + ((size_t)st * TV + r) * VP,
-                                 a.vecs + (row0 + (int64_t)tile * TV + r) * a.pitch + dc * DC, (uint32_t)(dcur * 4),
-                                 full + st);
                 }
             }
+            // rotate the pipeline; the thresholds of the next item are read as late as possible
+            const int pair2 = fetch_pair(m2);
+            m0 = m1; pair0 = pair1;
+            m1 = m2; pair1 = pair2;
+            m2 = fetch_item(it3);
+            gthr0 = fetch_gthr(pair0);
         }
     } else if (warp >= SCAN_COMPUTE_WARPS) {
         // ===================================================================== select warps
+        // Every key at or below its query's running threshold is appended to the query's candidate buffer in
+        // global memory (one atomicAdd per (query, tile), all of the warp's queries in one instruction). Each
+        // time a query's fill passes a multiple of `step`, the warp that crossed it re-derives the threshold
+        // (kc-th smallest key appended so far) and publishes it with atomicMin.
+        constexpr int NSEL = SCAN_SELECT_WARPS;
         const int sw = warp - SCAN_COMPUTE_WARPS;
+        uint32_t* hist = hists + sw * 256;
+        const int qcap = a.qcap;
+        const int step = kc > 64 ? kc : 64;
+        const unsigned below = (1u << lane) - 1u;
         uint32_t T = 0;
         for (uint32_t n = 0;; ++n) {
             const int ib = n % nq;
             mbar_wait(qfull + ib, (n / nq) & 1u);
-            const ItemDesc d = descs[ib];
+            const WorkItem d = descs[ib].w;
             if (d.seg < 0) break;
-            // lane j < 8 keeps the (pair, threshold) of query g = sw + 4j
-            int my_pair = -1;
-            uint32_t my_gthr = KEY_MAX;
+            // lane j keeps the state of query slot g = sw + NSEL*j: query index and threshold
+            int my_q = -1;
+            uint32_t my_lim = 0;
             {
-                const int g = sw + 4 * lane;
-                if (lane < 8 && g < d.g_cnt) {
-                    my_pair = a.seg_pairs[d.g_begin + g];
-                    my_gthr = a.gthr[my_pair / a.P];
+                const int g = sw + NSEL * lane;
+                if (g < d.g_cnt) {
+                    my_q = descs[ib].pair[g] / a.P;
+                    const uint32_t t = descs[ib].gthr[g];
+                    my_lim = t < KEY_MAX ? t : KEY_MAX - 1;  // KEY_MAX marks an invalid row
                 }
             }
-            for (int g = sw; g < d.g_cnt; g += 4)
-                for (int i = lane; i < kc; i += 32) top[(size_t)g * kc + i] = COMP_MAX;
-            __syncwarp();
             const int ntiles = (d.nrows + TV - 1) / TV;
             for (int tile = 0; tile < ntiles; ++tile, ++T) {
                 const int grp = T & 1u, kb = (T >> 1) & 1u;
+                // what every other SM has learnt about my queries meanwhile (used from the next tile on)
+                const uint32_t g_now = my_q >= 0 ? __ldcg(a.gthr + my_q) : 0u;
                 mbar_wait(kfull + grp * 2 + kb, (T >> 2) & 1u);
                 const uint32_t* kbase = Ks + (size_t)(grp * 2 + kb) * gq * KP;
-                for (int j = 0; sw + 4 * j < d.g_cnt; ++j) {
-                    const int g = sw + 4 * j;
-                    uint32_t gthr_q = __shfl_sync(0xffffffffu, my_gthr, j);
-                    const int pair = __shfl_sync(0xffffffffu, my_pair, j);
-                    uint32_t* gthr_global = a.gthr + pair / a.P;
-                    if (kc <= 32)
-                        select_tile<1>(top + (size_t)g * kc, kc, kbase + g * KP, tile * TV, lane, gthr_q, gthr_global);
-                    else if (kc <= 128)
-                        select_tile<4>(top + (size_t)g * kc, kc, kbase + g * KP, tile * TV, lane, gthr_q, gthr_global);
-                    else
-                        select_tile_generic(top + (size_t)g * kc, kc, kbase + g * KP, tile * TV, lane, gthr_q, gthr_global);
-                    if (lane == j) my_gthr = gthr_q;
+                // phase 1: pass masks of all my queries (independent loads / ballots)
+                unsigned mym0 = 0, mym1 = 0;
+                for (int j = 0; sw + NSEL * j < d.g_cnt; ++j) {
+                    const int g = sw + NSEL * j;
+                    uint32_t lim = __shfl_sync(0xffffffffu, my_lim, j);
+                    const uint32_t k0 = kbase[g * KP + lane], k1 = kbase[g * KP + 32 + lane];
+                    unsigned m0 = __ballot_sync(0xffffffffu, k0 <= lim);
+                    unsigned m1 = __ballot_sync(0xffffffffu, k1 <= lim);
+                    if (kc <= 48 && __popc(m0) + __popc(m1) > kc + 8) {
+                        // a loose (stale or missing) threshold: this tile alone bounds the kc-th best key
+                        const uint32_t* kq = kbase + g * KP;
+                        const uint32_t t = radix_select([kq](int i) { return kq[i]; }, TV, kc, hist, lane);
+                        if (t < lim) {
+                            lim = t;
+                            m0 = __ballot_sync(0xffffffffu, k0 <= lim);
+                            m1 = __ballot_sync(0xffffffffu, k1 <= lim);
+                            if (lane == 0) atomicMin(a.gthr + descs[ib].pair[g] / a.P, lim);
+                        }
+                    }
+                    if (lane == j) { mym0 = m0; mym1 = m1; my_lim = lim; }
+                }
+                // phase 2: reserve buffer slots, one atomic per query with at least one passing key
+                const int nn = __popc(mym0) + __popc(mym1);
+                int base = 0;
+                if (nn > 0) base = atomicAdd(&a.qcount[my_q], nn);
+                unsigned todo = __ballot_sync(0xffffffffu, nn > 0);
+                unsigned cross = 0;  // queries whose fill passed a multiple of `step`
+                // phase 3: write the entries
+                const uint32_t arow0 = (uint32_t)(d.row0 + (int64_t)tile * TV);
+                while (todo) {
+                    const int j = __ffs(todo) - 1;
+                    todo &= todo - 1;
+                    const int g = sw + NSEL * j;
+                    const unsigned m0 = __shfl_sync(0xffffffffu, mym0, j), m1 = __shfl_sync(0xffffffffu, mym1, j);
+                    const int b = __shfl_sync(0xffffffffu, base, j);
+                    const int q = __shfl_sync(0xffffffffu, my_q, j);
+                    uint64_t* qb = a.qbuf + (size_t)q * qcap;
+                    const int c0 = __popc(m0), c1 = __popc(m1);
+                    if ((m0 >> lane) & 1u) {
+                        const int slot = b + __popc(m0 & below);
+                        if (slot < qcap) qb[slot] = ((uint64_t)kbase[g * KP + lane] << 32) | (arow0 + lane);
+                    }
+                    if ((m1 >> lane) & 1u) {
+                        const int slot = b + c0 + __popc(m1 & below);
+                        if (slot < qcap) qb[slot] = ((uint64_t)kbase[g * KP + 32 + lane] << 32) | (arow0 + 32 + lane);
+                    }
+                    const int e = b + c0 + c1;
+                    if (b / step != e / step && e >= kc) cross |= 1u << j;
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(kempty + grp * 2 + kb);
-            }
-            // emit the per-(query, segment) candidates
-            for (int j = 0; sw + 4 * j < d.g_cnt; ++j) {
-                const int g = sw + 4 * j;
-                const int pair = __shfl_sync(0xffffffffu, my_pair, j);
-                const uint64_t* tg = top + (size_t)g * kc;
-                uint64_t* out = a.cand + (size_t)pair * kc;
-                int cnt = 0;
-                for (int base = 0; base < kc; base += 32) {
-                    int i = base + lane;
-                    uint64_t v = (i < kc) ? tg[i] : COMP_MAX;
-                    if (v != COMP_MAX) out[i] = v;
-                    cnt += __popc(__ballot_sync(0xffffffffu, v != COMP_MAX));
+                // phase 4 (key buffer already released): refresh the thresholds of the queries that crossed.
+                // The entries this warp just stored are read back by other lanes: order them first.
+                if (cross) __threadfence();
+                while (cross) {
+                    const int j = __ffs(cross) - 1;
+                    cross &= cross - 1;
+                    const int q = __shfl_sync(0xffffffffu, my_q, j);
+                    const int fill = __shfl_sync(0xffffffffu, base + nn, j);
+                    const unsigned long long* qb = reinterpret_cast<const unsigned long long*>(a.qbuf) + (size_t)q * qcap;
+                    const uint32_t t = radix_select([qb](int i) { return (uint32_t)(__ldcg(qb + i) >> 32); },
+                                                    fill < qcap ? fill : qcap, kc, hist, lane);
+                    if (t < KEY_MAX) {
+                        if (lane == 0) atomicMin(a.gthr + q, t);
+                        if (lane == j && t < my_lim) my_lim = t;
+                    }
                 }
-                if (lane == 0) a.cand_n[pair] = cnt;
+                if (g_now < my_lim) my_lim = g_now;
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(qempty + ib);
@@ -560,17 +617,19 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) scan_kernel(const ScanArgs a)
         const int grp = warp >> 2, gw = warp & 3;
         const int rb = gw & 1, qh = gw >> 1;
         const int lr = lane & 7, lq = lane >> 3;
+        const uint32_t lrx = (uint32_t)lr << 4;
         uint32_t T = 0, U = 0;
         for (uint32_t n = 0;; ++n) {
             const int ib = n % nq;
             mbar_wait(qfull + ib, (n / nq) & 1u);
-            const ItemDesc d = descs[ib];
+            const WorkItem d = descs[ib].w;
             if (d.seg < 0) break;
             const int g_cnt = d.g_cnt;
             // queries of this lane: g = qh + 2*(lq + 4t); t < nt is warp-uniform
             const int jmax = (g_cnt - qh + 1) >> 1;            // number of j = lq + 4t with g < g_cnt
             const int nt = (jmax + 3) >> 2;                    // 0..4
             const float* qbase = Qs + ((size_t)ib * gq + qh + 2 * lq) * QP;
+            const int qstep = 8 * QP / 4;                      // float4 stride between this lane's queries
             const int ntiles = (d.nrows + TV - 1) / TV;
             for (int tile = 0; tile < ntiles; ++tile, ++T, U += ndc) {
                 if ((int)(T & 1u) != grp) continue;
@@ -593,44 +652,14 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) scan_kernel(const ScanArgs a)
                     const int st = u % NS;
                     mbar_wait(full + st, (u / NS) & 1u);
                     const int dcur4 = min(DC, dp - dc * DC) >> 2;
-                    const float4* vrow = reinterpret_cast<const float4*>(Vs + ((size_t)st * TV + rb * 32 + lr) * VP);
+                    const unsigned char* vbase = Vs + (size_t)st * STAGE_BYTES + (size_t)(rb * 32 + lr) * 128;
                     const float4* qrow = reinterpret_cast<const float4*>(qbase + dc * DC);
-                    constexpr int VSTEP = 8 * VP / 4;          // float4 stride between this lane's rows
-                    const int qstep = 8 * QP / 4;              // float4 stride between this lane's queries
-                    if (nt == 4) {
-#pragma unroll 4
-                        for (int c = 0; c < dcur4; ++c) {
-                            float4 v[4], q[4];
-#pragma unroll
-                            for (int i = 0; i < 4; ++i) v[i] = vrow[i * VSTEP + c];
-#pragma unroll
-                            for (int t = 0; t < 4; ++t) q[t] = qrow[t * qstep + c];
-#pragma unroll
-                            for (int t = 0; t < 4; ++t)
-#pragma unroll
-                                for (int i = 0; i < 4; ++i) {
-                                    acc[i][t] = ffma2(make_float2(v[i].x, v[i].y), make_float2(q[t].x, q[t].y), acc[i][t]);
-                                    acc[i][t] = ffma2(make_float2(v[i].z, v[i].w), make_float2(q[t].z, q[t].w), acc[i][t]);
-                                }
-                        }
-                    } else if (nt >= 1) {
-#pragma unroll 2
-                        for (int c = 0; c < dcur4; ++c) {
-                            float4 v[4];
-#pragma unroll
-                            for (int i = 0; i < 4; ++i) v[i] = vrow[i * VSTEP + c];
-#pragma unroll
-                            for (int t = 0; t < 3; ++t) {
-                                if (t < nt) {
-                                    const float4 q4 = qrow[t * qstep + c];
-#pragma unroll
-                                    for (int i = 0; i < 4; ++i) {
-                                        acc[i][t] = ffma2(make_float2(v[i].x, v[i].y), make_float2(q4.x, q4.y), acc[i][t]);
-                                        acc[i][t] = ffma2(make_float2(v[i].z, v[i].w), make_float2(q4.z, q4.w), acc[i][t]);
-                                    }
-                                }
-                            }
-                        }
+                    switch (nt) {
+                        case 1: fma_chunk<1>(acc, vbase, lrx, qrow, qstep, dcur4); break;
+                        case 2: fma_chunk<2>(acc, vbase, lrx, qrow, qstep, dcur4); break;
+                        case 3: fma_chunk<3>(acc, vbase, lrx, qrow, qstep, dcur4); break;
+                        case 4: fma_chunk<4>(acc, vbase, lrx, qrow, qstep, dcur4); break;
+                        default: break;
                     }
                     __syncwarp();
                     if (lane == 0) mbar_arrive(empty + st);
@@ -701,8 +730,9 @@ struct MergeArgs {
     int64_t q_pitch;
     const int32_t* pair_seg;
     const uint32_t* gthr;
-    const uint64_t* cand;
-    const int32_t* cand_n;
+    const uint64_t* qbuf;
+    const int32_t* qcount;
+    int qcap;
     int32_t* flags;
     int32_t* ctrl;
     int P, kc, k;
@@ -738,22 +768,23 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_refine_kernel(const Merge
         s_qn = s;
     }
 
-    // ---- gather survivors: emitted candidates whose filter key is within the final threshold
+    // ---- gather survivors: appended candidates whose filter key is within the final threshold
     const uint32_t gthr = a.gthr[q];
-    bool overflow = false;
-    for (int j = tid; j < a.P; j += blockDim.x) {
-        const int seg = a.pair_seg[q * a.P + j];
-        if (seg < 0) continue;
-        const int64_t pair = q * a.P + j;
-        const int n = a.cand_n[pair];
-        const uint64_t r0 = (uint64_t)a.seg_row0[seg];
-        const uint64_t* c = a.cand + (size_t)pair * a.kc;
-        for (int i = 0; i < n; ++i) {
+    const int appended = a.qcount[q];
+    if (tid == 0) {  // statistics for qk_scan_partitions' `stats`
+        atomicMax(&a.ctrl[3], appended);
+        atomicAdd(reinterpret_cast<unsigned long long*>(a.ctrl + 4), (unsigned long long)appended);
+    }
+    bool overflow = appended > a.qcap;  // entries were dropped: only the exact re-scan can answer
+    {
+        const int n = appended < a.qcap ? appended : a.qcap;
+        const uint64_t* c = a.qbuf + (size_t)q * a.qcap;
+        for (int i = tid; i < n; i += blockDim.x) {
             const uint64_t v = c[i];
             const uint32_t key = (uint32_t)(v >> 32);
-            if (key > gthr) break;  // runs are sorted ascending
+            if (key > gthr || key == KEY_MAX) continue;
             const int pos = atomicAdd(&s_n, 1);
-            if (pos < MERGE_SORT_CAP) sbuf[pos] = ((uint64_t)key << 32) | (uint32_t)(r0 + (uint32_t)v);
+            if (pos < MERGE_SORT_CAP) sbuf[pos] = v;
             else overflow = true;
         }
     }
@@ -767,17 +798,23 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_refine_kernel(const Merge
         block_bitonic_sort(sbuf, np, [](uint64_t x, uint64_t y) { return x < y; });
         nc = ns < a.kc ? ns : a.kc;
         // ---- exact refine in the reference's summation order
-        for (int i = tid; i < kcp; i += blockDim.x) {
-            if (i < nc) {
-                const uint32_t row = (uint32_t)sbuf[i];
-                const float dist = ref_pair_distance<kIP>(qs, a.vecs + (int64_t)row * a.pitch, a.d);
-                // order by the value the reference orders by: sqrt'ed for l2 (list_scanning.h:260)
-                const uint32_t dk = f2key(kIP ? -dist : (a.rank_squared ? dist : __fsqrt_rn(dist)));
-                rkey[i] = ((uint64_t)dk << 32) | (uint32_t)i;
-                rid[i] = a.ids ? a.ids[row] : (int64_t)row;
-                rrow[i] = row;
-            } else {
-                rkey[i] = COMP_MAX;
+        // eight lanes per candidate, one per accumulator of the reference's 8-wide loop
+        for (int base = 0; base < kcp; base += MERGE_THREADS / 8) {
+            const int i = base + (tid >> 3), j = tid & 7;
+            if (i < kcp) {  // uniform inside every 8-lane group
+                if (i < nc) {
+                    const uint32_t row = (uint32_t)sbuf[i];
+                    const float dist = ref_pair_distance_g8<kIP>(qs, a.vecs + (int64_t)row * a.pitch, a.d, j);
+                    if (j == 0) {
+                        // order by the value the reference orders by: sqrt'ed for l2 (list_scanning.h:260)
+                        const uint32_t dk = f2key(kIP ? -dist : (a.rank_squared ? dist : __fsqrt_rn(dist)));
+                        rkey[i] = ((uint64_t)dk << 32) | (uint32_t)i;
+                        rid[i] = a.ids ? a.ids[row] : (int64_t)row;
+                        rrow[i] = row;
+                    }
+                } else if (j == 0) {
+                    rkey[i] = COMP_MAX;
+                }
             }
         }
         const int64_t* ridc = rid;
@@ -1050,16 +1087,49 @@ struct ProfileRecord {
 static ProfileRecord* g_prof = nullptr;
 static int g_prof_cap = 0, g_prof_n = 0;
 
-static int launch_scan(const ScanArgs& sa, int metric, size_t smem, cudaStream_t stream) {
+// Tensor map of the row arena for the scan kernel's TMA loads: [num_rows x pitch] f32, box = 64 rows x 32
+// floats (128 B), 128-byte swizzle, out-of-bounds elements read as zero.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static int make_row_tensor_map(const qk_store_t* st, CUtensorMap* out) {
+    static EncodeTiledFn encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        QK_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (!fn || qres != cudaDriverEntryPointSuccess) {
+            set_error("cuTensorMapEncodeTiled is not available from the CUDA driver");
+            return QK_ERR_CUDA;
+        }
+        encode = (EncodeTiledFn)fn;
+    }
+    QK_REQUIRE(st->num_rows > 0, "store.num_rows must be set");
+    cuuint64_t dims[2] = {(cuuint64_t)st->pitch, (cuuint64_t)st->num_rows};
+    cuuint64_t strides[1] = {(cuuint64_t)st->pitch * sizeof(float)};
+    cuuint32_t box[2] = {32u, (cuuint32_t)SCAN_TV};
+    cuuint32_t estr[2] = {1u, 1u};
+    CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)st->vectors, dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld pitch=%lld)", (int)r,
+                  (long long)st->num_rows, (long long)st->pitch);
+        return QK_ERR_CUDA;
+    }
+    return QK_OK;
+}
+
+static int launch_scan(const ScanArgs& sa, const CUtensorMap& vmap, int metric, size_t smem, cudaStream_t stream) {
     const int grid = sm_count();
     if (metric == QK_METRIC_INNER_PRODUCT) {
         auto kern = scan_kernel<true>;
         QK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, SCAN_THREADS, smem, stream>>>(sa);
+        kern<<<grid, SCAN_THREADS, smem, stream>>>(sa, vmap);
     } else {
         auto kern = scan_kernel<false>;
         QK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, SCAN_THREADS, smem, stream>>>(sa);
+        kern<<<grid, SCAN_THREADS, smem, stream>>>(sa, vmap);
     }
     QK_CUDA(cudaGetLastError());
     return QK_OK;
@@ -1117,15 +1187,16 @@ int qk::scan_partitions_impl(const qk_store_t* st, const float* queries, int64_t
     int32_t* seg_start = (int32_t*)(ws + p.off_seg_start);
     int32_t* item_start = (int32_t*)(ws + p.off_item_start);
     int32_t* seg_pairs = (int32_t*)(ws + p.off_seg_pairs);
-    int2* items = (int2*)(ws + p.off_items);
+    WorkItem* items = (WorkItem*)(ws + p.off_items);
     uint32_t* gthr = (uint32_t*)(ws + p.off_gthr);
-    int32_t* cand_n = (int32_t*)(ws + p.off_cand_n);
-    uint64_t* cand = (uint64_t*)(ws + p.off_cand);
+    int32_t* qcount = (int32_t*)(ws + p.off_qcount);
+    uint64_t* qbuf = (uint64_t*)(ws + p.off_qbuf);
     const int S = st->num_segments;
     const int64_t QP = Q * p.P;
 
-    // seg_count, seg_fill, flags, ctrl are contiguous: one memset
+    // seg_count, seg_fill, flags, qcount, ctrl are contiguous: one memset; candidate slots start as +inf
     QK_CUDA(cudaMemsetAsync(ws + p.off_seg_count, 0, p.off_seg_start - p.off_seg_count, stream));
+    QK_CUDA(cudaMemsetAsync(qbuf, 0xff, (size_t)Q * p.qcap * 8, stream));
     const bool single = (p.P == nprobe);
     if (single) {
         int64_t n = Q * nprobe;
@@ -1143,16 +1214,19 @@ int qk::scan_partitions_impl(const qk_store_t* st, const float* queries, int64_t
     {
         int64_t n = QP > S ? QP : S;
         scatter_pairs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(pair_seg, QP, S, seg_start, seg_fill,
-                                                                               seg_pairs, item_start, items);
+                                                                               seg_pairs, item_start, st->seg_row0,
+                                                                               st->seg_rows, p.gq, items);
         QK_CUDA(cudaGetLastError());
     }
     ScanArgs sa;
-    sa.vecs = st->vectors; sa.pitch = st->pitch; sa.dp = p.dp;
-    sa.seg_row0 = st->seg_row0; sa.seg_rows = st->seg_rows;
+    sa.norms = st->row_norms; sa.dp = p.dp;
     sa.queries = queries; sa.q_pitch = q_pitch;
-    sa.seg_start = seg_start; sa.seg_pairs = seg_pairs; sa.items = items; sa.ctrl = ctrl;
-    sa.gthr = gthr; sa.cand = cand; sa.cand_n = cand_n;
-    sa.P = p.P; sa.kc = p.kc; sa.gq = p.gq; sa.nq = p.nq;
+    sa.seg_pairs = seg_pairs; sa.items = items; sa.ctrl = ctrl;
+    sa.gthr = gthr; sa.qcount = qcount; sa.qbuf = qbuf;
+    sa.P = p.P; sa.kc = p.kc; sa.gq = p.gq; sa.nq = p.nq; sa.qcap = p.qcap;
+    CUtensorMap vmap;
+    rc = make_row_tensor_map(st, &vmap);
+    if (rc) return rc;
     sa.norms = st->row_norms;
     ProfileRecord* rec = nullptr;
     if (g_prof && g_prof_n < g_prof_cap) {
@@ -1160,14 +1234,14 @@ int qk::scan_partitions_impl(const qk_store_t* st, const float* queries, int64_t
         rec->queries = Q; rec->nprobe = nprobe; rec->k = k; rec->used = 1;
         QK_CUDA(cudaEventRecord(rec->start, stream));
     }
-    rc = launch_scan(sa, metric, p.smem, stream);
+    rc = launch_scan(sa, vmap, metric, p.smem, stream);
     if (rc) return rc;
     if (rec) QK_CUDA(cudaEventRecord(rec->stop, stream));
 
     MergeArgs ma;
     ma.vecs = st->vectors; ma.pitch = st->pitch; ma.ids = st->ids; ma.d = st->d;
     ma.seg_row0 = st->seg_row0; ma.queries = queries; ma.q_pitch = q_pitch;
-    ma.pair_seg = pair_seg; ma.gthr = gthr; ma.cand = cand; ma.cand_n = cand_n;
+    ma.pair_seg = pair_seg; ma.gthr = gthr; ma.qbuf = qbuf; ma.qcount = qcount; ma.qcap = p.qcap;
     ma.flags = flags; ma.ctrl = ctrl; ma.P = p.P; ma.kc = p.kc; ma.k = k;
     ma.max_row_norm = st->max_row_norm;
     ma.out_ids = out_ids; ma.out_dist = out_dist; ma.out_rows = out_rows;
@@ -1197,7 +1271,7 @@ int qk::scan_partitions_impl(const qk_store_t* st, const float* queries, int64_t
         }
         QK_CUDA(cudaGetLastError());
     }
-    if (stats) QK_CUDA(cudaMemcpyAsync(stats, ctrl + 2, sizeof(int32_t), cudaMemcpyDeviceToDevice, stream));
+    if (stats) QK_CUDA(cudaMemcpyAsync(stats, ctrl + 2, 4 * sizeof(int32_t), cudaMemcpyDeviceToDevice, stream));
     return QK_OK;
 }
 

@@ -25,6 +25,7 @@ from .store import PartitionStore
 SERIALIZATION_MAGIC = 0x44494E4C  # common.h:66
 SERIALIZATION_VERSION = 3         # common.h:67
 _WORKSPACE_LIMIT = 6 << 30        # split query batches whose scan workspace would exceed this
+_FINE_SEGMENT_PAIRS = 1024        # batches with fewer (query, list) pairs use the fine segment cut
 
 
 def _stream():
@@ -36,13 +37,16 @@ def _device() -> torch.device:
     return torch.device("cuda", torch.cuda.current_device())
 
 
+LAST_SCAN_STATS = None  # set QK_SCAN_STATS=1: int32[4] device tensor of the last qk_scan_partitions call
+
+
 def scan_partitions(store: PartitionStore, xq: torch.Tensor, probe_slots: torch.Tensor, k: int, metric: int,
                     want_rows: bool = False):
     """qk_scan_partitions over a device query batch xq [Q, pitch] and probe_slots [Q, nprobe] (int32).
     Returns (ids [Q,k] int64, distances [Q,k] float32[, rows]) on the device."""
     lib = _lib.load()
-    st, _ = store.tables()
     Q, nprobe = int(probe_slots.shape[0]), int(probe_slots.shape[1])
+    st, _ = store.tables(fine=Q * nprobe < _FINE_SEGMENT_PAIRS)
     dev = xq.device
     out_ids = torch.empty((Q, k), dtype=torch.int64, device=dev)
     out_dist = torch.empty((Q, k), dtype=torch.float32, device=dev)
@@ -66,11 +70,15 @@ def scan_partitions(store: PartitionStore, xq: torch.Tensor, probe_slots: torch.
             break
         chunk = (chunk + 1) // 2
     ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+    stats = None
+    if os.environ.get("QK_SCAN_STATS") == "1":
+        global LAST_SCAN_STATS
+        stats = LAST_SCAN_STATS = torch.zeros(4, dtype=torch.int32, device=dev)
     for b in range(0, Q, chunk):
         n = min(chunk, Q - b)
         check(lib.qk_scan_partitions(C.byref(st), ptr(xq[b:]), n, xq.stride(0), ptr(probe_slots[b:]), nprobe, metric, k,
                                      ptr(out_ids[b:]), ptr(out_dist[b:]), ptr(out_rows[b:]) if want_rows else None,
-                                     ptr(ws), wsb, None, _stream()))
+                                     ptr(ws), wsb, ptr(stats), _stream()))
     return (out_ids, out_dist, out_rows) if want_rows else (out_ids, out_dist)
 
 

@@ -49,9 +49,7 @@ class PartitionStore:
         self.curr_list_id = 0
         self.max_row_norm = 0.0
         self._dirty = True
-        self._tables = None
-        self._struct = None
-        self._id_to_slot = None
+        self._cache = {}
 
     # ------------------------------------------------------------------ basic queries
     @property
@@ -331,25 +329,30 @@ class PartitionStore:
         self.max_row_norm = max(norm, self.max_row_norm)
 
     # ------------------------------------------------------------------ device tables for the kernels
-    def tables(self):
-        """(QkStore struct, id_to_slot tensor); rebuilt lazily after any mutation."""
-        if not self._dirty and self._struct is not None:
-            return self._struct, self._id_to_slot
+    def tables(self, fine: bool = False):
+        """(QkStore struct, id_to_slot tensor); rebuilt lazily after any mutation.
+
+        Lists are cut into scan segments. The default cut (QK_SEGMENT_ROWS) keeps a segment far longer than
+        the candidate count kept per (query, segment), which is what makes the streaming top-k cheap; the
+        parallelism of a large batch comes from chunking the queries. `fine=True` cuts at 256 rows instead:
+        for small batches (few (query, list) pairs) that is what spreads a long list -- a flat index is ONE
+        list -- over the SMs."""
+        key = "fine" if fine else "coarse"
+        if self._dirty:
+            self._cache = {}
+            self._dirty = False
+        if key in self._cache:
+            return self._cache[key]
+        seg_len = 256 if fine else _MAX_SEGMENT_ROWS
         nslots = self.slot_pid.size
         size = self.list_size
-        # scan-segment length: long lists (a flat index is ONE list) are cut so that the whole GPU gets work
-        # items even for a small query batch; IVF lists are far shorter than this and stay whole.
-        total = int(size.sum()) if nslots else 0
-        seg_len = min(_MAX_SEGMENT_ROWS, max(256, -(-total // 1024)))
-        seg_len = (seg_len + 63) // 64 * 64
-        QK_SEGMENT_ROWS = seg_len  # noqa: F841 (shadows the module constant below on purpose)
-        nseg = (size + QK_SEGMENT_ROWS - 1) // QK_SEGMENT_ROWS
+        nseg = (size + seg_len - 1) // seg_len
         seg0 = np.concatenate([[0], np.cumsum(nseg)[:-1]]) if nslots else np.zeros(0, np.int64)
         S = int(nseg.sum())
         seg_list = np.repeat(np.arange(nslots), nseg)
         seg_idx = np.arange(S) - np.repeat(seg0, nseg)
-        seg_row0 = self.list_row0[seg_list] + seg_idx * QK_SEGMENT_ROWS
-        seg_rows = np.minimum(QK_SEGMENT_ROWS, size[seg_list] - seg_idx * QK_SEGMENT_ROWS)
+        seg_row0 = self.list_row0[seg_list] + seg_idx * seg_len
+        seg_rows = np.minimum(seg_len, size[seg_list] - seg_idx * seg_len)
         dev = self.device
         t = {
             "list_seg0": torch.from_numpy(seg0.astype(np.int32)).to(dev),
@@ -361,7 +364,7 @@ class PartitionStore:
         id_to_slot = np.full(table_size, -1, dtype=np.int32)
         for pid, s in self.pid_slot.items():
             id_to_slot[pid] = s
-        self._id_to_slot = torch.from_numpy(id_to_slot).to(dev)
+        t["id_to_slot"] = torch.from_numpy(id_to_slot).to(dev)
         st = QkStore()
         st.vectors = self.vectors.data_ptr()
         st.ids = self.ids.data_ptr()
@@ -376,7 +379,7 @@ class PartitionStore:
         st.seg_rows = t["seg_rows"].data_ptr()
         st.max_row_norm = float(self.max_row_norm)
         st.row_norms = self.norms.data_ptr()
-        self._tables = t
-        self._struct = st
-        self._dirty = False
-        return st, self._id_to_slot
+        st.num_rows = int(self.vectors.shape[0])
+        st._keepalive = t  # the struct holds raw pointers into these tensors
+        self._cache[key] = (st, t["id_to_slot"])
+        return self._cache[key]
