@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <math.h>
+#include <stdio.h>
 #include "../../include/quake_b200.h"
 
 #if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
@@ -168,10 +169,18 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// Spins until the phase with the given parity has completed. A wait that lasts longer than any legitimate one
+// (seconds) means a pipeline protocol error: report where and trap instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t done = 0;
     const uint32_t a = smem_u32(bar);
+    uint32_t spins = 0;
     while (!done) {
+        if (++spins == (1u << 26)) {
+            printf("quake_b200: mbarrier wait timed out: block %d warp %d lane %d barrier@%u parity %u\n", blockIdx.x,
+                   threadIdx.x >> 5, threadIdx.x & 31, a & 0xffffu, parity);
+            __trap();
+        }
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"

@@ -26,6 +26,8 @@
 //                        boundary) the query is flagged ...
 //   6. exact_rescan      ... and re-scanned exhaustively in exact arithmetic (rare).
 #include "common.cuh"
+#include <cstring>
+#include <cstdlib>
 
 namespace qk {
 
@@ -533,6 +535,59 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) scan_kernel(const ScanArgs a,
                     my_lim = t < KEY_MAX ? t : KEY_MAX - 1;  // KEY_MAX marks an invalid row
                 }
             }
+            // Per tile: (1) pass masks + the passing keys into registers, key buffer released at once;
+            // (2) one atomicAdd per query reserves buffer slots; (3) the entries of the PREVIOUS tile are
+            // written -- its atomics were issued one tile ago, so their latency is off the critical path.
+            constexpr int JMAX = (SCAN_GQ + NSEL - 1) / NSEL;
+            struct Pending {
+                uint32_t k0[JMAX], k1[JMAX];  // this lane's two keys of every query slot
+                unsigned m0, m1;              // lane j: pass masks of query slot j
+                int base, nn;                 // lane j: reserved slot range
+                uint32_t arow0;
+                bool live;
+            };
+            Pending pend;
+            pend.live = false;
+            pend.m0 = pend.m1 = 0; pend.base = pend.nn = 0; pend.arow0 = 0;
+            auto flush = [&](const Pending& pd) {
+                unsigned todo = __ballot_sync(0xffffffffu, pd.nn > 0);
+                unsigned cross = 0;  // queries whose fill passed a multiple of `step`
+#pragma unroll
+                for (int j = 0; j < JMAX; ++j) {
+                    if (!((todo >> j) & 1u)) continue;
+                    const unsigned m0 = __shfl_sync(0xffffffffu, pd.m0, j), m1 = __shfl_sync(0xffffffffu, pd.m1, j);
+                    const int b = __shfl_sync(0xffffffffu, pd.base, j);
+                    const int q = __shfl_sync(0xffffffffu, my_q, j);
+                    uint64_t* qb = a.qbuf + (size_t)q * qcap;
+                    const int c0 = __popc(m0), c1 = __popc(m1);
+                    if ((m0 >> lane) & 1u) {
+                        const int slot = b + __popc(m0 & below);
+                        if (slot < qcap) qb[slot] = ((uint64_t)pd.k0[j] << 32) | (pd.arow0 + lane);
+                    }
+                    if ((m1 >> lane) & 1u) {
+                        const int slot = b + c0 + __popc(m1 & below);
+                        if (slot < qcap) qb[slot] = ((uint64_t)pd.k1[j] << 32) | (pd.arow0 + 32 + lane);
+                    }
+                    const int e = b + c0 + c1;
+                    if (b / step != e / step && e >= kc) cross |= 1u << j;
+                }
+                // refresh the thresholds of the queries that crossed. The entries this warp just stored are
+                // read back by other lanes: order them first.
+                if (cross) __threadfence();
+                while (cross) {
+                    const int j = __ffs(cross) - 1;
+                    cross &= cross - 1;
+                    const int q = __shfl_sync(0xffffffffu, my_q, j);
+                    const int fill = __shfl_sync(0xffffffffu, pd.base + pd.nn, j);
+                    const unsigned long long* qb = reinterpret_cast<const unsigned long long*>(a.qbuf) + (size_t)q * qcap;
+                    const uint32_t t = radix_select([qb](int i) { return (uint32_t)(__ldcg(qb + i) >> 32); },
+                                                    fill < qcap ? fill : qcap, kc, hist, lane);
+                    if (t < KEY_MAX) {
+                        if (lane == 0) atomicMin(a.gthr + q, t);
+                        if (lane == j && t < my_lim) my_lim = t;
+                    }
+                }
+            };
             const int ntiles = (d.nrows + TV - 1) / TV;
             for (int tile = 0; tile < ntiles; ++tile, ++T) {
                 const int grp = T & 1u, kb = (T >> 1) & 1u;
@@ -540,10 +595,15 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) scan_kernel(const ScanArgs a,
                 const uint32_t g_now = my_q >= 0 ? __ldcg(a.gthr + my_q) : 0u;
                 mbar_wait(kfull + grp * 2 + kb, (T >> 2) & 1u);
                 const uint32_t* kbase = Ks + (size_t)(grp * 2 + kb) * gq * KP;
-                // phase 1: pass masks of all my queries (independent loads / ballots)
-                unsigned mym0 = 0, mym1 = 0;
-                for (int j = 0; sw + NSEL * j < d.g_cnt; ++j) {
+                Pending cur;
+                cur.live = true;
+                cur.m0 = cur.m1 = 0;
+                cur.arow0 = (uint32_t)(d.row0 + (int64_t)tile * TV);
+#pragma unroll
+                for (int j = 0; j < JMAX; ++j) {
                     const int g = sw + NSEL * j;
+                    cur.k0[j] = cur.k1[j] = KEY_MAX;
+                    if (g >= d.g_cnt) continue;  // warp-uniform
                     uint32_t lim = __shfl_sync(0xffffffffu, my_lim, j);
                     const uint32_t k0 = kbase[g * KP + lane], k1 = kbase[g * KP + 32 + lane];
                     unsigned m0 = __ballot_sync(0xffffffffu, k0 <= lim);
@@ -559,56 +619,19 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) scan_kernel(const ScanArgs a,
                             if (lane == 0) atomicMin(a.gthr + descs[ib].pair[g] / a.P, lim);
                         }
                     }
-                    if (lane == j) { mym0 = m0; mym1 = m1; my_lim = lim; }
-                }
-                // phase 2: reserve buffer slots, one atomic per query with at least one passing key
-                const int nn = __popc(mym0) + __popc(mym1);
-                int base = 0;
-                if (nn > 0) base = atomicAdd(&a.qcount[my_q], nn);
-                unsigned todo = __ballot_sync(0xffffffffu, nn > 0);
-                unsigned cross = 0;  // queries whose fill passed a multiple of `step`
-                // phase 3: write the entries
-                const uint32_t arow0 = (uint32_t)(d.row0 + (int64_t)tile * TV);
-                while (todo) {
-                    const int j = __ffs(todo) - 1;
-                    todo &= todo - 1;
-                    const int g = sw + NSEL * j;
-                    const unsigned m0 = __shfl_sync(0xffffffffu, mym0, j), m1 = __shfl_sync(0xffffffffu, mym1, j);
-                    const int b = __shfl_sync(0xffffffffu, base, j);
-                    const int q = __shfl_sync(0xffffffffu, my_q, j);
-                    uint64_t* qb = a.qbuf + (size_t)q * qcap;
-                    const int c0 = __popc(m0), c1 = __popc(m1);
-                    if ((m0 >> lane) & 1u) {
-                        const int slot = b + __popc(m0 & below);
-                        if (slot < qcap) qb[slot] = ((uint64_t)kbase[g * KP + lane] << 32) | (arow0 + lane);
-                    }
-                    if ((m1 >> lane) & 1u) {
-                        const int slot = b + c0 + __popc(m1 & below);
-                        if (slot < qcap) qb[slot] = ((uint64_t)kbase[g * KP + 32 + lane] << 32) | (arow0 + 32 + lane);
-                    }
-                    const int e = b + c0 + c1;
-                    if (b / step != e / step && e >= kc) cross |= 1u << j;
+                    cur.k0[j] = k0; cur.k1[j] = k1;
+                    if (lane == j) { cur.m0 = m0; cur.m1 = m1; my_lim = lim; }
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(kempty + grp * 2 + kb);
-                // phase 4 (key buffer already released): refresh the thresholds of the queries that crossed.
-                // The entries this warp just stored are read back by other lanes: order them first.
-                if (cross) __threadfence();
-                while (cross) {
-                    const int j = __ffs(cross) - 1;
-                    cross &= cross - 1;
-                    const int q = __shfl_sync(0xffffffffu, my_q, j);
-                    const int fill = __shfl_sync(0xffffffffu, base + nn, j);
-                    const unsigned long long* qb = reinterpret_cast<const unsigned long long*>(a.qbuf) + (size_t)q * qcap;
-                    const uint32_t t = radix_select([qb](int i) { return (uint32_t)(__ldcg(qb + i) >> 32); },
-                                                    fill < qcap ? fill : qcap, kc, hist, lane);
-                    if (t < KEY_MAX) {
-                        if (lane == 0) atomicMin(a.gthr + q, t);
-                        if (lane == j && t < my_lim) my_lim = t;
-                    }
-                }
+                cur.nn = __popc(cur.m0) + __popc(cur.m1);
+                cur.base = 0;
+                if (cur.nn > 0) cur.base = atomicAdd(&a.qcount[my_q], cur.nn);
+                if (pend.live) flush(pend);
+                pend = cur;
                 if (g_now < my_lim) my_lim = g_now;
             }
+            if (pend.live) flush(pend);
             __syncwarp();
             if (lane == 0) mbar_arrive(qempty + ib);
         }
@@ -690,6 +713,10 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) scan_kernel(const ScanArgs a,
     }
 }
 
+}  // namespace qk
+#include "scan_mma.cuh"
+namespace qk {
+
 // ------------------------------------------------------------------------------------------------
 // block-wide bitonic sort of n (power of two) uint64 keys in shared memory
 // ------------------------------------------------------------------------------------------------
@@ -737,6 +764,7 @@ struct MergeArgs {
     int32_t* ctrl;
     int P, kc, k;
     float max_row_norm;
+    double filter_gam;  // extra relative error bound of the filter's dot products (tensor-core path), vs |q||v|
     int64_t* out_ids;
     float* out_dist;
     int64_t* out_rows;
@@ -836,7 +864,7 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_refine_kernel(const Merge
                 const double e2 = (a.d / 8 + 12) * eps;
                 bool ok;
                 if (!kIP) {
-                    const double e1 = gam * (U * U + 2.0 * qnorm * U) + 4.0 * eps * fabs((double)a_score);
+                    const double e1 = gam * U * U + 2.0 * (gam + a.filter_gam) * qnorm * U + 4.0 * eps * fabs((double)a_score);
                     // lb bounds the reference-order SQUARED distance of every rejected row from below; the
                     // reference compares sqrt'ed values, and sqrt_rn is monotone, so a rejected row cannot
                     // tie or beat the k-th as soon as sqrt_rn(round_down(lb)) is strictly above it.
@@ -845,7 +873,7 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_refine_kernel(const Merge
                     ok = a.rank_squared ? (lb > (double)rk) : (lbf > 0.f && __fsqrt_rn(lbf) > rk);
                 } else {
                     // scores are -<q,v>: any rejected v has ip <= -a_score + err; need that below the k-th exact ip
-                    const double err = (gam + e2) * qnorm * U + 4.0 * eps * fabs((double)a_score);
+                    const double err = (gam + a.filter_gam + e2) * qnorm * U + 4.0 * eps * fabs((double)a_score);
                     ok = (-(double)a_score + err) < -(double)rk;
                 }
                 s_n = ok ? 0 : -1;
@@ -1092,7 +1120,7 @@ static int g_prof_cap = 0, g_prof_n = 0;
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static int make_row_tensor_map(const qk_store_t* st, CUtensorMap* out) {
+static int make_row_tensor_map(const qk_store_t* st, int box_rows, CUtensorMap* out) {
     static EncodeTiledFn encode = nullptr;
     if (!encode) {
         void* fn = nullptr;
@@ -1107,7 +1135,7 @@ static int make_row_tensor_map(const qk_store_t* st, CUtensorMap* out) {
     QK_REQUIRE(st->num_rows > 0, "store.num_rows must be set");
     cuuint64_t dims[2] = {(cuuint64_t)st->pitch, (cuuint64_t)st->num_rows};
     cuuint64_t strides[1] = {(cuuint64_t)st->pitch * sizeof(float)};
-    cuuint32_t box[2] = {32u, (cuuint32_t)SCAN_TV};
+    cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1u, 1u};
     CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)st->vectors, dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -1120,9 +1148,20 @@ static int make_row_tensor_map(const qk_store_t* st, CUtensorMap* out) {
     return QK_OK;
 }
 
-static int launch_scan(const ScanArgs& sa, const CUtensorMap& vmap, int metric, size_t smem, cudaStream_t stream) {
+static int launch_scan(const ScanArgs& sa, const CUtensorMap& vmap, int metric, size_t smem, bool mma, cudaStream_t stream) {
     const int grid = sm_count();
-    if (metric == QK_METRIC_INNER_PRODUCT) {
+    if (mma) {
+        const size_t msmem = scan_mma_smem_bytes();
+        if (metric == QK_METRIC_INNER_PRODUCT) {
+            auto kern = scan_mma_kernel<true>;
+            QK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem));
+            kern<<<grid, MMA_THREADS, msmem, stream>>>(sa, vmap);
+        } else {
+            auto kern = scan_mma_kernel<false>;
+            QK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem));
+            kern<<<grid, MMA_THREADS, msmem, stream>>>(sa, vmap);
+        }
+    } else if (metric == QK_METRIC_INNER_PRODUCT) {
         auto kern = scan_kernel<true>;
         QK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<grid, SCAN_THREADS, smem, stream>>>(sa, vmap);
@@ -1174,7 +1213,8 @@ int qk::scan_partitions_impl(const qk_store_t* st, const float* queries, int64_t
         return QK_ERR_WORKSPACE;
     }
     if (g_scan_variant < 0) {
-        g_scan_variant = 0;
+        const char* e = getenv("QK_SCAN_PATH");
+        g_scan_variant = (e && strcmp(e, "ffma") == 0) ? 1 : 0;
         const char* f = getenv("QK_FORCE_RESCAN");
         g_force_rescan = f ? atoi(f) : 0;
     }
@@ -1225,7 +1265,10 @@ int qk::scan_partitions_impl(const qk_store_t* st, const float* queries, int64_t
     sa.gthr = gthr; sa.qcount = qcount; sa.qbuf = qbuf;
     sa.P = p.P; sa.kc = p.kc; sa.gq = p.gq; sa.nq = p.nq; sa.qcap = p.qcap;
     CUtensorMap vmap;
-    rc = make_row_tensor_map(st, &vmap);
+    // d <= 128: tensor-core filter (tcgen05, 3xTF32 split); otherwise the FP32-pipe kernel. QK_SCAN_PATH=ffma
+    // forces the latter (tests cross-check the two).
+    const bool use_mma = (g_scan_variant == 0) && p.dp <= 128;
+    rc = make_row_tensor_map(st, use_mma ? MMA_TM : SCAN_TV, &vmap);
     if (rc) return rc;
     sa.norms = st->row_norms;
     ProfileRecord* rec = nullptr;
@@ -1234,7 +1277,7 @@ int qk::scan_partitions_impl(const qk_store_t* st, const float* queries, int64_t
         rec->queries = Q; rec->nprobe = nprobe; rec->k = k; rec->used = 1;
         QK_CUDA(cudaEventRecord(rec->start, stream));
     }
-    rc = launch_scan(sa, vmap, metric, p.smem, stream);
+    rc = launch_scan(sa, vmap, metric, p.smem, use_mma, stream);
     if (rc) return rc;
     if (rec) QK_CUDA(cudaEventRecord(rec->stop, stream));
 
@@ -1244,6 +1287,8 @@ int qk::scan_partitions_impl(const qk_store_t* st, const float* queries, int64_t
     ma.pair_seg = pair_seg; ma.gthr = gthr; ma.qbuf = qbuf; ma.qcount = qcount; ma.qcap = p.qcap;
     ma.flags = flags; ma.ctrl = ctrl; ma.P = p.P; ma.kc = p.kc; ma.k = k;
     ma.max_row_norm = st->max_row_norm;
+    // 3xTF32 dot products: measured ~2^-20 of sum|q_i v_i| (scripts/umma_probe.cu); bounded here by 2^-17 |q||v|
+    ma.filter_gam = use_mma ? 7.62939453125e-06 : 0.0;
     ma.out_ids = out_ids; ma.out_dist = out_dist; ma.out_rows = out_rows;
     ma.force_rescan = g_force_rescan;
     ma.rank_squared = rank_squared;

@@ -1,0 +1,427 @@
+// Tensor-core variant of the scan (filter) kernel for d <= 128 -- included by scan.cu.
+//
+// The grouped partition scan is a small dense contraction per work item: [<=32 queries x d] . [rows x d]^T.
+// Scoring it on the FP32 pipe is bound by shared-memory operand traffic (an 8x8 register tile per thread would
+// be needed to feed FFMA at rate), so this kernel hands the contraction to the 5th-generation tensor cores:
+// tcgen05.mma kind::tf32 with M = 128 rows, N = 32 queries, K = 8, operands read straight from the
+// TMA-written (128-byte swizzled) shared-memory tiles, accumulators in tensor memory. TF32 keeps only 10
+// mantissa bits, far too few for a distance filter, so every product is split as
+//       a*b ~= a_hi*b_hi + a_lo*b_hi + a_hi*b_lo,      x_hi = x truncated to TF32 (what the tensor core reads
+//                                                       from an fp32 word), x_lo = x - x_hi (exact in fp32)
+// which leaves a relative error of about 2^-20 per dot product (measured: scripts/umma_probe.cu) -- the filter
+// only has to be good enough for the exact refine + error-bound proof that follows it (merge_refine_kernel).
+// The a_lo tile never touches shared memory: the split warps write it to tensor memory (tcgen05.st) and the
+// second MMA of each K-step takes its A operand from there.
+//
+// Roles (14 warps, one persistent CTA per SM):
+//   warp 0      producer: work items (atomic counter, metadata pipelined), TMA tensor loads of the row tiles
+//               (box 128 rows x 32 floats, ring of 8), cp.async gather of the query chunk into the swizzled
+//               K-major B layout
+//   warp 1      MMA issuer (one lane): 3 MMAs per K-step, tcgen05.commit onto the pipeline mbarriers
+//   warps 2-5   split: a_lo = a - trunc(a) -> tensor memory, b_lo -> shared memory (once per item)
+//   warps 6-13  epilogue + selection, two groups of four taking alternate tiles: tcgen05.ld of the
+//               accumulators (thread = row, 32 queries in registers), keys, threshold test, append to the
+//               per-query candidate buffers, threshold refresh (same scheme as the FFMA kernel's select warps)
+#pragma once
+
+namespace qk {
+
+static constexpr int MMA_TM = 128;            // rows per tile (UMMA M)
+static constexpr int MMA_NQ = 32;             // query slots per item (UMMA N)
+static constexpr int MMA_BOX = 32;            // floats per TMA box row (128 B, one swizzle atom row)
+static constexpr int MMA_STAGES = 8;          // ring of A boxes, 16 KB each
+static constexpr int MMA_BOX_BYTES = MMA_TM * 128;
+static constexpr int MMA_NB = 2;              // item slots (B operand + descriptor)
+static constexpr int MMA_BBOX_BYTES = MMA_NQ * 128;  // 4 KB: 32 queries x 32 floats
+static constexpr int MMA_THREADS = 32 * 14;
+static constexpr int MMA_TMEM_COLS = 512;
+static constexpr int MMA_TMEM_D = 0;          // 2 accumulator buffers x 32 columns
+static constexpr int MMA_TMEM_ALO = 64;       // 8 a_lo boxes x 32 columns
+
+static size_t scan_mma_smem_bytes() {
+    return (size_t)SCAN_SMEM_HEADER + (size_t)MMA_STAGES * MMA_BOX_BYTES + (size_t)MMA_NB * 8 * MMA_BBOX_BYTES +
+           (size_t)8 * 256 * sizeof(uint32_t) + 1024;
+}
+
+// ---- tcgen05 wrappers --------------------------------------------------------------------------------------
+// K-major, SWIZZLE_128B shared-memory matrix descriptor: rows of 128 B, 8-row groups 1024 B apart
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+    return (uint64_t)((saddr >> 4) & 0x3fffu) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+           ((uint64_t)2 << 61);
+}
+// instruction descriptor: D = f32, A = B = tf32, both K-major
+__host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_ss(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+        "l"(da), "l"(db), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(db), "r"(idesc), "r"(acc)
+        : "memory");
+}
+// arrive on `bar` once every tcgen05 operation issued so far by this thread has completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]),
+          "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]),
+          "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+        "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+        "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]),
+        "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]),
+        "r"(v[30]), "r"(v[31])
+        : "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ float tf32_lo(float x) { return x - __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
+
+// kc-th smallest of one key per lane (kc <= 32), by bisection on the key bits
+__device__ __forceinline__ uint32_t warp_kth_smallest(uint32_t key, int kc) {
+    uint32_t lo = 0;
+#pragma unroll 1
+    for (int bit = 31; bit >= 0; --bit) {
+        const uint32_t cand = lo | (1u << bit);
+        if (__popc(__ballot_sync(0xffffffffu, key < cand)) < kc) lo = cand;
+    }
+    return lo;
+}
+
+template <bool kIP>
+__global__ void __launch_bounds__(MMA_THREADS, 1) scan_mma_kernel(const ScanArgs a, const __grid_constant__ CUtensorMap vmap) {
+    constexpr int TM = MMA_TM, NS = MMA_STAGES, NB = MMA_NB;
+    extern __shared__ __align__(16) unsigned char smem_dyn[];
+    unsigned char* smem_raw = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
+    uint64_t* a_full = bars;           // [NS] producer (tx)                 -> split warps, MMA issuer
+    uint64_t* a_empty = bars + 8;      // [NS] 4 split warps + MMA commit    -> producer
+    uint64_t* alo_full = bars + 16;    // [NS] 4 split warps                 -> MMA issuer
+    uint64_t* b_full = bars + 24;      // [NB] 32 producer lanes             -> split warps, epilogue (descriptor)
+    uint64_t* b_ready = bars + 26;     // [NB] 4 split warps (b_lo written)  -> MMA issuer
+    uint64_t* b_empty = bars + 28;     // [NB] 12 warps + MMA commit         -> producer
+    uint64_t* d_full = bars + 30;      // [2]  MMA commit                    -> epilogue group
+    uint64_t* d_empty = bars + 32;     // [2]  4 epilogue warps              -> MMA issuer
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + 384);
+    ItemDesc* descs = reinterpret_cast<ItemDesc*>(smem_raw + 512);  // [NB]
+    unsigned char* As = smem_raw + SCAN_SMEM_HEADER;                // [NS][128 rows][128 B]
+    unsigned char* Bs = As + (size_t)NS * MMA_BOX_BYTES;            // [NB][hi: 4 boxes | lo: 4 boxes][32 rows][128 B]
+    uint32_t* hists = reinterpret_cast<uint32_t*>(Bs + (size_t)NB * 8 * MMA_BBOX_BYTES);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int dp = a.dp, kc = a.kc;
+    const int nbox = (dp + MMA_BOX - 1) / MMA_BOX;  // 1..4
+    if (tid == 0) {
+        for (int s = 0; s < NS; ++s) { mbar_init(a_full + s, 1); mbar_init(a_empty + s, 5); mbar_init(alo_full + s, 4); }
+        for (int s = 0; s < NB; ++s) { mbar_init(b_full + s, 32); mbar_init(b_ready + s, 4); mbar_init(b_empty + s, 13); }
+        for (int s = 0; s < 2; ++s) { mbar_init(d_full + s, 1); mbar_init(d_empty + s, 4); }
+        mbar_fence_init();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(MMA_TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================================================================== producer
+        const int n_items = a.ctrl[1];
+        auto fetch_index = [&]() {
+            int it = 0;
+            if (lane == 0) it = atomicAdd(&a.ctrl[0], 1);
+            return __shfl_sync(0xffffffffu, it, 0);
+        };
+        auto fetch_item = [&](int it) {
+            WorkItem w;
+            w.seg = -1; w.g_begin = 0; w.g_cnt = 0; w.nrows = 0; w.row0 = 0; w.pad_ = 0;
+            if (it < n_items) w = a.items[it];
+            return w;
+        };
+        auto fetch_pair = [&](const WorkItem& w) { return (w.seg >= 0 && lane < w.g_cnt) ? a.seg_pairs[w.g_begin + lane] : -1; };
+        auto fetch_gthr = [&](int pair) { return pair >= 0 ? __ldcg(a.gthr + pair / a.P) : KEY_MAX; };
+        WorkItem m0 = fetch_item(fetch_index());
+        WorkItem m1 = fetch_item(fetch_index());
+        WorkItem m2 = fetch_item(fetch_index());
+        int pair0 = fetch_pair(m0);
+        int pair1 = fetch_pair(m1);
+        uint32_t gthr0 = fetch_gthr(pair0);
+        uint32_t U = 0;
+        const int dp4 = dp >> 2;
+        for (uint32_t n = 0;; ++n) {
+            const int ib = n % NB;
+            const int it3 = fetch_index();
+            mbar_wait(b_empty + ib, ((n / NB) & 1u) ^ 1u);
+            if (m0.seg < 0) {
+                if (lane == 0) descs[ib].w.seg = -1;
+                __syncwarp();
+                mbar_arrive(b_full + ib);  // all 32 lanes
+                break;
+            }
+            const int g_cnt = m0.g_cnt, nrows = m0.nrows;
+            const int64_t row0 = m0.row0;
+            descs[ib].pair[lane] = pair0;
+            descs[ib].gthr[lane] = gthr0;
+            if (lane == 0) descs[ib].w = m0;
+            __threadfence_block();
+            // query chunk -> B_hi in the canonical K-major 128-byte-swizzled layout: box b = 32 floats of every
+            // query, query g at g * 128 B, 16-byte chunk cc stored at cc ^ (g & 7); padding chunks are zeroed
+            {
+                unsigned char* bhi = Bs + (size_t)ib * 8 * MMA_BBOX_BYTES;
+                for (int g = 0; g < g_cnt; ++g) {
+                    const int64_t q = __shfl_sync(0xffffffffu, pair0, g) / a.P;
+                    const float* src = a.queries + q * a.q_pitch;
+                    for (int c = lane; c < nbox * 8; c += 32) {
+                        unsigned char* dst = bhi + (size_t)(c >> 3) * MMA_BBOX_BYTES + g * 128 + (((c & 7) ^ (g & 7)) << 4);
+                        if (c < dp4) cp_async16(dst, src + 4 * c);
+                        else *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                }
+                cp_async_mbar_arrive_noinc(b_full + ib);
+            }
+            const int ntiles = (nrows + TM - 1) / TM;
+            for (int tile = 0; tile < ntiles; ++tile) {
+                for (int b = 0; b < nbox; ++b, ++U) {
+                    const int st = U % NS;
+                    mbar_wait(a_empty + st, ((U / NS) & 1u) ^ 1u);
+                    if (lane == 0) {
+                        mbar_expect_tx(a_full + st, (uint32_t)MMA_BOX_BYTES);
+                        tma_load_2d(As + (size_t)st * MMA_BOX_BYTES, &vmap, b * MMA_BOX, (int)(row0 + (int64_t)tile * TM),
+                                    a_full + st);
+                    }
+                    __syncwarp();
+                }
+            }
+            const int pair2 = fetch_pair(m2);
+            m0 = m1; pair0 = pair1;
+            m1 = m2; pair1 = pair2;
+            m2 = fetch_item(it3);
+            gthr0 = fetch_gthr(pair0);
+        }
+    } else if (warp == 1) {
+        // ===================================================================== MMA issuer
+        constexpr uint32_t IDESC = umma_idesc_tf32(MMA_TM, MMA_NQ);
+        uint32_t T = 0, U = 0;
+        for (uint32_t n = 0;; ++n) {
+            const int ib = n % NB;
+            mbar_wait(b_ready + ib, (n / NB) & 1u);
+            const WorkItem d = descs[ib].w;
+            if (d.seg < 0) break;
+            const uint32_t bhi = smem_u32(Bs + (size_t)ib * 8 * MMA_BBOX_BYTES);
+            const uint32_t blo = bhi + 4 * MMA_BBOX_BYTES;
+            const int ntiles = (d.nrows + TM - 1) / TM;
+            for (int tile = 0; tile < ntiles; ++tile, ++T) {
+                const int db = T & 1u;
+                mbar_wait(d_empty + db, ((T >> 1) & 1u) ^ 1u);
+                const uint32_t tmem_d = tmem + MMA_TMEM_D + db * MMA_NQ;
+                for (int b = 0; b < nbox; ++b, ++U) {
+                    const int st = U % NS;
+                    mbar_wait(a_full + st, (U / NS) & 1u);
+                    mbar_wait(alo_full + st, (U / NS) & 1u);
+                    tc_fence_after();
+                    if (lane == 0) {
+                        const uint32_t abase = smem_u32(As + (size_t)st * MMA_BOX_BYTES);
+                        const uint32_t talo = tmem + MMA_TMEM_ALO + st * MMA_BOX;
+                        const int ksteps = min(4, (dp - b * MMA_BOX + 7) >> 3);
+                        for (int kk = 0; kk < ksteps; ++kk) {
+                            const uint64_t da = umma_desc_sw128(abase + kk * 32);
+                            const uint64_t dbh = umma_desc_sw128(bhi + b * MMA_BBOX_BYTES + kk * 32);
+                            const uint64_t dbl = umma_desc_sw128(blo + b * MMA_BBOX_BYTES + kk * 32);
+                            umma_ss(tmem_d, da, dbh, IDESC, (b | kk) ? 1u : 0u);
+                            umma_ts(tmem_d, talo + kk * 8, dbh, IDESC, 1u);
+                            umma_ss(tmem_d, da, dbl, IDESC, 1u);
+                        }
+                        umma_commit(a_empty + st);  // the row box (and its a_lo columns) may be refilled
+                    }
+                    __syncwarp();
+                }
+                if (lane == 0) umma_commit(d_full + db);
+                __syncwarp();
+            }
+            if (lane == 0) umma_commit(b_empty + ib);
+            __syncwarp();
+        }
+    } else if (warp < 6) {
+        // ===================================================================== split warps
+        const int q4 = warp & 3;  // the tensor-memory lane quadrant this warp may access
+        const int st_tid = (warp - 2) * 32 + lane;
+        uint32_t U = 0;
+        for (uint32_t n = 0;; ++n) {
+            const int ib = n % NB;
+            mbar_wait(b_full + ib, (n / NB) & 1u);
+            const WorkItem d = descs[ib].w;
+            if (d.seg < 0) {  // pass the end-of-work marker on to the MMA issuer
+                __syncwarp();
+                if (lane == 0) mbar_arrive(b_ready + ib);
+                break;
+            }
+            {   // b_lo: elementwise over the swizzled B_hi buffer (same offsets)
+                const float4* hi = reinterpret_cast<const float4*>(Bs + (size_t)ib * 8 * MMA_BBOX_BYTES);
+                float4* lo = reinterpret_cast<float4*>(Bs + (size_t)ib * 8 * MMA_BBOX_BYTES + 4 * MMA_BBOX_BYTES);
+                for (int i = st_tid; i < nbox * (MMA_BBOX_BYTES / 16); i += 128) {
+                    const float4 x = hi[i];
+                    lo[i] = make_float4(tf32_lo(x.x), tf32_lo(x.y), tf32_lo(x.z), tf32_lo(x.w));
+                }
+                fence_proxy_async();  // B_hi (cp.async) and B_lo are read by the tensor core through the async proxy
+                __syncwarp();
+                if (lane == 0) mbar_arrive(b_ready + ib);
+            }
+            const int ntiles = (d.nrows + TM - 1) / TM;
+            const int r = q4 * 32 + lane;  // this thread's row of the tile == its tensor-memory lane
+            for (int tile = 0; tile < ntiles; ++tile) {
+                for (int b = 0; b < nbox; ++b, ++U) {
+                    const int st = U % NS;
+                    mbar_wait(a_full + st, (U / NS) & 1u);
+                    const unsigned char* rowp = As + (size_t)st * MMA_BOX_BYTES + r * 128;
+                    uint32_t v[32];
+#pragma unroll
+                    for (int cc = 0; cc < 8; ++cc) {
+                        const float4 x = *reinterpret_cast<const float4*>(rowp + ((cc ^ (r & 7)) << 4));
+                        v[4 * cc + 0] = __float_as_uint(tf32_lo(x.x));
+                        v[4 * cc + 1] = __float_as_uint(tf32_lo(x.y));
+                        v[4 * cc + 2] = __float_as_uint(tf32_lo(x.z));
+                        v[4 * cc + 3] = __float_as_uint(tf32_lo(x.w));
+                    }
+                    tmem_st32(tmem + MMA_TMEM_ALO + st * MMA_BOX + ((uint32_t)(q4 * 32) << 16), v);
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) { mbar_arrive(alo_full + st); mbar_arrive(a_empty + st); }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(b_empty + ib);
+        }
+    } else {
+        // ===================================================================== epilogue + selection
+        const int eg = (warp - 6) >> 2;  // group: takes tiles with (T & 1) == eg
+        const int q4 = warp & 3;
+        uint32_t* hist = hists + (warp - 6) * 256;
+        const int qcap = a.qcap;
+        const int step = kc > 64 ? kc : 64;
+        const unsigned below = (1u << lane) - 1u;
+        uint32_t T = 0;
+        for (uint32_t n = 0;; ++n) {
+            const int ib = n % NB;
+            mbar_wait(b_full + ib, (n / NB) & 1u);
+            const WorkItem d = descs[ib].w;
+            if (d.seg < 0) break;
+            // lane g keeps the state of query slot g
+            int my_q = -1;
+            uint32_t my_lim = 0;
+            if (lane < d.g_cnt) {
+                my_q = descs[ib].pair[lane] / a.P;
+                const uint32_t t = descs[ib].gthr[lane];
+                my_lim = t < KEY_MAX ? t : KEY_MAX - 1;  // KEY_MAX marks an invalid row
+            }
+            const int ntiles = (d.nrows + TM - 1) / TM;
+            for (int tile = 0; tile < ntiles; ++tile, ++T) {
+                if ((int)(T & 1u) != eg) continue;
+                const int tr = min(TM, d.nrows - tile * TM);
+                const int r = q4 * 32 + lane;
+                const uint32_t g_now = my_q >= 0 ? __ldcg(a.gthr + my_q) : 0u;
+                float nrm = 0.f;
+                if (!kIP && r < tr) nrm = __ldg(a.norms + d.row0 + (int64_t)tile * TM + r);
+                mbar_wait(d_full + eg, (T >> 1) & 1u);
+                tc_fence_after();
+                uint32_t v[32];
+                tmem_ld32(tmem + MMA_TMEM_D + eg * MMA_NQ + ((uint32_t)(q4 * 32) << 16), v);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(d_empty + eg);
+                // keys of this thread's row for every query slot; pass masks (lane g keeps query g's mask)
+                unsigned mymask = 0;
+#pragma unroll
+                for (int g = 0; g < MMA_NQ; ++g) {
+                    if (g < d.g_cnt) {  // warp-uniform
+                        const float dot = __uint_as_float(v[g]);
+                        const float sc = kIP ? -dot : fmaf(-2.f, dot, nrm);
+                        const uint32_t key = (r < tr) ? f2key(sc) : KEY_MAX;
+                        v[g] = key;
+                        uint32_t lim = __shfl_sync(0xffffffffu, my_lim, g);
+                        unsigned m = __ballot_sync(0xffffffffu, key <= lim);
+                        if (kc <= 28 && __popc(m) > kc + 2) {
+                            // a loose (stale or missing) threshold: these 32 rows alone bound the kc-th best key
+                            const uint32_t t = warp_kth_smallest(key, kc);
+                            if (t < lim) {
+                                lim = t;
+                                m = __ballot_sync(0xffffffffu, key <= lim);
+                                if (lane == g) { atomicMin(a.gthr + my_q, lim); my_lim = lim; }
+                            }
+                        }
+                        if (lane == g) mymask = m;
+                    }
+                }
+                // reserve buffer slots: one atomic per query with a passing row, all queries in one instruction
+                const int nn = __popc(mymask);
+                int base = 0;
+                if (nn > 0) base = atomicAdd(&a.qcount[my_q], nn);
+                unsigned todo = __ballot_sync(0xffffffffu, nn > 0);
+                unsigned cross = 0;
+                const uint32_t arow = (uint32_t)(d.row0 + (int64_t)tile * TM + r);
+#pragma unroll
+                for (int g = 0; g < MMA_NQ; ++g) {
+                    if ((todo >> g) & 1u) {  // warp-uniform
+                        const unsigned m = __shfl_sync(0xffffffffu, mymask, g);
+                        const int bb = __shfl_sync(0xffffffffu, base, g);
+                        const int q = __shfl_sync(0xffffffffu, my_q, g);
+                        if ((m >> lane) & 1u) {
+                            const int slot = bb + __popc(m & below);
+                            if (slot < qcap) a.qbuf[(size_t)q * qcap + slot] = ((uint64_t)v[g] << 32) | arow;
+                        }
+                        const int e = bb + __popc(m);
+                        if (bb / step != e / step && e >= kc) cross |= 1u << g;
+                    }
+                }
+                // refresh the thresholds of the queries whose fill passed a multiple of `step`
+                if (cross) __threadfence();
+                while (cross) {
+                    const int g = __ffs(cross) - 1;
+                    cross &= cross - 1;
+                    const int q = __shfl_sync(0xffffffffu, my_q, g);
+                    const int fill = __shfl_sync(0xffffffffu, base + nn, g);
+                    const unsigned long long* qb = reinterpret_cast<const unsigned long long*>(a.qbuf) + (size_t)q * qcap;
+                    const uint32_t t = radix_select([qb](int i) { return (uint32_t)(__ldcg(qb + i) >> 32); },
+                                                    fill < qcap ? fill : qcap, kc, hist, lane);
+                    if (t < KEY_MAX) {
+                        if (lane == 0) atomicMin(a.gthr + q, t);
+                        if (lane == g && t < my_lim) my_lim = t;
+                    }
+                }
+                if (g_now < my_lim) my_lim = g_now;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(b_empty + ib);
+        }
+    }
+    // ---- teardown: all tensor-memory traffic of this CTA has completed once every role has left its loop
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(MMA_TMEM_COLS));
+}
+
+}  // namespace qk

@@ -62,7 +62,7 @@ def _check(st, lists, Q, nprobe, k, metric, seed, skip_frac=0.0):
 
 
 @pytest.mark.parametrize("metric", ["l2", "ip"])
-@pytest.mark.parametrize("d", [128, 96, 32, 100, 3])
+@pytest.mark.parametrize("d", [128, 96, 32, 100, 3, 200])
 def test_scan_matches_oracle(metric, d):
     g = np.random.default_rng(d)
     sizes = g.integers(0, 700, size=64)
@@ -117,5 +117,23 @@ def test_forced_exact_rescan_path(monkeypatch):
             "t._check(st, lists, Q=64, nprobe=5, k=10, metric='l2', seed=9);"
             "t._check(st, lists, Q=64, nprobe=5, k=10, metric='ip', seed=9); print('ok')") % (root, os.path.join(root, 'tests'))
     env = dict(os.environ, QK_FORCE_RESCAN="1")
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, cwd=root)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
+
+
+def test_fp32_pipe_kernel_path():
+    """d <= 128 normally runs the tensor-core filter; QK_SCAN_PATH=ffma forces the FP32-pipe kernel (the one
+    larger d uses) over the same cases."""
+    import subprocess, sys, os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import sys; sys.path.insert(0, %r);"
+            "import numpy as np, tests.test_gpu_scan as t;"
+            "g = np.random.default_rng(1); sizes = g.integers(0, 700, size=64); sizes[3] = 0; sizes[5] = 1;"
+            "st, lists = t._make_store(sizes, 128, seed=3);"
+            "assert t._check(st, lists, Q=200, nprobe=8, k=10, metric='l2', seed=1) == 0;"
+            "assert t._check(st, lists, Q=200, nprobe=8, k=100, metric='ip', seed=2) == 0;"
+            "st, lists = t._make_store(sizes, 100, seed=4);"
+            "assert t._check(st, lists, Q=70, nprobe=8, k=10, metric='l2', seed=1) == 0; print('ok')") % (root,)
+    env = dict(os.environ, QK_SCAN_PATH="ffma")
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, cwd=root)
     assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
