@@ -87,7 +87,7 @@ static_assert(256 + SCAN_MAX_NQ * sizeof(ItemDesc) <= SCAN_SMEM_HEADER, "header"
 // is handed to the exact re-scan.
 static int candidate_buffer_cap(int kc) {
     int c = 32 * kc;
-    if (c < 1024) c = 1024;
+    if (c < 2048) c = 2048;
     if (c > 65536) c = 65536;
     return c;
 }

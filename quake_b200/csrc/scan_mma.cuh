@@ -29,18 +29,19 @@ namespace qk {
 static constexpr int MMA_TM = 128;            // rows per tile (UMMA M)
 static constexpr int MMA_NQ = 32;             // query slots per item (UMMA N)
 static constexpr int MMA_BOX = 32;            // floats per TMA box row (128 B, one swizzle atom row)
-static constexpr int MMA_STAGES = 8;          // ring of A boxes, 16 KB each
+static constexpr int MMA_STAGES = 6;          // ring of A boxes, 16 KB each
 static constexpr int MMA_BOX_BYTES = MMA_TM * 128;
-static constexpr int MMA_NB = 2;              // item slots (B operand + descriptor)
+static constexpr int MMA_NB = 3;              // B-operand slots (query chunk hi + lo, 32 KB each)
+static constexpr int MMA_ND = 5;              // work-item descriptor slots (the selection warps lag the MMAs)
 static constexpr int MMA_BBOX_BYTES = MMA_NQ * 128;  // 4 KB: 32 queries x 32 floats
 static constexpr int MMA_THREADS = 32 * 14;
 static constexpr int MMA_TMEM_COLS = 512;
 static constexpr int MMA_TMEM_D = 0;          // 2 accumulator buffers x 32 columns
-static constexpr int MMA_TMEM_ALO = 64;       // 8 a_lo boxes x 32 columns
+static constexpr int MMA_TMEM_ALO = 64;       // MMA_STAGES a_lo boxes x 32 columns
 
 static size_t scan_mma_smem_bytes() {
     return (size_t)SCAN_SMEM_HEADER + (size_t)MMA_STAGES * MMA_BOX_BYTES + (size_t)MMA_NB * 8 * MMA_BBOX_BYTES +
-           (size_t)8 * 256 * sizeof(uint32_t) + 1024;
+           (size_t)8 * 256 * sizeof(uint32_t) + (size_t)2 * 256 * sizeof(uint32_t) + 1024;
 }
 
 // ---- tcgen05 wrappers --------------------------------------------------------------------------------------
@@ -113,30 +114,35 @@ __device__ __forceinline__ uint32_t warp_kth_smallest(uint32_t key, int kc) {
 
 template <bool kIP>
 __global__ void __launch_bounds__(MMA_THREADS, 1) scan_mma_kernel(const ScanArgs a, const __grid_constant__ CUtensorMap vmap) {
-    constexpr int TM = MMA_TM, NS = MMA_STAGES, NB = MMA_NB;
+    constexpr int TM = MMA_TM, NS = MMA_STAGES, NB = MMA_NB, ND = MMA_ND;
+    static_assert(512 + MMA_ND * sizeof(ItemDesc) <= SCAN_SMEM_HEADER, "descriptor ring");
     extern __shared__ __align__(16) unsigned char smem_dyn[];
     unsigned char* smem_raw = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
     uint64_t* a_full = bars;           // [NS] producer (tx)                 -> split warps, MMA issuer
     uint64_t* a_empty = bars + 8;      // [NS] 4 split warps + MMA commit    -> producer
     uint64_t* alo_full = bars + 16;    // [NS] 4 split warps                 -> MMA issuer
-    uint64_t* b_full = bars + 24;      // [NB] 32 producer lanes             -> split warps, epilogue (descriptor)
-    uint64_t* b_ready = bars + 26;     // [NB] 4 split warps (b_lo written)  -> MMA issuer
-    uint64_t* b_empty = bars + 28;     // [NB] 12 warps + MMA commit         -> producer
-    uint64_t* d_full = bars + 30;      // [2]  MMA commit                    -> epilogue group
-    uint64_t* d_empty = bars + 32;     // [2]  4 epilogue warps              -> MMA issuer
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + 384);
-    ItemDesc* descs = reinterpret_cast<ItemDesc*>(smem_raw + 512);  // [NB]
+    uint64_t* b_full = bars + 24;      // [NB] 32 producer lanes (cp.async)  -> split warps
+    uint64_t* b_ready = bars + 28;     // [NB] 4 split warps (b_lo written)  -> MMA issuer
+    uint64_t* b_empty = bars + 32;     // [NB] MMA commit                    -> producer
+    uint64_t* i_full = bars + 36;      // [ND] producer (descriptor written) -> every consumer warp
+    uint64_t* i_empty = bars + 44;     // [ND] 13 consumer warps             -> producer
+    uint64_t* d_full = bars + 52;      // [2]  MMA commit                    -> epilogue group
+    uint64_t* d_empty = bars + 54;     // [2]  4 epilogue warps              -> MMA issuer
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + 456);
+    ItemDesc* descs = reinterpret_cast<ItemDesc*>(smem_raw + 512);  // [ND]
     unsigned char* As = smem_raw + SCAN_SMEM_HEADER;                // [NS][128 rows][128 B]
     unsigned char* Bs = As + (size_t)NS * MMA_BOX_BYTES;            // [NB][hi: 4 boxes | lo: 4 boxes][32 rows][128 B]
     uint32_t* hists = reinterpret_cast<uint32_t*>(Bs + (size_t)NB * 8 * MMA_BBOX_BYTES);
+    uint32_t* xch = hists + 8 * 256;  // [2 groups][128 keys | 4 warps x 32 counts] exchange for the tile-level threshold
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int dp = a.dp, kc = a.kc;
     const int nbox = (dp + MMA_BOX - 1) / MMA_BOX;  // 1..4
     if (tid == 0) {
         for (int s = 0; s < NS; ++s) { mbar_init(a_full + s, 1); mbar_init(a_empty + s, 5); mbar_init(alo_full + s, 4); }
-        for (int s = 0; s < NB; ++s) { mbar_init(b_full + s, 32); mbar_init(b_ready + s, 4); mbar_init(b_empty + s, 13); }
+        for (int s = 0; s < NB; ++s) { mbar_init(b_full + s, 32); mbar_init(b_ready + s, 4); mbar_init(b_empty + s, 1); }
+        for (int s = 0; s < ND; ++s) { mbar_init(i_full + s, 1); mbar_init(i_empty + s, 13); }
         for (int s = 0; s < 2; ++s) { mbar_init(d_full + s, 1); mbar_init(d_empty + s, 4); }
         mbar_fence_init();
     }
@@ -174,23 +180,26 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) scan_mma_kernel(const ScanArgs
         uint32_t U = 0;
         const int dp4 = dp >> 2;
         for (uint32_t n = 0;; ++n) {
-            const int ib = n % NB;
+            const int ib = n % NB, id = n % ND;
             const int it3 = fetch_index();
-            mbar_wait(b_empty + ib, ((n / NB) & 1u) ^ 1u);
+            mbar_wait(i_empty + id, ((n / ND) & 1u) ^ 1u);
             if (m0.seg < 0) {
-                if (lane == 0) descs[ib].w.seg = -1;
-                __syncwarp();
-                mbar_arrive(b_full + ib);  // all 32 lanes
+                if (lane == 0) {
+                    descs[id].w.seg = -1;
+                    mbar_arrive(i_full + id);
+                }
                 break;
             }
             const int g_cnt = m0.g_cnt, nrows = m0.nrows;
             const int64_t row0 = m0.row0;
-            descs[ib].pair[lane] = pair0;
-            descs[ib].gthr[lane] = gthr0;
-            if (lane == 0) descs[ib].w = m0;
-            __threadfence_block();
+            descs[id].pair[lane] = pair0;
+            descs[id].gthr[lane] = gthr0;
+            if (lane == 0) descs[id].w = m0;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(i_full + id);
             // query chunk -> B_hi in the canonical K-major 128-byte-swizzled layout: box b = 32 floats of every
             // query, query g at g * 128 B, 16-byte chunk cc stored at cc ^ (g & 7); padding chunks are zeroed
+            mbar_wait(b_empty + ib, ((n / NB) & 1u) ^ 1u);
             {
                 unsigned char* bhi = Bs + (size_t)ib * 8 * MMA_BBOX_BYTES;
                 for (int g = 0; g < g_cnt; ++g) {
@@ -228,10 +237,13 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) scan_mma_kernel(const ScanArgs
         constexpr uint32_t IDESC = umma_idesc_tf32(MMA_TM, MMA_NQ);
         uint32_t T = 0, U = 0;
         for (uint32_t n = 0;; ++n) {
-            const int ib = n % NB;
-            mbar_wait(b_ready + ib, (n / NB) & 1u);
-            const WorkItem d = descs[ib].w;
+            const int ib = n % NB, id = n % ND;
+            mbar_wait(i_full + id, (n / ND) & 1u);
+            const WorkItem d = descs[id].w;
             if (d.seg < 0) break;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(i_empty + id);  // only the descriptor header was needed
+            mbar_wait(b_ready + ib, (n / NB) & 1u);
             const uint32_t bhi = smem_u32(Bs + (size_t)ib * 8 * MMA_BBOX_BYTES);
             const uint32_t blo = bhi + 4 * MMA_BBOX_BYTES;
             const int ntiles = (d.nrows + TM - 1) / TM;
@@ -272,14 +284,13 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) scan_mma_kernel(const ScanArgs
         const int st_tid = (warp - 2) * 32 + lane;
         uint32_t U = 0;
         for (uint32_t n = 0;; ++n) {
-            const int ib = n % NB;
+            const int ib = n % NB, id = n % ND;
+            mbar_wait(i_full + id, (n / ND) & 1u);
+            const WorkItem d = descs[id].w;
+            if (d.seg < 0) break;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(i_empty + id);
             mbar_wait(b_full + ib, (n / NB) & 1u);
-            const WorkItem d = descs[ib].w;
-            if (d.seg < 0) {  // pass the end-of-work marker on to the MMA issuer
-                __syncwarp();
-                if (lane == 0) mbar_arrive(b_ready + ib);
-                break;
-            }
             {   // b_lo: elementwise over the swizzled B_hi buffer (same offsets)
                 const float4* hi = reinterpret_cast<const float4*>(Bs + (size_t)ib * 8 * MMA_BBOX_BYTES);
                 float4* lo = reinterpret_cast<float4*>(Bs + (size_t)ib * 8 * MMA_BBOX_BYTES + 4 * MMA_BBOX_BYTES);
@@ -313,8 +324,6 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) scan_mma_kernel(const ScanArgs
                     if (lane == 0) { mbar_arrive(alo_full + st); mbar_arrive(a_empty + st); }
                 }
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(b_empty + ib);
         }
     } else {
         // ===================================================================== epilogue + selection
@@ -326,16 +335,16 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) scan_mma_kernel(const ScanArgs
         const unsigned below = (1u << lane) - 1u;
         uint32_t T = 0;
         for (uint32_t n = 0;; ++n) {
-            const int ib = n % NB;
-            mbar_wait(b_full + ib, (n / NB) & 1u);
-            const WorkItem d = descs[ib].w;
+            const int id = n % ND;
+            mbar_wait(i_full + id, (n / ND) & 1u);
+            const WorkItem d = descs[id].w;
             if (d.seg < 0) break;
             // lane g keeps the state of query slot g
             int my_q = -1;
             uint32_t my_lim = 0;
             if (lane < d.g_cnt) {
-                my_q = descs[ib].pair[lane] / a.P;
-                const uint32_t t = descs[ib].gthr[lane];
+                my_q = descs[id].pair[lane] / a.P;
+                const uint32_t t = descs[id].gthr[lane];
                 my_lim = t < KEY_MAX ? t : KEY_MAX - 1;  // KEY_MAX marks an invalid row
             }
             const int ntiles = (d.nrows + TM - 1) / TM;
@@ -362,18 +371,46 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) scan_mma_kernel(const ScanArgs
                         const float sc = kIP ? -dot : fmaf(-2.f, dot, nrm);
                         const uint32_t key = (r < tr) ? f2key(sc) : KEY_MAX;
                         v[g] = key;
-                        uint32_t lim = __shfl_sync(0xffffffffu, my_lim, g);
-                        unsigned m = __ballot_sync(0xffffffffu, key <= lim);
-                        if (kc <= 28 && __popc(m) > kc + 2) {
-                            // a loose (stale or missing) threshold: these 32 rows alone bound the kc-th best key
-                            const uint32_t t = warp_kth_smallest(key, kc);
-                            if (t < lim) {
-                                lim = t;
-                                m = __ballot_sync(0xffffffffu, key <= lim);
-                                if (lane == g) { atomicMin(a.gthr + my_q, lim); my_lim = lim; }
+                        const uint32_t lim = __shfl_sync(0xffffffffu, my_lim, g);
+                        const unsigned m = __ballot_sync(0xffffffffu, key <= lim);
+                        if (lane == g) mymask = m;
+                    }
+                }
+                // A query whose threshold is loose (missing or stale) would flood its candidate buffer: when the
+                // four warps of the group together pass more than 2*kc of the tile's 128 rows, the tile alone
+                // bounds the kc-th best key -- exchange the keys through shared memory and bisect.
+                if (kc <= 64) {
+                    uint32_t* gx = xch + eg * 256;
+                    gx[128 + q4 * 32 + lane] = __popc(mymask);
+                    asm volatile("bar.sync %0, 128;" ::"r"(1 + eg) : "memory");
+                    const uint32_t tot = gx[128 + lane] + gx[160 + lane] + gx[192 + lane] + gx[224 + lane];
+                    unsigned loose = __ballot_sync(0xffffffffu, lane < d.g_cnt && tot > 2u * (uint32_t)kc);
+                    asm volatile("bar.sync %0, 128;" ::"r"(1 + eg) : "memory");
+#pragma unroll
+                    for (int g = 0; g < MMA_NQ; ++g) {
+                        if ((loose >> g) & 1u) {  // identical in the four warps of the group
+                            gx[q4 * 32 + lane] = v[g];
+                            asm volatile("bar.sync %0, 128;" ::"r"(1 + eg) : "memory");
+                            const uint32_t k0 = gx[lane], k1 = gx[32 + lane], k2 = gx[64 + lane], k3 = gx[96 + lane];
+                            uint32_t lo = 0;
+#pragma unroll 1
+                            for (int bit = 31; bit >= 0; --bit) {
+                                const uint32_t cand = lo | (1u << bit);
+                                const int c = __popc(__ballot_sync(0xffffffffu, k0 < cand)) + __popc(__ballot_sync(0xffffffffu, k1 < cand)) +
+                                              __popc(__ballot_sync(0xffffffffu, k2 < cand)) + __popc(__ballot_sync(0xffffffffu, k3 < cand));
+                                if (c < kc) lo = cand;
+                            }
+                            asm volatile("bar.sync %0, 128;" ::"r"(1 + eg) : "memory");
+                            const uint32_t lim = __shfl_sync(0xffffffffu, my_lim, g);
+                            if (lo < lim) {  // lo = kc-th smallest key of the tile
+                                const unsigned m = __ballot_sync(0xffffffffu, v[g] <= lo);
+                                if (lane == g) {
+                                    mymask = m;
+                                    my_lim = lo;
+                                    if (q4 == 0) atomicMin(a.gthr + my_q, lo);
+                                }
                             }
                         }
-                        if (lane == g) mymask = m;
                     }
                 }
                 // reserve buffer slots: one atomic per query with a passing row, all queries in one instruction
@@ -415,7 +452,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) scan_mma_kernel(const ScanArgs
                 if (g_now < my_lim) my_lim = g_now;
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(b_empty + ib);
+            if (lane == 0) mbar_arrive(i_empty + id);
         }
     }
     // ---- teardown: all tensor-memory traffic of this CTA has completed once every role has left its loop
