@@ -332,6 +332,80 @@ __device__ __forceinline__ uint32_t radix_select(KeyAt key_at, int n, int kc, ui
 }
 
 // ------------------------------------------------------------------------------------------------
+// 3b. threshold seeds
+// ------------------------------------------------------------------------------------------------
+// One warp per query: the kc-th smallest filter score over a small sample of the query's probed rows (the first
+// `sample` rows of its first probed lists, scored on the FP32 pipe) is an upper bound on the kc-th smallest over
+// all of them, so the scan starts with a useful threshold instead of admitting everything. The sample is scored
+// in different arithmetic than the scan kernel (plain FMA chain vs. split TF32 / FFMA2 tiles), so the bound is
+// widened by more than the two error bounds together.
+template <bool kIP>
+__global__ void __launch_bounds__(256) seed_thresholds_kernel(const float* __restrict__ vecs, int64_t pitch,
+                                                              const float* __restrict__ norms, int d, int dp,
+                                                              const float* __restrict__ queries, int64_t q_pitch, int64_t Q,
+                                                              const int32_t* __restrict__ pair_seg, int P,
+                                                              const int64_t* __restrict__ seg_row0,
+                                                              const int32_t* __restrict__ seg_rows, int kc, int sample,
+                                                              float max_row_norm, float rel_margin,
+                                                              uint32_t* __restrict__ gthr) {
+    extern __shared__ __align__(16) float seed_sm[];  // [8 warps][dp] queries, then [8 warps][sample] keys
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t q = (int64_t)blockIdx.x * 8 + warp;
+    if (q >= Q) return;
+    float* qs = seed_sm + (size_t)warp * dp;
+    uint32_t* keys = reinterpret_cast<uint32_t*>(seed_sm + (size_t)8 * dp) + (size_t)warp * sample;
+    float qq = 0.f;
+    for (int i = lane; i < dp; i += 32) {
+        const float x = i < d ? queries[q * q_pitch + i] : 0.f;
+        qs[i] = x;
+        qq = fmaf(x, x, qq);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) qq += __shfl_xor_sync(0xffffffffu, qq, o);
+    __syncwarp();
+    const float4* q4 = reinterpret_cast<const float4*>(qs);
+    // the first `sample` rows of the query's probed segments, in probe order
+    int have = 0;
+    for (int j = 0; j < P && have < sample; ++j) {
+        const int seg = pair_seg[q * P + j];
+        if (seg < 0) continue;
+        const int take = min(seg_rows[seg], sample - have);
+        const int64_t r0 = seg_row0[seg];
+        for (int i = lane; i < take; i += 32) {
+            const int64_t row = r0 + i;
+            const float4* v4 = reinterpret_cast<const float4*>(vecs + row * pitch);
+            float a0 = 0.f, a1 = 0.f;
+            for (int c = 0; c < (dp >> 2); ++c) {
+                const float4 x = __ldg(v4 + c), y = q4[c];
+                a0 = fmaf(x.x, y.x, a0); a1 = fmaf(x.y, y.y, a1);
+                a0 = fmaf(x.z, y.z, a0); a1 = fmaf(x.w, y.w, a1);
+            }
+            const float dot = a0 + a1;
+            keys[have + i] = f2key(kIP ? -dot : fmaf(-2.f, dot, norms[row]));
+        }
+        have += take;
+    }
+    if (have < kc) return;  // fewer sampled rows than candidates wanted: no bound
+    for (int i = have + lane; i < sample; i += 32) keys[i] = KEY_MAX;
+    __syncwarp();
+    const int nslot = (have + 31) >> 5;
+    uint32_t lo = 0;  // kc-th smallest key of the sample, by bisection on the key bits
+#pragma unroll 1
+    for (int bit = 31; bit >= 0; --bit) {
+        const uint32_t cand = lo | (1u << bit);
+        int c = 0;
+        for (int s = 0; s < nslot; ++s) c += __popc(__ballot_sync(0xffffffffu, keys[s * 32 + lane] < cand));
+        if (c < kc) lo = cand;
+    }
+    if (lane == 0 && lo < KEY_MAX) {
+        const float t = key2f(lo);
+        const float margin = __fadd_ru(__fmul_ru(rel_margin, __fmul_ru(sqrtf(qq), max_row_norm)), fabsf(t) * 9.5367431640625e-07f);
+        const float tm = __fadd_ru(t, margin);
+        if (tm == tm) atomicMin(gthr + q, f2key(tm));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // 4. the scan (filter) kernel
 // ------------------------------------------------------------------------------------------------
 struct ScanArgs {
@@ -769,6 +843,7 @@ struct MergeArgs {
     float* out_dist;
     int64_t* out_rows;
     int force_rescan;
+    const int32_t* seg_rows;
     int rank_squared;  // l2 only: order by the squared distance (k-means assign: faiss Top1 on squared l2)
 };
 
@@ -781,13 +856,13 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_refine_kernel(const Merge
     uint64_t* rkey = reinterpret_cast<uint64_t*>(qs + ((a.d + 3) & ~3));   // [kcp] (distkey<<32 | slot)
     int64_t* rid = reinterpret_cast<int64_t*>(rkey + kcp);                 // [kcp]
     uint32_t* rrow = reinterpret_cast<uint32_t*>(rid + kcp);               // [kcp]
-    __shared__ int s_n;
+    __shared__ int s_n, s_tot;
     __shared__ double s_qn;
 
     const int64_t q = blockIdx.x;
     const int tid = threadIdx.x;
     const float inf_pad = kIP ? -INFINITY : INFINITY;
-    if (tid == 0) { s_n = 0; }
+    if (tid == 0) { s_n = 0; s_tot = 0; }
     for (int i = tid; i < a.d; i += blockDim.x) qs[i] = a.queries[q * a.q_pitch + i];
     __syncthreads();
     if (tid == 0) {
@@ -818,6 +893,19 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_refine_kernel(const Merge
     }
     overflow = __syncthreads_or(overflow);
     int ns = s_n;
+    if (ns < a.kc && !overflow) {
+        // Fewer survivors than candidates wanted is only legitimate when the query probed fewer than kc rows
+        // altogether (every threshold is an upper bound on the kc-th best key). Anything else means a threshold
+        // was too tight: leave the query to the exact re-scan.
+        int total = 0;
+        for (int j = tid; j < a.P; j += blockDim.x) {
+            const int seg = a.pair_seg[q * a.P + j];
+            if (seg >= 0) total += a.seg_rows[seg];
+        }
+        if (total) atomicAdd(&s_tot, total);
+        __syncthreads();
+        overflow = s_tot > ns;
+    }
     bool rescan = overflow || a.force_rescan;
     int nc = 0;
     if (!rescan) {
@@ -1249,6 +1337,33 @@ int qk::scan_partitions_impl(const qk_store_t* st, const float* queries, int64_t
                                                                               seg_count, gthr, false);
     }
     QK_CUDA(cudaGetLastError());
+    {
+        // threshold seeds from a sample of the query's first probed rows: about 8 * kc of them (pass rate of the
+        // seed ~ 1/8), bounded by the read traffic it costs -- unless the whole store is small enough to sit in
+        // L2 (a flat index / the centroid list, shared by every query)
+        int sample = 32;
+        while (sample < 1024 && sample < 8 * p.kc) sample <<= 1;
+        const size_t store_bytes = (size_t)st->num_rows * st->pitch * sizeof(float);
+        if (store_bytes > ((size_t)32 << 20))
+            while (sample > 32 && (size_t)Q * sample * p.dp * sizeof(float) > ((size_t)96 << 20)) sample >>= 1;
+        const size_t ssm = (size_t)8 * (p.dp + sample) * sizeof(float);
+        if (sample >= p.kc && ssm <= 48 * 1024) {
+            const bool mma_path = (g_scan_variant == 0) && p.dp <= 128;
+            const float rel_margin = 4.f * (float)(st->d + 8) * 5.9604645e-08f + (mma_path ? 4.f * 7.62939453125e-06f : 0.f);
+            const unsigned grid = (unsigned)((Q + 7) / 8);
+            if (metric == QK_METRIC_INNER_PRODUCT)
+                seed_thresholds_kernel<true><<<grid, 256, ssm, stream>>>(st->vectors, st->pitch, st->row_norms, st->d, p.dp,
+                                                                         queries, q_pitch, Q, pair_seg, p.P, st->seg_row0,
+                                                                         st->seg_rows, p.kc, sample, st->max_row_norm,
+                                                                         rel_margin, gthr);
+            else
+                seed_thresholds_kernel<false><<<grid, 256, ssm, stream>>>(st->vectors, st->pitch, st->row_norms, st->d, p.dp,
+                                                                          queries, q_pitch, Q, pair_seg, p.P, st->seg_row0,
+                                                                          st->seg_rows, p.kc, sample, st->max_row_norm,
+                                                                          rel_margin, gthr);
+            QK_CUDA(cudaGetLastError());
+        }
+    }
     prefix_segments_kernel<<<1, 1024, 0, stream>>>(seg_count, S, p.gq, seg_start, item_start, ctrl);
     QK_CUDA(cudaGetLastError());
     {
@@ -1291,6 +1406,7 @@ int qk::scan_partitions_impl(const qk_store_t* st, const float* queries, int64_t
     ma.filter_gam = use_mma ? 7.62939453125e-06 : 0.0;
     ma.out_ids = out_ids; ma.out_dist = out_dist; ma.out_rows = out_rows;
     ma.force_rescan = g_force_rescan;
+    ma.seg_rows = st->seg_rows;
     ma.rank_squared = rank_squared;
     {
         int kcp = 1;

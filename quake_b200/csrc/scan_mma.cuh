@@ -13,15 +13,19 @@
 // The a_lo tile never touches shared memory: the split warps write it to tensor memory (tcgen05.st) and the
 // second MMA of each K-step takes its A operand from there.
 //
-// Roles (14 warps, one persistent CTA per SM):
+// Roles (16 warps, one persistent CTA per SM):
 //   warp 0      producer: work items (atomic counter, metadata pipelined), TMA tensor loads of the row tiles
 //               (box 128 rows x 32 floats, ring of 8), cp.async gather of the query chunk into the swizzled
 //               K-major B layout
 //   warp 1      MMA issuer (one lane): 3 MMAs per K-step, tcgen05.commit onto the pipeline mbarriers
 //   warps 2-5   split: a_lo = a - trunc(a) -> tensor memory, b_lo -> shared memory (once per item)
 //   warps 6-13  epilogue + selection, two groups of four taking alternate tiles: tcgen05.ld of the
-//               accumulators (thread = row, 32 queries in registers), keys, threshold test, append to the
-//               per-query candidate buffers, threshold refresh (same scheme as the FFMA kernel's select warps)
+//               accumulators (thread = row, 32 queries in registers), score vs the query's threshold in the
+//               float domain (one FFMA + one compare per score), thread-level append of the rare survivors to the
+//               per-query candidate buffers (one global atomic per survivor, issued in batches of four)
+//   warps 14-15 threshold refresh, off the critical path: when a query's fill passes a multiple of 64 the
+//               appending thread posts (query, fill) in its warp's mailbox; a refresh warp re-derives the
+//               kc-th smallest key appended so far (radix select over the buffer) and publishes it with atomicMin
 #pragma once
 
 namespace qk {
@@ -34,14 +38,22 @@ static constexpr int MMA_BOX_BYTES = MMA_TM * 128;
 static constexpr int MMA_NB = 3;              // B-operand slots (query chunk hi + lo, 32 KB each)
 static constexpr int MMA_ND = 5;              // work-item descriptor slots (the selection warps lag the MMAs)
 static constexpr int MMA_BBOX_BYTES = MMA_NQ * 128;  // 4 KB: 32 queries x 32 floats
-static constexpr int MMA_THREADS = 32 * 14;
+static constexpr int MMA_THREADS = 32 * 16;
+static constexpr int MMA_SMEM_HEADER = 4096;   // mbarriers, mailboxes, descriptor ring
+static constexpr int MMA_REFRESH_CAP = 1024;   // candidates a refresh looks at (any subset gives a valid bound)
 static constexpr int MMA_TMEM_COLS = 512;
 static constexpr int MMA_TMEM_D = 0;          // 2 accumulator buffers x 32 columns
 static constexpr int MMA_TMEM_ALO = 64;       // MMA_STAGES a_lo boxes x 32 columns
 
+struct MmaDesc {  // published in shared memory by the producer warp for every work item in flight
+    WorkItem w;
+    int q[MMA_NQ];       // query index of every query slot (-1: unused slot)
+    float limf[MMA_NQ];  // the queries' filter-score thresholds (float domain; +inf = none yet, -inf = unused slot)
+};
+
 static size_t scan_mma_smem_bytes() {
-    return (size_t)SCAN_SMEM_HEADER + (size_t)MMA_STAGES * MMA_BOX_BYTES + (size_t)MMA_NB * 8 * MMA_BBOX_BYTES +
-           (size_t)8 * 256 * sizeof(uint32_t) + (size_t)2 * 256 * sizeof(uint32_t) + 1024;
+    return (size_t)MMA_SMEM_HEADER + (size_t)MMA_STAGES * MMA_BOX_BYTES + (size_t)MMA_NB * 8 * MMA_BBOX_BYTES +
+           (size_t)2 * 256 * sizeof(uint32_t) + (size_t)2 * MMA_REFRESH_CAP * sizeof(uint32_t) + 1024;
 }
 
 // ---- tcgen05 wrappers --------------------------------------------------------------------------------------
@@ -112,10 +124,26 @@ __device__ __forceinline__ uint32_t warp_kth_smallest(uint32_t key, int kc) {
     return lo;
 }
 
+// v[g] for a run-time g without spilling v[] to local memory: a 5-level select tree (31 SELs)
+__device__ __forceinline__ uint32_t pick32(const uint32_t (&v)[32], int g) {
+    uint32_t a[16], b[8], c[4];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) a[i] = (g & 1) ? v[2 * i + 1] : v[2 * i];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) b[i] = (g & 2) ? a[2 * i + 1] : a[2 * i];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) c[i] = (g & 4) ? b[2 * i + 1] : b[2 * i];
+    const uint32_t d0 = (g & 8) ? c[1] : c[0], d1 = (g & 8) ? c[3] : c[2];
+    return (g & 16) ? d1 : d0;
+}
+
+// threshold key -> float-domain limit: KEY_MAX (no threshold yet) admits everything but NaN
+__device__ __forceinline__ float key2lim(uint32_t t) { return t == KEY_MAX ? INFINITY : key2f(t); }
+
 template <bool kIP>
 __global__ void __launch_bounds__(MMA_THREADS, 1) scan_mma_kernel(const ScanArgs a, const __grid_constant__ CUtensorMap vmap) {
     constexpr int TM = MMA_TM, NS = MMA_STAGES, NB = MMA_NB, ND = MMA_ND;
-    static_assert(512 + MMA_ND * sizeof(ItemDesc) <= SCAN_SMEM_HEADER, "descriptor ring");
+    static_assert(640 + MMA_ND * sizeof(MmaDesc) <= MMA_SMEM_HEADER, "descriptor ring");
     extern __shared__ __align__(16) unsigned char smem_dyn[];
     unsigned char* smem_raw = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
@@ -130,11 +158,13 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) scan_mma_kernel(const ScanArgs
     uint64_t* d_full = bars + 52;      // [2]  MMA commit                    -> epilogue group
     uint64_t* d_empty = bars + 54;     // [2]  4 epilogue warps              -> MMA issuer
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + 456);
-    ItemDesc* descs = reinterpret_cast<ItemDesc*>(smem_raw + 512);  // [ND]
-    unsigned char* As = smem_raw + SCAN_SMEM_HEADER;                // [NS][128 rows][128 B]
+    volatile uint32_t* ep_done = reinterpret_cast<volatile uint32_t*>(smem_raw + 460);       // epilogue warps that left
+    volatile unsigned long long* mbox = reinterpret_cast<volatile unsigned long long*>(smem_raw + 512);  // [8] refresh requests
+    MmaDesc* descs = reinterpret_cast<MmaDesc*>(smem_raw + 640);    // [ND]
+    unsigned char* As = smem_raw + MMA_SMEM_HEADER;                 // [NS][128 rows][128 B]
     unsigned char* Bs = As + (size_t)NS * MMA_BOX_BYTES;            // [NB][hi: 4 boxes | lo: 4 boxes][32 rows][128 B]
-    uint32_t* hists = reinterpret_cast<uint32_t*>(Bs + (size_t)NB * 8 * MMA_BBOX_BYTES);
-    uint32_t* xch = hists + 8 * 256;  // [2 groups][128 keys | 4 warps x 32 counts] exchange for the tile-level threshold
+    uint32_t* hists = reinterpret_cast<uint32_t*>(Bs + (size_t)NB * 8 * MMA_BBOX_BYTES);  // [2 refresh warps][256]
+    uint32_t* rscratch = hists + 2 * 256;                                                  // [2][MMA_REFRESH_CAP] keys
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int dp = a.dp, kc = a.kc;
@@ -145,6 +175,8 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) scan_mma_kernel(const ScanArgs
         for (int s = 0; s < ND; ++s) { mbar_init(i_full + s, 1); mbar_init(i_empty + s, 13); }
         for (int s = 0; s < 2; ++s) { mbar_init(d_full + s, 1); mbar_init(d_empty + s, 4); }
         mbar_fence_init();
+        *ep_done = 0;
+        for (int s = 0; s < 8; ++s) mbox[s] = 0ull;
     }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(MMA_TMEM_COLS));
@@ -157,11 +189,13 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) scan_mma_kernel(const ScanArgs
 
     if (warp == 0) {
         // ===================================================================== producer
+        // Work items are taken from an atomic counter three items ahead; every metadata load (index -> item ->
+        // pair ids -> thresholds) is consumed one iteration after it was issued, so none of them is waited for.
         const int n_items = a.ctrl[1];
-        auto fetch_index = [&]() {
+        auto fetch_index = [&]() {  // lane 0 holds the result; broadcast where it is consumed
             int it = 0;
             if (lane == 0) it = atomicAdd(&a.ctrl[0], 1);
-            return __shfl_sync(0xffffffffu, it, 0);
+            return it;
         };
         auto fetch_item = [&](int it) {
             WorkItem w;
@@ -169,19 +203,21 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) scan_mma_kernel(const ScanArgs
             if (it < n_items) w = a.items[it];
             return w;
         };
-        auto fetch_pair = [&](const WorkItem& w) { return (w.seg >= 0 && lane < w.g_cnt) ? a.seg_pairs[w.g_begin + lane] : -1; };
-        auto fetch_gthr = [&](int pair) { return pair >= 0 ? __ldcg(a.gthr + pair / a.P) : KEY_MAX; };
-        WorkItem m0 = fetch_item(fetch_index());
-        WorkItem m1 = fetch_item(fetch_index());
-        WorkItem m2 = fetch_item(fetch_index());
-        int pair0 = fetch_pair(m0);
-        int pair1 = fetch_pair(m1);
-        uint32_t gthr0 = fetch_gthr(pair0);
+        // query index of this lane's slot (the pair index is query * P + slot)
+        auto fetch_query = [&](const WorkItem& w) { return (w.seg >= 0 && lane < w.g_cnt) ? a.seg_pairs[w.g_begin + lane] / a.P : -1; };
+        auto fetch_gthr = [&](int q) { return q >= 0 ? __ldcg(a.gthr + q) : KEY_MAX; };
+        WorkItem m0 = fetch_item(__shfl_sync(0xffffffffu, fetch_index(), 0));
+        WorkItem m1 = fetch_item(__shfl_sync(0xffffffffu, fetch_index(), 0));
+        int it2 = fetch_index();
+        int q0 = fetch_query(m0);
+        int q1 = fetch_query(m1);
+        uint32_t gthr0 = fetch_gthr(q0);
+        WorkItem m2 = fetch_item(__shfl_sync(0xffffffffu, it2, 0));
         uint32_t U = 0;
         const int dp4 = dp >> 2;
         for (uint32_t n = 0;; ++n) {
             const int ib = n % NB, id = n % ND;
-            const int it3 = fetch_index();
+            const int it3 = fetch_index();  // consumed at the end of this iteration
             mbar_wait(i_empty + id, ((n / ND) & 1u) ^ 1u);
             if (m0.seg < 0) {
                 if (lane == 0) {
@@ -192,8 +228,8 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) scan_mma_kernel(const ScanArgs
             }
             const int g_cnt = m0.g_cnt, nrows = m0.nrows;
             const int64_t row0 = m0.row0;
-            descs[id].pair[lane] = pair0;
-            descs[id].gthr[lane] = gthr0;
+            descs[id].q[lane] = q0;
+            descs[id].limf[lane] = q0 >= 0 ? key2lim(gthr0) : -INFINITY;
             if (lane == 0) descs[id].w = m0;
             __syncwarp();
             if (lane == 0) mbar_arrive(i_full + id);
@@ -203,7 +239,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) scan_mma_kernel(const ScanArgs
             {
                 unsigned char* bhi = Bs + (size_t)ib * 8 * MMA_BBOX_BYTES;
                 for (int g = 0; g < g_cnt; ++g) {
-                    const int64_t q = __shfl_sync(0xffffffffu, pair0, g) / a.P;
+                    const int64_t q = __shfl_sync(0xffffffffu, q0, g);
                     const float* src = a.queries + q * a.q_pitch;
                     for (int c = lane; c < nbox * 8; c += 32) {
                         unsigned char* dst = bhi + (size_t)(c >> 3) * MMA_BBOX_BYTES + g * 128 + (((c & 7) ^ (g & 7)) << 4);
@@ -226,11 +262,11 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) scan_mma_kernel(const ScanArgs
                     __syncwarp();
                 }
             }
-            const int pair2 = fetch_pair(m2);
-            m0 = m1; pair0 = pair1;
-            m1 = m2; pair1 = pair2;
-            m2 = fetch_item(it3);
-            gthr0 = fetch_gthr(pair0);
+            const int q2 = fetch_query(m2);
+            m0 = m1; q0 = q1;
+            m1 = m2; q1 = q2;
+            m2 = fetch_item(__shfl_sync(0xffffffffu, it3, 0));
+            gthr0 = fetch_gthr(q0);
         }
     } else if (warp == 1) {
         // ===================================================================== MMA issuer
@@ -325,34 +361,30 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) scan_mma_kernel(const ScanArgs
                 }
             }
         }
-    } else {
+    } else if (warp < 14) {
         // ===================================================================== epilogue + selection
         const int eg = (warp - 6) >> 2;  // group: takes tiles with (T & 1) == eg
         const int q4 = warp & 3;
-        uint32_t* hist = hists + (warp - 6) * 256;
         const int qcap = a.qcap;
-        const int step = kc > 64 ? kc : 64;
-        const unsigned below = (1u << lane) - 1u;
+        volatile unsigned long long* my_box = mbox + (warp - 6);
         uint32_t T = 0;
         for (uint32_t n = 0;; ++n) {
             const int id = n % ND;
             mbar_wait(i_full + id, (n / ND) & 1u);
             const WorkItem d = descs[id].w;
             if (d.seg < 0) break;
-            // lane g keeps the state of query slot g
-            int my_q = -1;
-            uint32_t my_lim = 0;
-            if (lane < d.g_cnt) {
-                my_q = descs[id].pair[lane] / a.P;
-                const uint32_t t = descs[id].gthr[lane];
-                my_lim = t < KEY_MAX ? t : KEY_MAX - 1;  // KEY_MAX marks an invalid row
-            }
+            const int g_cnt = d.g_cnt;
+            const uint32_t gvalid = g_cnt >= 32 ? 0xffffffffu : ((1u << g_cnt) - 1u);
+            const int* dq = descs[id].q;
+            float* limf = descs[id].limf;
+            const int my_q = dq[lane];  // lane g watches query slot g's global threshold
             const int ntiles = (d.nrows + TM - 1) / TM;
             for (int tile = 0; tile < ntiles; ++tile, ++T) {
                 if ((int)(T & 1u) != eg) continue;
                 const int tr = min(TM, d.nrows - tile * TM);
                 const int r = q4 * 32 + lane;
-                const uint32_t g_now = my_q >= 0 ? __ldcg(a.gthr + my_q) : 0u;
+                // what every other SM has learnt about the queries meanwhile (folded in after this tile)
+                const uint32_t g_now = my_q >= 0 ? __ldcg(a.gthr + my_q) : KEY_MAX;
                 float nrm = 0.f;
                 if (!kIP && r < tr) nrm = __ldg(a.norms + d.row0 + (int64_t)tile * TM + r);
                 mbar_wait(d_full + eg, (T >> 1) & 1u);
@@ -362,97 +394,108 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) scan_mma_kernel(const ScanArgs
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(d_empty + eg);
-                // keys of this thread's row for every query slot; pass masks (lane g keeps query g's mask)
-                unsigned mymask = 0;
+                // ---- scores of this thread's row against the 32 query slots; bit g of pm: the score passes
+                uint32_t pm = 0;
 #pragma unroll
-                for (int g = 0; g < MMA_NQ; ++g) {
-                    if (g < d.g_cnt) {  // warp-uniform
+                for (int g4 = 0; g4 < 8; ++g4) {
+                    const float4 L = reinterpret_cast<const float4*>(limf)[g4];
+                    const float lim[4] = {L.x, L.y, L.z, L.w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int g = 4 * g4 + j;
                         const float dot = __uint_as_float(v[g]);
                         const float sc = kIP ? -dot : fmaf(-2.f, dot, nrm);
-                        const uint32_t key = (r < tr) ? f2key(sc) : KEY_MAX;
-                        v[g] = key;
-                        const uint32_t lim = __shfl_sync(0xffffffffu, my_lim, g);
-                        const unsigned m = __ballot_sync(0xffffffffu, key <= lim);
-                        if (lane == g) mymask = m;
+                        v[g] = __float_as_uint(sc);
+                        pm |= (sc <= lim[j]) ? (1u << g) : 0u;
                     }
                 }
-                // A query whose threshold is loose (missing or stale) would flood its candidate buffer: when the
-                // four warps of the group together pass more than 2*kc of the tile's 128 rows, the tile alone
-                // bounds the kc-th best key -- exchange the keys through shared memory and bisect.
-                if (kc <= 64) {
-                    uint32_t* gx = xch + eg * 256;
-                    gx[128 + q4 * 32 + lane] = __popc(mymask);
-                    asm volatile("bar.sync %0, 128;" ::"r"(1 + eg) : "memory");
-                    const uint32_t tot = gx[128 + lane] + gx[160 + lane] + gx[192 + lane] + gx[224 + lane];
-                    unsigned loose = __ballot_sync(0xffffffffu, lane < d.g_cnt && tot > 2u * (uint32_t)kc);
-                    asm volatile("bar.sync %0, 128;" ::"r"(1 + eg) : "memory");
-#pragma unroll
-                    for (int g = 0; g < MMA_NQ; ++g) {
-                        if ((loose >> g) & 1u) {  // identical in the four warps of the group
-                            gx[q4 * 32 + lane] = v[g];
-                            asm volatile("bar.sync %0, 128;" ::"r"(1 + eg) : "memory");
-                            const uint32_t k0 = gx[lane], k1 = gx[32 + lane], k2 = gx[64 + lane], k3 = gx[96 + lane];
-                            uint32_t lo = 0;
-#pragma unroll 1
-                            for (int bit = 31; bit >= 0; --bit) {
-                                const uint32_t cand = lo | (1u << bit);
-                                const int c = __popc(__ballot_sync(0xffffffffu, k0 < cand)) + __popc(__ballot_sync(0xffffffffu, k1 < cand)) +
-                                              __popc(__ballot_sync(0xffffffffu, k2 < cand)) + __popc(__ballot_sync(0xffffffffu, k3 < cand));
-                                if (c < kc) lo = cand;
-                            }
-                            asm volatile("bar.sync %0, 128;" ::"r"(1 + eg) : "memory");
-                            const uint32_t lim = __shfl_sync(0xffffffffu, my_lim, g);
-                            if (lo < lim) {  // lo = kc-th smallest key of the tile
-                                const unsigned m = __ballot_sync(0xffffffffu, v[g] <= lo);
-                                if (lane == g) {
-                                    mymask = m;
-                                    my_lim = lo;
-                                    if (q4 == 0) atomicMin(a.gthr + my_q, lo);
-                                }
-                            }
-                        }
-                    }
-                }
-                // reserve buffer slots: one atomic per query with a passing row, all queries in one instruction
-                const int nn = __popc(mymask);
-                int base = 0;
-                if (nn > 0) base = atomicAdd(&a.qcount[my_q], nn);
-                unsigned todo = __ballot_sync(0xffffffffu, nn > 0);
-                unsigned cross = 0;
+                pm &= gvalid;
+                if (r >= tr) pm = 0;
+                // ---- survivors: one atomic each (issued four at a time), then the entry stores
                 const uint32_t arow = (uint32_t)(d.row0 + (int64_t)tile * TM + r);
+                while (__any_sync(0xffffffffu, pm != 0)) {
+                    int qs[4], base[4];
+                    uint32_t key[4];
 #pragma unroll
-                for (int g = 0; g < MMA_NQ; ++g) {
-                    if ((todo >> g) & 1u) {  // warp-uniform
-                        const unsigned m = __shfl_sync(0xffffffffu, mymask, g);
-                        const int bb = __shfl_sync(0xffffffffu, base, g);
-                        const int q = __shfl_sync(0xffffffffu, my_q, g);
-                        if ((m >> lane) & 1u) {
-                            const int slot = bb + __popc(m & below);
-                            if (slot < qcap) a.qbuf[(size_t)q * qcap + slot] = ((uint64_t)v[g] << 32) | arow;
+                    for (int i = 0; i < 4; ++i) {
+                        qs[i] = -1;
+                        key[i] = 0;
+                        if (pm) {
+                            const int g = __ffs(pm) - 1;
+                            pm &= pm - 1;
+                            qs[i] = dq[g];
+                            key[i] = f2key(__uint_as_float(pick32(v, g)));
                         }
-                        const int e = bb + __popc(m);
-                        if (bb / step != e / step && e >= kc) cross |= 1u << g;
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) base[i] = qs[i] >= 0 ? atomicAdd(&a.qcount[qs[i]], 1) : 0;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        if (qs[i] >= 0) {
+                            const int slot = base[i];
+                            if (slot < qcap) a.qbuf[(size_t)qs[i] * qcap + slot] = ((uint64_t)key[i] << 32) | arow;
+                            // the fill passed a multiple of 64: ask a refresh warp for a new threshold (a busy
+                            // mailbox just drops the request -- thresholds are an optimisation)
+                            if ((slot & 63) == 63 && slot + 1 >= kc && *my_box == 0ull)
+                                *my_box = ((unsigned long long)(qs[i] + 1) << 32) | (uint32_t)(slot + 1);
+                        }
                     }
                 }
-                // refresh the thresholds of the queries whose fill passed a multiple of `step`
-                if (cross) __threadfence();
-                while (cross) {
-                    const int g = __ffs(cross) - 1;
-                    cross &= cross - 1;
-                    const int q = __shfl_sync(0xffffffffu, my_q, g);
-                    const int fill = __shfl_sync(0xffffffffu, base + nn, g);
-                    const unsigned long long* qb = reinterpret_cast<const unsigned long long*>(a.qbuf) + (size_t)q * qcap;
-                    const uint32_t t = radix_select([qb](int i) { return (uint32_t)(__ldcg(qb + i) >> 32); },
-                                                    fill < qcap ? fill : qcap, kc, hist, lane);
-                    if (t < KEY_MAX) {
-                        if (lane == 0) atomicMin(a.gthr + q, t);
-                        if (lane == g && t < my_lim) my_lim = t;
-                    }
+                // fold in the global thresholds read at the top of the tile (a benign race between the two groups:
+                // every value ever written is a valid upper bound)
+                if (q4 == 0 && my_q >= 0) {
+                    const float f = key2lim(g_now);
+                    if (f < limf[lane]) limf[lane] = f;
                 }
-                if (g_now < my_lim) my_lim = g_now;
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(i_empty + id);
+        }
+        __syncwarp();
+        if (lane == 0) atomicAdd(const_cast<uint32_t*>(ep_done), 1u);
+    } else {
+        // ===================================================================== threshold refresh (off the critical path)
+        const int rw = warp - 14;  // serves the mailboxes of epilogue warps 4*rw .. 4*rw+3
+        uint32_t* hist = hists + rw * 256;
+        uint32_t* keys = rscratch + rw * MMA_REFRESH_CAP;
+        const int qcap = a.qcap;
+        for (;;) {
+            bool did = false;
+            for (int i = 0; i < 4; ++i) {
+                volatile unsigned long long* mb = mbox + rw * 4 + i;
+                const unsigned long long req = *mb;
+                if (req == 0ull) continue;  // warp-uniform: every lane read the same word
+                did = true;
+                const int q = (int)(req >> 32) - 1;
+                int fill = (int)(uint32_t)req;
+                if (fill > qcap) fill = qcap;
+                // the most recent entries carry the tightest keys; any subset yields a valid upper bound
+                const int n = fill < MMA_REFRESH_CAP ? fill : MMA_REFRESH_CAP;
+                const unsigned long long* qb = reinterpret_cast<const unsigned long long*>(a.qbuf) + (size_t)q * qcap + (fill - n);
+                for (int base = 0; base < n; base += 256) {
+                    unsigned long long e[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int idx = base + j * 32 + lane;
+                        e[j] = idx < n ? __ldcg(qb + idx) : ~0ull;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int idx = base + j * 32 + lane;
+                        if (idx < n) keys[idx] = (uint32_t)(e[j] >> 32);
+                    }
+                }
+                __syncwarp();
+                const uint32_t* kk = keys;
+                const uint32_t t = radix_select([kk](int i2) { return kk[i2]; }, n, kc, hist, lane);
+                if (t < KEY_MAX && lane == 0) atomicMin(a.gthr + q, t);
+                __syncwarp();
+                if (lane == 0) *mb = 0ull;
+            }
+            if (!did) {
+                if (*ep_done >= 8u) break;
+                __nanosleep(200);
+            }
         }
     }
     // ---- teardown: all tensor-memory traffic of this CTA has completed once every role has left its loop

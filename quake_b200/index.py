@@ -25,7 +25,6 @@ from .store import PartitionStore
 SERIALIZATION_MAGIC = 0x44494E4C  # common.h:66
 SERIALIZATION_VERSION = 3         # common.h:67
 _WORKSPACE_LIMIT = 6 << 30        # split query batches whose scan workspace would exceed this
-_FINE_SEGMENT_PAIRS = 1024        # batches with fewer (query, list) pairs use the fine segment cut
 
 
 def _stream():
@@ -46,7 +45,7 @@ def scan_partitions(store: PartitionStore, xq: torch.Tensor, probe_slots: torch.
     Returns (ids [Q,k] int64, distances [Q,k] float32[, rows]) on the device."""
     lib = _lib.load()
     Q, nprobe = int(probe_slots.shape[0]), int(probe_slots.shape[1])
-    st, _ = store.tables(fine=Q * nprobe < _FINE_SEGMENT_PAIRS)
+    st, _ = store.tables(store.segment_len(Q, nprobe))
     dev = xq.device
     out_ids = torch.empty((Q, k), dtype=torch.int64, device=dev)
     out_dist = torch.empty((Q, k), dtype=torch.float32, device=dev)

@@ -329,21 +329,31 @@ class PartitionStore:
         self.max_row_norm = max(norm, self.max_row_norm)
 
     # ------------------------------------------------------------------ device tables for the kernels
-    def tables(self, fine: bool = False):
-        """(QkStore struct, id_to_slot tensor); rebuilt lazily after any mutation.
+    def segment_len(self, num_queries: int, nprobe: int) -> int:
+        """Scan-segment length for a batch. A work item of the scan kernel is (segment, chunk of <= 32 queries);
+        IVF lists are short and numerous, so the default cut (QK_SEGMENT_ROWS) leaves them whole. A store of a
+        few long lists (a flat index / the centroid list is ONE list) is cut finer until the batch yields a few
+        items per SM."""
+        if num_queries * nprobe < 1024:
+            return 256
+        if self.nlist > 16 or self.list_size.size == 0:
+            return _MAX_SEGMENT_ROWS
+        chunks = max(1, (num_queries + 31) // 32) * min(self.nlist, nprobe)
+        longest = max(int(self.list_size.max()), 1)
+        seg_len = _MAX_SEGMENT_ROWS
+        while seg_len > 256 and chunks * ((longest + seg_len - 1) // seg_len) < 4 * 148:
+            seg_len //= 2
+        return seg_len
 
-        Lists are cut into scan segments. The default cut (QK_SEGMENT_ROWS) keeps a segment far longer than
-        the candidate count kept per (query, segment), which is what makes the streaming top-k cheap; the
-        parallelism of a large batch comes from chunking the queries. `fine=True` cuts at 256 rows instead:
-        for small batches (few (query, list) pairs) that is what spreads a long list -- a flat index is ONE
-        list -- over the SMs."""
-        key = "fine" if fine else "coarse"
+    def tables(self, seg_len: int = _MAX_SEGMENT_ROWS):
+        """(QkStore struct, id_to_slot tensor) for scan segments of `seg_len` rows; rebuilt lazily after any
+        mutation."""
+        key = int(seg_len)
         if self._dirty:
             self._cache = {}
             self._dirty = False
         if key in self._cache:
             return self._cache[key]
-        seg_len = 256 if fine else _MAX_SEGMENT_ROWS
         nslots = self.slot_pid.size
         size = self.list_size
         nseg = (size + seg_len - 1) // seg_len
