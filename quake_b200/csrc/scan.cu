@@ -371,17 +371,22 @@ __global__ void __launch_bounds__(256) seed_thresholds_kernel(const float* __res
         if (seg < 0) continue;
         const int take = min(seg_rows[seg], sample - have);
         const int64_t r0 = seg_row0[seg];
-        for (int i = lane; i < take; i += 32) {
-            const int64_t row = r0 + i;
-            const float4* v4 = reinterpret_cast<const float4*>(vecs + row * pitch);
-            float a0 = 0.f, a1 = 0.f;
-            for (int c = 0; c < (dp >> 2); ++c) {
-                const float4 x = __ldg(v4 + c), y = q4[c];
-                a0 = fmaf(x.x, y.x, a0); a1 = fmaf(x.y, y.y, a1);
-                a0 = fmaf(x.z, y.z, a0); a1 = fmaf(x.w, y.w, a1);
+        // eight lanes per row (coalesced 128-byte pieces), four rows per step
+        for (int i0 = 0; i0 < take; i0 += 4) {
+            const int i = i0 + (lane >> 3);
+            float acc = 0.f;
+            if (i < take) {
+                const float4* v4 = reinterpret_cast<const float4*>(vecs + (r0 + i) * pitch);
+                for (int c = lane & 7; c < (dp >> 2); c += 8) {
+                    const float4 x = __ldg(v4 + c), y = q4[c];
+                    acc = fmaf(x.x, y.x, acc); acc = fmaf(x.y, y.y, acc);
+                    acc = fmaf(x.z, y.z, acc); acc = fmaf(x.w, y.w, acc);
+                }
             }
-            const float dot = a0 + a1;
-            keys[have + i] = f2key(kIP ? -dot : fmaf(-2.f, dot, norms[row]));
+            acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+            acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+            acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+            if (i < take && (lane & 7) == 0) keys[have + i] = f2key(kIP ? -acc : fmaf(-2.f, acc, norms[r0 + i]));
         }
         have += take;
     }

@@ -11,14 +11,16 @@
 // which leaves a relative error of about 2^-20 per dot product (measured: scripts/umma_probe.cu) -- the filter
 // only has to be good enough for the exact refine + error-bound proof that follows it (merge_refine_kernel).
 // The a_lo tile never touches shared memory: the split warps write it to tensor memory (tcgen05.st) and the
-// second MMA of each K-step takes its A operand from there.
+// second MMA of each K-step takes its A operand from there. b_hi and b_lo sit side by side in one K-major tile
+// (rows 0-31 / 32-63), so a_hi * [b_hi | b_lo] is ONE MMA with N = 64 whose two halves the epilogue adds: two
+// MMAs per K-step instead of three (the single issuing thread is the scarce resource, not the tensor pipe).
 //
 // Roles (16 warps, one persistent CTA per SM):
 //   warp 0      producer: work items (atomic counter, metadata pipelined), TMA tensor loads of the row tiles
-//               (box 128 rows x 32 floats, ring of 8), cp.async gather of the query chunk into the swizzled
-//               K-major B layout
-//   warp 1      MMA issuer (one lane): 3 MMAs per K-step, tcgen05.commit onto the pipeline mbarriers
-//   warps 2-5   split: a_lo = a - trunc(a) -> tensor memory, b_lo -> shared memory (once per item)
+//               (box 128 rows x 32 floats, ring of 8)
+//   warp 1      MMA issuer (one lane): 2 MMAs per K-step, tcgen05.commit onto the pipeline mbarriers
+//   warps 2-5   split: a_lo = a - trunc(a) -> tensor memory; gather of the item's query chunk (prefetched one item
+//               ahead) into the swizzled K-major B tiles, b_hi and b_lo
 //   warps 6-13  epilogue + selection, two groups of four taking alternate tiles: tcgen05.ld of the
 //               accumulators (thread = row, 32 queries in registers), score vs the query's threshold in the
 //               float domain (one FFMA + one compare per score), thread-level append of the rare survivors to the
@@ -33,17 +35,17 @@ namespace qk {
 static constexpr int MMA_TM = 128;            // rows per tile (UMMA M)
 static constexpr int MMA_NQ = 32;             // query slots per item (UMMA N)
 static constexpr int MMA_BOX = 32;            // floats per TMA box row (128 B, one swizzle atom row)
-static constexpr int MMA_STAGES = 6;          // ring of A boxes, 16 KB each
+static constexpr int MMA_STAGES = 8;          // ring of A boxes, 16 KB each (two whole 128-row tiles at d = 128)
 static constexpr int MMA_BOX_BYTES = MMA_TM * 128;
-static constexpr int MMA_NB = 3;              // B-operand slots (query chunk hi + lo, 32 KB each)
+static constexpr int MMA_NB = 2;              // B-operand slots (query chunk hi + lo, 32 KB each)
 static constexpr int MMA_ND = 5;              // work-item descriptor slots (the selection warps lag the MMAs)
-static constexpr int MMA_BBOX_BYTES = MMA_NQ * 128;  // 4 KB: 32 queries x 32 floats
+static constexpr int MMA_BBOX_BYTES = 2 * MMA_NQ * 128;  // 8 KB: (32 queries hi + 32 queries lo) x 32 floats
 static constexpr int MMA_THREADS = 32 * 16;
 static constexpr int MMA_SMEM_HEADER = 4096;   // mbarriers, mailboxes, descriptor ring
 static constexpr int MMA_REFRESH_CAP = 1024;   // candidates a refresh looks at (any subset gives a valid bound)
 static constexpr int MMA_TMEM_COLS = 512;
-static constexpr int MMA_TMEM_D = 0;          // 2 accumulator buffers x 32 columns
-static constexpr int MMA_TMEM_ALO = 64;       // MMA_STAGES a_lo boxes x 32 columns
+static constexpr int MMA_TMEM_D = 0;          // 2 accumulator buffers x 64 columns (a.b_hi | a_hi.b_lo)
+static constexpr int MMA_TMEM_ALO = 128;      // MMA_STAGES a_lo boxes x 32 columns
 
 struct MmaDesc {  // published in shared memory by the producer warp for every work item in flight
     WorkItem w;
@@ -52,7 +54,7 @@ struct MmaDesc {  // published in shared memory by the producer warp for every w
 };
 
 static size_t scan_mma_smem_bytes() {
-    return (size_t)MMA_SMEM_HEADER + (size_t)MMA_STAGES * MMA_BOX_BYTES + (size_t)MMA_NB * 8 * MMA_BBOX_BYTES +
+    return (size_t)MMA_SMEM_HEADER + (size_t)MMA_STAGES * MMA_BOX_BYTES + (size_t)MMA_NB * 4 * MMA_BBOX_BYTES +
            (size_t)2 * 256 * sizeof(uint32_t) + (size_t)2 * MMA_REFRESH_CAP * sizeof(uint32_t) + 1024;
 }
 
@@ -66,23 +68,29 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
 __host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+// The MMA / commit wrappers are called by ALL lanes of the (converged) issuing warp; one elected lane issues.
+// Keeping the election inside the asm spares the per-instruction "elect / retry" loop the compiler wraps around a
+// warp-uniform instruction that sits in a lane-divergent branch.
 __device__ __forceinline__ void umma_ss(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
     asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+        "{\n\t.reg .pred p, e;\n\telect.sync _|e, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
         "l"(da), "l"(db), "r"(idesc), "r"(acc)
         : "memory");
 }
 __device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc, uint32_t acc) {
     asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+        "{\n\t.reg .pred p, e;\n\telect.sync _|e, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(tmem_d),
         "r"(tmem_a), "l"(db), "r"(idesc), "r"(acc)
         : "memory");
 }
-// arrive on `bar` once every tcgen05 operation issued so far by this thread has completed
+// arrive on `bar` once every tcgen05 operation issued so far by the elected thread has completed
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+    asm volatile(
+        "{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
+        "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}\n" ::"r"(smem_u32(bar))
+        : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -99,6 +107,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         : "memory");
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
     asm volatile(
         "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
@@ -150,7 +167,6 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) scan_mma_kernel(const ScanArgs
     uint64_t* a_full = bars;           // [NS] producer (tx)                 -> split warps, MMA issuer
     uint64_t* a_empty = bars + 8;      // [NS] 4 split warps + MMA commit    -> producer
     uint64_t* alo_full = bars + 16;    // [NS] 4 split warps                 -> MMA issuer
-    uint64_t* b_full = bars + 24;      // [NB] 32 producer lanes (cp.async)  -> split warps
     uint64_t* b_ready = bars + 28;     // [NB] 4 split warps (b_lo written)  -> MMA issuer
     uint64_t* b_empty = bars + 32;     // [NB] MMA commit                    -> producer
     uint64_t* i_full = bars + 36;      // [ND] producer (descriptor written) -> every consumer warp
@@ -162,8 +178,8 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) scan_mma_kernel(const ScanArgs
     volatile unsigned long long* mbox = reinterpret_cast<volatile unsigned long long*>(smem_raw + 512);  // [8] refresh requests
     MmaDesc* descs = reinterpret_cast<MmaDesc*>(smem_raw + 640);    // [ND]
     unsigned char* As = smem_raw + MMA_SMEM_HEADER;                 // [NS][128 rows][128 B]
-    unsigned char* Bs = As + (size_t)NS * MMA_BOX_BYTES;            // [NB][hi: 4 boxes | lo: 4 boxes][32 rows][128 B]
-    uint32_t* hists = reinterpret_cast<uint32_t*>(Bs + (size_t)NB * 8 * MMA_BBOX_BYTES);  // [2 refresh warps][256]
+    unsigned char* Bs = As + (size_t)NS * MMA_BOX_BYTES;            // [NB][4 boxes][hi: 32 rows | lo: 32 rows][128 B]
+    uint32_t* hists = reinterpret_cast<uint32_t*>(Bs + (size_t)NB * 4 * MMA_BBOX_BYTES);  // [2 refresh warps][256]
     uint32_t* rscratch = hists + 2 * 256;                                                  // [2][MMA_REFRESH_CAP] keys
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -171,7 +187,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) scan_mma_kernel(const ScanArgs
     const int nbox = (dp + MMA_BOX - 1) / MMA_BOX;  // 1..4
     if (tid == 0) {
         for (int s = 0; s < NS; ++s) { mbar_init(a_full + s, 1); mbar_init(a_empty + s, 5); mbar_init(alo_full + s, 4); }
-        for (int s = 0; s < NB; ++s) { mbar_init(b_full + s, 32); mbar_init(b_ready + s, 4); mbar_init(b_empty + s, 1); }
+        for (int s = 0; s < NB; ++s) { mbar_init(b_ready + s, 4); mbar_init(b_empty + s, 1); }
         for (int s = 0; s < ND; ++s) { mbar_init(i_full + s, 1); mbar_init(i_empty + s, 13); }
         for (int s = 0; s < 2; ++s) { mbar_init(d_full + s, 1); mbar_init(d_empty + s, 4); }
         mbar_fence_init();
@@ -189,8 +205,10 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) scan_mma_kernel(const ScanArgs
 
     if (warp == 0) {
         // ===================================================================== producer
-        // Work items are taken from an atomic counter three items ahead; every metadata load (index -> item ->
-        // pair ids -> thresholds) is consumed one iteration after it was issued, so none of them is waited for.
+        // Work items are taken from an atomic counter several items ahead; every metadata load of the chain
+        // index -> item -> query ids -> thresholds is consumed one iteration after it was issued, so none of them
+        // is waited for. The descriptor of item n+1 is published BEFORE the row tiles of item n are issued, so
+        // the split warps can prefetch its query chunk (B operand) while item n streams.
         const int n_items = a.ctrl[1];
         auto fetch_index = [&]() {  // lane 0 holds the result; broadcast where it is consumed
             int it = 0;
@@ -206,71 +224,66 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) scan_mma_kernel(const ScanArgs
         // query index of this lane's slot (the pair index is query * P + slot)
         auto fetch_query = [&](const WorkItem& w) { return (w.seg >= 0 && lane < w.g_cnt) ? a.seg_pairs[w.g_begin + lane] / a.P : -1; };
         auto fetch_gthr = [&](int q) { return q >= 0 ? __ldcg(a.gthr + q) : KEY_MAX; };
-        WorkItem m0 = fetch_item(__shfl_sync(0xffffffffu, fetch_index(), 0));
-        WorkItem m1 = fetch_item(__shfl_sync(0xffffffffu, fetch_index(), 0));
-        int it2 = fetch_index();
-        int q0 = fetch_query(m0);
-        int q1 = fetch_query(m1);
-        uint32_t gthr0 = fetch_gthr(q0);
-        WorkItem m2 = fetch_item(__shfl_sync(0xffffffffu, it2, 0));
-        uint32_t U = 0;
-        const int dp4 = dp >> 2;
-        for (uint32_t n = 0;; ++n) {
-            const int ib = n % NB, id = n % ND;
-            const int it3 = fetch_index();  // consumed at the end of this iteration
+        // descriptor of item n; false when n is past the last item (the sentinel is published instead)
+        auto issue_desc_b = [&](uint32_t n, const WorkItem& m, int q, uint32_t gthr) {
+            const int id = n % ND;
             mbar_wait(i_empty + id, ((n / ND) & 1u) ^ 1u);
-            if (m0.seg < 0) {
+            if (m.seg < 0) {
                 if (lane == 0) {
                     descs[id].w.seg = -1;
                     mbar_arrive(i_full + id);
                 }
-                break;
+                return false;
             }
-            const int g_cnt = m0.g_cnt, nrows = m0.nrows;
-            const int64_t row0 = m0.row0;
-            descs[id].q[lane] = q0;
-            descs[id].limf[lane] = q0 >= 0 ? key2lim(gthr0) : -INFINITY;
-            if (lane == 0) descs[id].w = m0;
+            descs[id].q[lane] = q;
+            descs[id].limf[lane] = q >= 0 ? key2lim(gthr) : -INFINITY;
+            if (lane == 0) descs[id].w = m;
             __syncwarp();
             if (lane == 0) mbar_arrive(i_full + id);
-            // query chunk -> B_hi in the canonical K-major 128-byte-swizzled layout: box b = 32 floats of every
-            // query, query g at g * 128 B, 16-byte chunk cc stored at cc ^ (g & 7); padding chunks are zeroed
-            mbar_wait(b_empty + ib, ((n / NB) & 1u) ^ 1u);
-            {
-                unsigned char* bhi = Bs + (size_t)ib * 8 * MMA_BBOX_BYTES;
-                for (int g = 0; g < g_cnt; ++g) {
-                    const int64_t q = __shfl_sync(0xffffffffu, q0, g);
-                    const float* src = a.queries + q * a.q_pitch;
-                    for (int c = lane; c < nbox * 8; c += 32) {
-                        unsigned char* dst = bhi + (size_t)(c >> 3) * MMA_BBOX_BYTES + g * 128 + (((c & 7) ^ (g & 7)) << 4);
-                        if (c < dp4) cp_async16(dst, src + 4 * c);
-                        else *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
-                    }
-                }
-                cp_async_mbar_arrive_noinc(b_full + ib);
-            }
-            const int ntiles = (nrows + TM - 1) / TM;
+            return true;
+        };
+        WorkItem cur = fetch_item(__shfl_sync(0xffffffffu, fetch_index(), 0));
+        WorkItem m1 = fetch_item(__shfl_sync(0xffffffffu, fetch_index(), 0));
+        WorkItem m2 = fetch_item(__shfl_sync(0xffffffffu, fetch_index(), 0));
+        WorkItem m3 = fetch_item(__shfl_sync(0xffffffffu, fetch_index(), 0));
+        int i4 = fetch_index();
+        int q1 = fetch_query(m1), q2 = fetch_query(m2);
+        uint32_t g1 = fetch_gthr(q1);
+        bool live;
+        {
+            const int q0 = fetch_query(cur);
+            live = issue_desc_b(0, cur, q0, fetch_gthr(q0));
+        }
+        uint32_t U = 0;
+        for (uint32_t n = 0; live; ++n) {
+            const int i5 = fetch_index();  // consumed two iterations from now
+            const bool next_live = issue_desc_b(n + 1, m1, q1, g1);
+            // ---- row tiles of item n
+            const int ntiles = (cur.nrows + TM - 1) / TM;
             for (int tile = 0; tile < ntiles; ++tile) {
                 for (int b = 0; b < nbox; ++b, ++U) {
                     const int st = U % NS;
                     mbar_wait(a_empty + st, ((U / NS) & 1u) ^ 1u);
                     if (lane == 0) {
                         mbar_expect_tx(a_full + st, (uint32_t)MMA_BOX_BYTES);
-                        tma_load_2d(As + (size_t)st * MMA_BOX_BYTES, &vmap, b * MMA_BOX, (int)(row0 + (int64_t)tile * TM),
+                        tma_load_2d(As + (size_t)st * MMA_BOX_BYTES, &vmap, b * MMA_BOX, (int)(cur.row0 + (int64_t)tile * TM),
                                     a_full + st);
                     }
                     __syncwarp();
                 }
             }
-            const int q2 = fetch_query(m2);
-            m0 = m1; q0 = q1;
-            m1 = m2; q1 = q2;
-            m2 = fetch_item(__shfl_sync(0xffffffffu, it3, 0));
-            gthr0 = fetch_gthr(q0);
+            // ---- rotate the metadata pipeline
+            cur = m1;
+            m1 = m2; q1 = q2; g1 = fetch_gthr(q1);
+            m2 = m3; q2 = fetch_query(m2);
+            m3 = fetch_item(__shfl_sync(0xffffffffu, i4, 0));
+            i4 = i5;
+            live = next_live;
         }
     } else if (warp == 1) {
         // ===================================================================== MMA issuer
-        constexpr uint32_t IDESC = umma_idesc_tf32(MMA_TM, MMA_NQ);
+        constexpr uint32_t IDESC64 = umma_idesc_tf32(MMA_TM, 2 * MMA_NQ);  // a_hi . [b_hi | b_lo]
+        constexpr uint32_t IDESC32 = umma_idesc_tf32(MMA_TM, MMA_NQ);      // a_lo . b_hi
         uint32_t T = 0, U = 0;
         for (uint32_t n = 0;; ++n) {
             const int ib = n % NB, id = n % ND;
@@ -280,65 +293,96 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) scan_mma_kernel(const ScanArgs
             __syncwarp();
             if (lane == 0) mbar_arrive(i_empty + id);  // only the descriptor header was needed
             mbar_wait(b_ready + ib, (n / NB) & 1u);
-            const uint32_t bhi = smem_u32(Bs + (size_t)ib * 8 * MMA_BBOX_BYTES);
-            const uint32_t blo = bhi + 4 * MMA_BBOX_BYTES;
+            const uint32_t bs = smem_u32(Bs + (size_t)ib * 4 * MMA_BBOX_BYTES);
             const int ntiles = (d.nrows + TM - 1) / TM;
             for (int tile = 0; tile < ntiles; ++tile, ++T) {
                 const int db = T & 1u;
                 mbar_wait(d_empty + db, ((T >> 1) & 1u) ^ 1u);
-                const uint32_t tmem_d = tmem + MMA_TMEM_D + db * MMA_NQ;
-                for (int b = 0; b < nbox; ++b, ++U) {
-                    const int st = U % NS;
-                    mbar_wait(a_full + st, (U / NS) & 1u);
-                    mbar_wait(alo_full + st, (U / NS) & 1u);
-                    tc_fence_after();
-                    if (lane == 0) {
-                        const uint32_t abase = smem_u32(As + (size_t)st * MMA_BOX_BYTES);
-                        const uint32_t talo = tmem + MMA_TMEM_ALO + st * MMA_BOX;
-                        const int ksteps = min(4, (dp - b * MMA_BOX + 7) >> 3);
-                        for (int kk = 0; kk < ksteps; ++kk) {
-                            const uint64_t da = umma_desc_sw128(abase + kk * 32);
-                            const uint64_t dbh = umma_desc_sw128(bhi + b * MMA_BBOX_BYTES + kk * 32);
-                            const uint64_t dbl = umma_desc_sw128(blo + b * MMA_BBOX_BYTES + kk * 32);
-                            umma_ss(tmem_d, da, dbh, IDESC, (b | kk) ? 1u : 0u);
-                            umma_ts(tmem_d, talo + kk * 8, dbh, IDESC, 1u);
-                            umma_ss(tmem_d, da, dbl, IDESC, 1u);
-                        }
-                        umma_commit(a_empty + st);  // the row box (and its a_lo columns) may be refilled
-                    }
-                    __syncwarp();
+                const uint32_t tmem_d = tmem + MMA_TMEM_D + db * (2 * MMA_NQ);
+                // The split warps take the boxes in order and wait for the TMA data themselves, so the a_lo
+                // barrier of the tile's LAST box covers every box of the tile: one wait per tile.
+                {
+                    const uint32_t ul = U + nbox - 1;
+                    mbar_wait(alo_full + ul % NS, (ul / NS) & 1u);
                 }
-                if (lane == 0) umma_commit(d_full + db);
-                __syncwarp();
+                tc_fence_after();
+                for (int b = 0; b < nbox; ++b) {
+                    const int st = (U + b) % NS;
+                    const uint64_t da0 = umma_desc_sw128(smem_u32(As + (size_t)st * MMA_BOX_BYTES));
+                    const uint64_t db0 = umma_desc_sw128(bs + b * MMA_BBOX_BYTES);
+                    const uint32_t talo = tmem + MMA_TMEM_ALO + st * MMA_BOX;
+                    const int ksteps = min(4, (dp - b * MMA_BOX + 7) >> 3);
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) {
+                        if (kk < ksteps) {  // a K-step advances both start addresses by 32 B (2 descriptor units)
+                            umma_ss(tmem_d, da0 + 2 * kk, db0 + 2 * kk, IDESC64, (b | kk) ? 1u : 0u);
+                            umma_ts(tmem_d, talo + kk * 8, db0 + 2 * kk, IDESC32, 1u);
+                        }
+                    }
+                }
+                // the row boxes (and their a_lo columns) may be refilled once these MMAs have completed
+                for (int b = 0; b < nbox; ++b) umma_commit(a_empty + (U + b) % NS);
+                umma_commit(d_full + db);
+                U += nbox;
             }
-            if (lane == 0) umma_commit(b_empty + ib);
-            __syncwarp();
+            umma_commit(b_empty + ib);
         }
     } else if (warp < 6) {
         // ===================================================================== split warps
+        // Besides a_lo, these 128 threads build the B operand of every item: thread (warp w, lane c) owns the
+        // 16-byte chunk c of queries g = 4j + w (j < 8). The chunks of item n+1 are loaded into registers before
+        // the row boxes of item n are processed and written (b_hi and b_lo = b - tf32(b)) at the top of the next
+        // iteration, so the gather latency is hidden behind a whole item.
+        //   B tile layout: box b = 32 floats of every query; b_hi of query g at g * 128 B, b_lo at (32 + g) * 128 B,
+        //   16-byte chunk cc stored at cc ^ (g & 7) (canonical K-major SWIZZLE_128B); padding chunks are zero
         const int q4 = warp & 3;  // the tensor-memory lane quadrant this warp may access
-        const int st_tid = (warp - 2) * 32 + lane;
+        const int sw = warp - 2;
+        const int dp4 = dp >> 2;
+        const bool c_used = lane < nbox * 8;  // chunk column inside the boxes the MMA reads
         uint32_t U = 0;
-        for (uint32_t n = 0;; ++n) {
-            const int ib = n % NB, id = n % ND;
+        float4 bq[8];
+        auto prefetch_b = [&](uint32_t n, WorkItem& w) {  // reads descriptor n, issues the loads, releases it
+            const int id = n % ND;
             mbar_wait(i_full + id, (n / ND) & 1u);
-            const WorkItem d = descs[id].w;
-            if (d.seg < 0) break;
+            w = descs[id].w;
+            if (w.seg >= 0) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int g = 4 * j + sw;
+                    bq[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (g < w.g_cnt && lane < dp4)
+                        bq[j] = __ldg(reinterpret_cast<const float4*>(a.queries + (int64_t)descs[id].q[g] * a.q_pitch) + lane);
+                }
+            }
             __syncwarp();
             if (lane == 0) mbar_arrive(i_empty + id);
-            mbar_wait(b_full + ib, (n / NB) & 1u);
-            {   // b_lo: elementwise over the swizzled B_hi buffer (same offsets)
-                const float4* hi = reinterpret_cast<const float4*>(Bs + (size_t)ib * 8 * MMA_BBOX_BYTES);
-                float4* lo = reinterpret_cast<float4*>(Bs + (size_t)ib * 8 * MMA_BBOX_BYTES + 4 * MMA_BBOX_BYTES);
-                for (int i = st_tid; i < nbox * (MMA_BBOX_BYTES / 16); i += 128) {
-                    const float4 x = hi[i];
-                    lo[i] = make_float4(tf32_lo(x.x), tf32_lo(x.y), tf32_lo(x.z), tf32_lo(x.w));
+        };
+        WorkItem d;
+        prefetch_b(0, d);
+        for (uint32_t n = 0;; ++n) {
+            if (d.seg < 0) break;
+            const int ib = n % NB;
+            mbar_wait(b_empty + ib, ((n / NB) & 1u) ^ 1u);  // the MMAs of item n - NB have completed
+            if (c_used) {
+                unsigned char* bs = Bs + (size_t)ib * 4 * MMA_BBOX_BYTES + (size_t)(lane >> 3) * MMA_BBOX_BYTES;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int g = 4 * j + sw;
+                    if (g < d.g_cnt) {
+                        unsigned char* hp = bs + g * 128 + (((lane & 7) ^ (g & 7)) << 4);
+                        const float4 x = bq[j];
+                        *reinterpret_cast<float4*>(hp) = x;
+                        *reinterpret_cast<float4*>(hp + MMA_NQ * 128) =
+                            make_float4(tf32_lo(x.x), tf32_lo(x.y), tf32_lo(x.z), tf32_lo(x.w));
+                    }
                 }
-                fence_proxy_async();  // B_hi (cp.async) and B_lo are read by the tensor core through the async proxy
-                __syncwarp();
-                if (lane == 0) mbar_arrive(b_ready + ib);
             }
-            const int ntiles = (d.nrows + TM - 1) / TM;
+            fence_proxy_async();  // the tensor core reads B through the async proxy
+            __syncwarp();
+            if (lane == 0) mbar_arrive(b_ready + ib);
+            const int nrows = d.nrows;
+            prefetch_b(n + 1, d);  // d now describes item n+1
+            const int ntiles = (nrows + TM - 1) / TM;
             const int r = q4 * 32 + lane;  // this thread's row of the tile == its tensor-memory lane
             for (int tile = 0; tile < ntiles; ++tile) {
                 for (int b = 0; b < nbox; ++b, ++U) {
@@ -389,8 +433,19 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) scan_mma_kernel(const ScanArgs
                 if (!kIP && r < tr) nrm = __ldg(a.norms + d.row0 + (int64_t)tile * TM + r);
                 mbar_wait(d_full + eg, (T >> 1) & 1u);
                 tc_fence_after();
-                uint32_t v[32];
-                tmem_ld32(tmem + MMA_TMEM_D + eg * MMA_NQ + ((uint32_t)(q4 * 32) << 16), v);
+                uint32_t v[32];  // dot = (a_hi + a_lo) . b_hi [columns 0-31] + a_hi . b_lo [columns 32-63]
+                {
+                    const uint32_t td = tmem + MMA_TMEM_D + eg * (2 * MMA_NQ) + ((uint32_t)(q4 * 32) << 16);
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        uint32_t x[16], y[16];
+                        tmem_ld16_nowait(td + h * 16, x);
+                        tmem_ld16_nowait(td + MMA_NQ + h * 16, y);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) v[h * 16 + i] = __float_as_uint(__uint_as_float(x[i]) + __uint_as_float(y[i]));
+                    }
+                }
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(d_empty + eg);
