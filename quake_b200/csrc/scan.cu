@@ -348,58 +348,72 @@ __global__ void __launch_bounds__(256) seed_thresholds_kernel(const float* __res
                                                               const int32_t* __restrict__ seg_rows, int kc, int sample,
                                                               float max_row_norm, float rel_margin,
                                                               uint32_t* __restrict__ gthr) {
-    extern __shared__ __align__(16) float seed_sm[];  // [8 warps][dp] queries, then [8 warps][sample] keys
+    // two queries per CTA, four warps per query
+    extern __shared__ __align__(16) float seed_sm[];  // [2][dp] queries, then [2][sample] keys
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t q = (int64_t)blockIdx.x * 8 + warp;
-    if (q >= Q) return;
-    float* qs = seed_sm + (size_t)warp * dp;
-    uint32_t* keys = reinterpret_cast<uint32_t*>(seed_sm + (size_t)8 * dp) + (size_t)warp * sample;
-    float qq = 0.f;
-    for (int i = lane; i < dp; i += 32) {
-        const float x = i < d ? queries[q * q_pitch + i] : 0.f;
-        qs[i] = x;
-        qq = fmaf(x, x, qq);
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) qq += __shfl_xor_sync(0xffffffffu, qq, o);
-    __syncwarp();
+    const int grp = warp >> 2, gw = warp & 3;
+    const int64_t q = (int64_t)blockIdx.x * 2 + grp;
+    if (q >= Q) return;  // a whole 4-warp group leaves together: the named barrier below stays consistent
+    float* qs = seed_sm + (size_t)grp * dp;
+    uint32_t* keys = reinterpret_cast<uint32_t*>(seed_sm + (size_t)2 * dp) + (size_t)grp * sample;
+    for (int i = gw * 32 + lane; i < dp; i += 128) qs[i] = i < d ? queries[q * q_pitch + i] : 0.f;
+    asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
     const float4* q4 = reinterpret_cast<const float4*>(qs);
-    // the first `sample` rows of the query's probed segments, in probe order
+    const int dp4 = dp >> 2;
+    // the first `sample` rows of the query's probed segments, in probe order; eight lanes per row (coalesced
+    // 128-byte pieces), eight rows per warp step, the four warps of the group interleaved
     int have = 0;
     for (int j = 0; j < P && have < sample; ++j) {
         const int seg = pair_seg[q * P + j];
         if (seg < 0) continue;
         const int take = min(seg_rows[seg], sample - have);
         const int64_t r0 = seg_row0[seg];
-        // eight lanes per row (coalesced 128-byte pieces), four rows per step
-        for (int i0 = 0; i0 < take; i0 += 4) {
-            const int i = i0 + (lane >> 3);
-            float acc = 0.f;
-            if (i < take) {
-                const float4* v4 = reinterpret_cast<const float4*>(vecs + (r0 + i) * pitch);
-                for (int c = lane & 7; c < (dp >> 2); c += 8) {
-                    const float4 x = __ldg(v4 + c), y = q4[c];
-                    acc = fmaf(x.x, y.x, acc); acc = fmaf(x.y, y.y, acc);
-                    acc = fmaf(x.z, y.z, acc); acc = fmaf(x.w, y.w, acc);
-                }
+        for (int i0 = gw * 8; i0 < take; i0 += 32) {
+            const int ia = i0 + (lane >> 3), ib = ia + 4;
+            float acc0 = 0.f, acc1 = 0.f;
+            const float4* va = reinterpret_cast<const float4*>(vecs + (r0 + (ia < take ? ia : 0)) * pitch);
+            const float4* vb = reinterpret_cast<const float4*>(vecs + (r0 + (ib < take ? ib : 0)) * pitch);
+            for (int c = lane & 7; c < dp4; c += 8) {
+                const float4 x = __ldg(va + c), z = __ldg(vb + c), y = q4[c];
+                acc0 = fmaf(x.x, y.x, acc0); acc0 = fmaf(x.y, y.y, acc0);
+                acc0 = fmaf(x.z, y.z, acc0); acc0 = fmaf(x.w, y.w, acc0);
+                acc1 = fmaf(z.x, y.x, acc1); acc1 = fmaf(z.y, y.y, acc1);
+                acc1 = fmaf(z.z, y.z, acc1); acc1 = fmaf(z.w, y.w, acc1);
             }
-            acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-            acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-            acc += __shfl_xor_sync(0xffffffffu, acc, 4);
-            if (i < take && (lane & 7) == 0) keys[have + i] = f2key(kIP ? -acc : fmaf(-2.f, acc, norms[r0 + i]));
+#pragma unroll
+            for (int o = 1; o < 8; o <<= 1) {
+                acc0 += __shfl_xor_sync(0xffffffffu, acc0, o);
+                acc1 += __shfl_xor_sync(0xffffffffu, acc1, o);
+            }
+            if ((lane & 7) == 0) {
+                if (ia < take) keys[have + ia] = f2key(kIP ? -acc0 : fmaf(-2.f, acc0, norms[r0 + ia]));
+                if (ib < take) keys[have + ib] = f2key(kIP ? -acc1 : fmaf(-2.f, acc1, norms[r0 + ib]));
+            }
         }
         have += take;
     }
-    if (have < kc) return;  // fewer sampled rows than candidates wanted: no bound
-    for (int i = have + lane; i < sample; i += 32) keys[i] = KEY_MAX;
-    __syncwarp();
+    asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+    if (gw != 0 || have < kc) return;  // fewer sampled rows than candidates wanted: no bound
+    // kc-th smallest key of the sample, by bisection on the key bits (keys in registers, 32 per lane at most)
+    uint32_t kreg[32];
+#pragma unroll
+    for (int s2 = 0; s2 < 32; ++s2) {
+        const int i = s2 * 32 + lane;
+        kreg[s2] = i < have ? keys[i] : KEY_MAX;
+    }
     const int nslot = (have + 31) >> 5;
-    uint32_t lo = 0;  // kc-th smallest key of the sample, by bisection on the key bits
+    float qq = 0.f;
+    for (int i = lane; i < dp; i += 32) qq = fmaf(qs[i], qs[i], qq);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) qq += __shfl_xor_sync(0xffffffffu, qq, o);
+    uint32_t lo = 0;
 #pragma unroll 1
     for (int bit = 31; bit >= 0; --bit) {
         const uint32_t cand = lo | (1u << bit);
         int c = 0;
-        for (int s = 0; s < nslot; ++s) c += __popc(__ballot_sync(0xffffffffu, keys[s * 32 + lane] < cand));
+#pragma unroll
+        for (int s2 = 0; s2 < 32; ++s2)
+            if (s2 < nslot) c += __popc(__ballot_sync(0xffffffffu, kreg[s2] < cand));
         if (c < kc) lo = cand;
     }
     if (lane == 0 && lo < KEY_MAX) {
@@ -1351,11 +1365,11 @@ int qk::scan_partitions_impl(const qk_store_t* st, const float* queries, int64_t
         const size_t store_bytes = (size_t)st->num_rows * st->pitch * sizeof(float);
         if (store_bytes > ((size_t)32 << 20))
             while (sample > 32 && (size_t)Q * sample * p.dp * sizeof(float) > ((size_t)96 << 20)) sample >>= 1;
-        const size_t ssm = (size_t)8 * (p.dp + sample) * sizeof(float);
+        const size_t ssm = (size_t)2 * (p.dp + sample) * sizeof(float);
         if (sample >= p.kc && ssm <= 48 * 1024) {
             const bool mma_path = (g_scan_variant == 0) && p.dp <= 128;
             const float rel_margin = 4.f * (float)(st->d + 8) * 5.9604645e-08f + (mma_path ? 4.f * 7.62939453125e-06f : 0.f);
-            const unsigned grid = (unsigned)((Q + 7) / 8);
+            const unsigned grid = (unsigned)((Q + 1) / 2);
             if (metric == QK_METRIC_INNER_PRODUCT)
                 seed_thresholds_kernel<true><<<grid, 256, ssm, stream>>>(st->vectors, st->pitch, st->row_norms, st->d, p.dp,
                                                                          queries, q_pitch, Q, pair_seg, p.P, st->seg_row0,
