@@ -122,6 +122,34 @@ int qk_merge_topk(const float* part_distances, const int64_t* part_ids, int num_
                   int64_t num_queries, int k, int metric,
                   int64_t* out_ids, float* out_distances, void* stream);
 
+/* ---- Adaptive Partition Scanning (recall_target > 0) ----------------------------------------------
+ * Replaces the APS part of QueryCoordinator::serial_scan (src/cpp/src/query_coordinator.cpp:521-579) and the
+ * geometry it calls (src/cpp/include/geometry.h).
+ *
+ * qk_host_beta_table: HOST call; table[1001] = I_x((d+1)/2, 1/2) at x = i/1000 (geometry.h:163-186; the caller
+ * uploads it once per dimension).
+ * qk_aps_boundary_distances: compute_boundary_distances (geometry.h:57-113) for every query against its m
+ * rank-ordered candidate centroids. cand_rows [Q x m]: arena rows of the candidates in `centroids` (the parent
+ * store's vectors), -1 where the coarse scan returned fewer; out [Q x m], entry 0 (and invalid ones) = -1.
+ * qk_aps_advance: one ROUND of the reference's per-query loop over probe ranks p0 .. p0+R-1 for the queries
+ * listed in `active`: round_ids / round_distances [num_active x R x k] hold the top-k of every (query, rank)
+ * partition scan of the round (one qk_scan_partitions call with one probe per pseudo-query). Per query: merge,
+ * k-th distance, recall profile (compute_recall_profile, geometry.h:345-407) when the radius moved by more than
+ * recompute_threshold, stop when sum(probs[0..p-1]) >= recall_target. State arrays are indexed by query:
+ * run_ids/run_distances [Q x k] (padded -1 / +-inf), run_count, radius (initialise to +-1e6,
+ * query_coordinator.cpp:524-527), have_probs, probs [Q x m], done, scanned (partitions scanned so far).
+ * still_active: device int32, number of listed queries that need another round. k <= 1024. */
+int qk_host_beta_table(int d, double* table);
+int qk_aps_boundary_distances(const float* queries, int64_t num_queries, int64_t query_pitch, int d,
+                              const float* centroids, int64_t centroid_pitch, const int64_t* cand_rows, int m,
+                              int metric, float* out_boundary, void* stream);
+int qk_aps_advance(const int32_t* active, int64_t num_active, int R, int p0, int m, int k, int d, int metric,
+                   const int32_t* slots, const int64_t* round_ids, const float* round_distances,
+                   const float* boundary, const double* beta_table, float recall_target,
+                   float recompute_threshold, int use_precomputed, int64_t* run_ids, float* run_distances,
+                   int32_t* run_count, float* radius, int32_t* have_probs, float* probs, int32_t* done,
+                   int32_t* scanned, int32_t* still_active, void* stream);
+
 /* ---- k-means assign / update / scatter ----------------------------------------------------
  * Replaces faiss::IndexFlat::search(k=1) inside faiss::Clustering::train and the final assignment
  * of kmeans() (src/cpp/src/clustering.cpp:65), and batched_scan_list(k=1) in

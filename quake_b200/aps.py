@@ -1,6 +1,95 @@
-"""Adaptive Partition Scanning (APS) driver -- filled in after the fixed-nprobe path."""
+"""Adaptive Partition Scanning (APS) driver: recall_target > 0 on the serial-scan path.
+
+Host-side mirror of the APS part of QueryCoordinator::serial_scan
+(/root/reference/src/cpp/src/query_coordinator.cpp:521-579). The arithmetic runs on the device
+(qk_aps_boundary_distances, qk_scan_partitions, qk_aps_advance -- csrc/aps.cu); this file sequences the rounds.
+"""
 from __future__ import annotations
 
+import ctypes as C
 
-def adaptive_scan(index, xq, p_ids, slots, sp):
-    raise NotImplementedError("APS (recall_target > 0) is not implemented yet in quake_b200")
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import check, ptr
+
+_FIRST_ROUND = 4   # probe ranks scanned in the first round; doubles every round up to _MAX_ROUND
+_MAX_ROUND = 32
+_MAX_PSEUDO = 1 << 16  # pseudo-queries (query, rank) per scan call
+
+_beta_tables: dict = {}
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def beta_table(d: int, device) -> torch.Tensor:
+    """incomplete_beta_lookup's table (geometry.h:163-186) for dimension d, computed on the host in double and
+    cached on the device. (The reference keeps ONE process-global table initialised with the first d it sees;
+    here every dimension gets its own.)"""
+    key = (int(d), str(device))
+    if key not in _beta_tables:
+        arr = np.empty(1001, dtype=np.float64)
+        check(_lib.load().qk_host_beta_table(int(d), arr.ctypes.data_as(C.POINTER(C.c_double))))
+        _beta_tables[key] = torch.from_numpy(arr).to(device)
+    return _beta_tables[key]
+
+
+def adaptive_scan(index, xq: torch.Tensor, cand_rows: torch.Tensor, slots: torch.Tensor, sp):
+    """xq [Q, pitch] device queries; cand_rows [Q, m] arena rows of the rank-ordered candidate centroids in the
+    parent store; slots [Q, m] list slots of the candidates in this index's store (-1 = skip).
+    Returns (ids [Q, k], distances [Q, k], partitions scanned per query [Q])."""
+    from .index import scan_partitions  # local import: index.py imports this module
+
+    lib = _lib.load()
+    Q, m = int(slots.shape[0]), int(slots.shape[1])
+    if m < 2:
+        # compute_recall_profile (geometry.h:350-352)
+        raise RuntimeError("Boundary distances must have at least 2 partitions to create an estimate.")
+    k = max(int(sp.k), 1)
+    if k > 1024:
+        raise ValueError("quake_b200: APS supports k <= 1024")
+    dev = xq.device
+    store, pstore = index.store, index.parent.store
+    d, metric = store.d, index.metric
+    ip = metric == _lib.QK_METRIC_INNER_PRODUCT
+    slots = slots.to(torch.int32).contiguous()
+    cand_rows = cand_rows.to(torch.int64).contiguous()
+
+    boundary = torch.empty((Q, m), dtype=torch.float32, device=dev)
+    check(lib.qk_aps_boundary_distances(ptr(xq), Q, xq.stride(0), d, ptr(pstore.vectors), pstore.pitch, ptr(cand_rows),
+                                        m, metric, ptr(boundary), _stream()))
+    table = beta_table(d, dev) if (bool(sp.use_precomputed) and not ip) else None
+
+    run_ids = torch.full((Q, k), -1, dtype=torch.int64, device=dev)
+    run_dist = torch.full((Q, k), float("-inf") if ip else float("inf"), dtype=torch.float32, device=dev)
+    run_cnt = torch.zeros(Q, dtype=torch.int32, device=dev)
+    radius = torch.full((Q,), -1000000.0 if ip else 1000000.0, dtype=torch.float32, device=dev)  # query_coordinator.cpp:524-527
+    have = torch.zeros(Q, dtype=torch.int32, device=dev)
+    probs = torch.zeros((Q, m), dtype=torch.float32, device=dev)
+    done = torch.zeros(Q, dtype=torch.int32, device=dev)
+    scanned = torch.zeros(Q, dtype=torch.int32, device=dev)
+    still = torch.zeros(1, dtype=torch.int32, device=dev)
+
+    active = torch.arange(Q, dtype=torch.int32, device=dev)
+    p, R = 0, _FIRST_ROUND
+    while p < m and active.numel() > 0:
+        Qa = int(active.numel())
+        r_eff = min(R, m - p, max(1, _MAX_PSEUDO // Qa))
+        act64 = active.to(torch.int64)
+        xa = xq.index_select(0, act64)
+        xrep = xa.repeat_interleave(r_eff, dim=0)                       # pseudo-query (a, r) = a * r_eff + r
+        probe = slots.index_select(0, act64)[:, p:p + r_eff].reshape(-1, 1).contiguous()
+        r_ids, r_dist = scan_partitions(store, xrep, probe, k, metric)
+        check(lib.qk_aps_advance(ptr(active), Qa, r_eff, p, m, k, d, metric, ptr(slots), ptr(r_ids), ptr(r_dist),
+                                 ptr(boundary), ptr(table), float(sp.recall_target), float(sp.recompute_threshold),
+                                 int(bool(sp.use_precomputed)), ptr(run_ids), ptr(run_dist), ptr(run_cnt), ptr(radius),
+                                 ptr(have), ptr(probs), ptr(done), ptr(scanned), ptr(still), _stream()))
+        p += r_eff
+        R = min(2 * R, _MAX_ROUND)
+        if int(still.item()) == 0:   # one host read per round: how many queries go on
+            break
+        active = torch.nonzero(done == 0).reshape(-1).to(torch.int32)
+    return run_ids, run_dist, scanned

@@ -165,8 +165,10 @@ class QuakeIndex:
         tinfo.total_time_ns = int((time.perf_counter() - t0) * 1e9)
         return res
 
-    def _search_device(self, xq: torch.Tensor, sp: SearchParams, tinfo: SearchTimingInfo | None = None):
-        """Device-resident search: xq [Q, pitch] on the index's device -> (ids, distances) device tensors."""
+    def _search_device(self, xq: torch.Tensor, sp: SearchParams, tinfo: SearchTimingInfo | None = None,
+                       want_rows: bool = False):
+        """Device-resident search: xq [Q, pitch] on the index's device -> (ids, distances, parent timing) device
+        tensors; with want_rows (flat index only) the arena rows of the results replace the timing."""
         Q = int(xq.shape[0])
         k = int(sp.k) if sp is not None and int(sp.k) > 0 else 1
         dev = xq.device
@@ -177,6 +179,8 @@ class QuakeIndex:
             pids = self.store.partition_ids()
             slots = torch.tensor([self.store.pid_slot[int(p)] for p in pids], dtype=torch.int32, device=dev)
             probe = slots[None, :].expand(Q, -1).contiguous()
+            if want_rows:
+                return scan_partitions(self.store, xq, probe, k, self.metric, want_rows=True)
             ids, dist = scan_partitions(self.store, xq, probe, k, self.metric)
             return ids, dist, parent_info
         nlist = self.nlist()
@@ -189,7 +193,7 @@ class QuakeIndex:
         else:
             psp.k = min(int(sp.nprobe), nlist)
         t1 = time.perf_counter()
-        p_ids, _p_dist, _ = self.parent._search_device(xq, psp)
+        p_ids, _p_dist, p_rows = self.parent._search_device(xq, psp, want_rows=use_aps)
         parent_info.n_queries = Q
         parent_info.n_clusters = self.parent.nlist()
         _, table = self.store.tables()
@@ -198,9 +202,12 @@ class QuakeIndex:
         check(lib.qk_map_ids_to_slots(ptr(p_ids), p_ids.numel(), ptr(table), table.numel(), ptr(slots), _stream()))
         parent_info.total_time_ns = int((time.perf_counter() - t1) * 1e9)
         if use_aps:
-            ids, dist, scanned = aps.adaptive_scan(self, xq, p_ids, slots, sp)
+            if self.parent.parent is not None:
+                raise RuntimeError("quake_b200: APS needs a flat parent (two-level index)")
+            ids, dist, scanned = aps.adaptive_scan(self, xq, p_rows, slots, sp)
+            self.last_partitions_scanned = scanned  # per query, device int32 (the reference only reports it for workers)
             if tinfo is not None:
-                tinfo.partitions_scanned = int(scanned)
+                tinfo.partitions_scanned = int(scanned.sum().item())
         else:
             ids, dist = scan_partitions(self.store, xq, slots, k, self.metric)
         if self.maintenance_policy_params is not None and self.current_level == 0:

@@ -279,3 +279,63 @@ def test_merge_topk_matches_sort():
             got_d = od[q].cpu().numpy()
             assert np.array_equal(got_d[:len(pairs)], np.array([p[0] for p in pairs], np.float32))
             assert np.all(np.isinf(got_d[len(pairs):]))
+
+
+# ------------------------------------------------------------------ APS (recall_target > 0)
+@pytest.mark.parametrize("metric", ["l2", "ip"])
+def test_aps_matches_reference_golden(metric):
+    """Adaptive partition scanning through serial_scan (query_coordinator.cpp:521-579): the index the REFERENCE
+    built, the REFERENCE's own APS results (recall_target 0.9, 10 % initial candidates, exact beta function)."""
+    qb = _qb()
+    S = np.load(os.path.join(GOLDEN, "search.npz"))
+    idx = qb.QuakeIndex()
+    idx.load(os.path.join(GOLDEN, f"index_{metric}"))
+    sp = qb.SearchParams()
+    sp.k, sp.recall_target, sp.initial_search_fraction, sp.use_precomputed = 10, 0.9, 0.1, False
+    res = idx.search(torch.from_numpy(S[f"{metric}_q"]), sp)
+    _assert_result(res.ids, res.distances, S[f"{metric}_aps_ids"], S[f"{metric}_aps_dist"])
+
+
+@pytest.mark.parametrize("metric,pre,target,k", [("l2", True, 0.9, 10), ("l2", False, 0.8, 10), ("ip", True, 0.9, 10),
+                                                 ("l2", True, 0.95, 100)])
+def test_aps_matches_oracle(metric, pre, target, k):
+    """Same index on both sides; ids, distances AND the number of partitions every query scanned must be those
+    of the sequential loop."""
+    qb = _qb()
+    torch.manual_seed(1234)
+    n, d, nlist = 30000, 32, 200
+    x = torch.randn(n, d)
+    if metric == "ip":
+        x = x / x.norm(dim=1, keepdim=True)
+    bp = qb.IndexBuildParams()
+    bp.nlist, bp.metric = nlist, metric
+    idx = qb.QuakeIndex()
+    idx.build(x, torch.arange(n, dtype=torch.int64), bp)
+    torch.manual_seed(4321)
+    q = torch.randn(70, d)
+    if metric == "ip":
+        q = q / q.norm(dim=1, keepdim=True)
+    sp = qb.SearchParams()
+    sp.k, sp.recall_target, sp.initial_search_fraction, sp.use_precomputed = k, target, 0.25, pre
+    res = idx.search(q, sp)
+    pids, lists, cv, ci = orc.index_lists(idx)
+    oi, od, cid, sc = orc.search_lists(pids, lists, cv, ci, q, k, 0, idx.metric, recall_target=target,
+                                       initial_search_fraction=0.25, use_precomputed=pre, return_probe=True)
+    _assert_result(res.ids, res.distances, oi.numpy(), od.numpy())
+    assert np.array_equal(idx.last_partitions_scanned.cpu().numpy(), sc)
+    assert 1 < sc.mean() < 50  # the early exit is actually exercised
+
+
+def test_aps_needs_two_candidates():
+    """compute_recall_profile throws with fewer than 2 candidate partitions (geometry.h:350-352)."""
+    qb = _qb()
+    torch.manual_seed(5)
+    x = torch.randn(2000, 16)
+    bp = qb.IndexBuildParams()
+    bp.nlist = 8
+    idx = qb.QuakeIndex()
+    idx.build(x, torch.arange(2000, dtype=torch.int64), bp)
+    sp = qb.SearchParams()
+    sp.k, sp.recall_target, sp.initial_search_fraction = 5, 0.9, 0.01  # int(8 * 0.01) = 0 -> 1 candidate
+    with pytest.raises(RuntimeError):
+        idx.search(torch.randn(3, 16), sp)
