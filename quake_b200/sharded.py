@@ -73,11 +73,13 @@ class ShardedQuakeIndex:
 
     build()/search() are collective calls: every rank passes the same queries and gets the same result."""
 
-    def __init__(self, group=None):
+    def __init__(self, group=None, rank: int | None = None, world: int | None = None):
+        """rank/world default to the process group's; passing them explicitly builds one shard of a W-way split
+        inside a single process (tests; search_partial() then yields that shard's un-merged answer)."""
         from .index import QuakeIndex
         self.group = group
-        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
-        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = rank if rank is not None else (dist.get_rank(group) if dist.is_initialized() else 0)
+        self.world = world if world is not None else (dist.get_world_size(group) if dist.is_initialized() else 1)
         self.local = QuakeIndex()  # parent replicated; store holds the owned lists only
         self.metric = 1
         self._ntotal = 0
@@ -190,23 +192,28 @@ class ShardedQuakeIndex:
         return self._ntotal
 
     def nlist(self) -> int:
-        return self.local.parent.nlist() if self.local.parent is not None else 0
+        # the number of partitions of the whole index = the number of centroids the (flat) parent holds
+        return self.local.parent.ntotal() if self.local.parent is not None else 0
 
     def search_device(self, xq: torch.Tensor, sp: SearchParams):
         """xq [Q, pitch] on this rank's device (the same queries on every rank) -> merged (ids, distances)."""
+        ids, dd = self.search_partial(xq, sp)
+        return gather_and_merge(ids, dd, max(int(sp.k), 1), self.metric, self.group)
+
+    def search_partial(self, xq: torch.Tensor, sp: SearchParams):
+        """This rank's partial top-k: coarse scan for all queries, partition scan of the probed lists it owns."""
         from .index import scan_partitions
         idx = self.local
         k = max(int(sp.k), 1)
         psp = SearchParams()
         psp.batched_scan = True
-        psp.k = min(int(sp.nprobe), idx.parent.nlist())
+        psp.k = min(int(sp.nprobe), self.nlist())
         p_ids, _, _ = idx.parent._search_device(xq, psp)
         _, table = idx.store.tables()
         slots = torch.empty(p_ids.shape, dtype=torch.int32, device=xq.device)
         check(_lib.load().qk_map_ids_to_slots(ptr(p_ids), p_ids.numel(), ptr(table), table.numel(), ptr(slots), _stream()))
         slots = mask_foreign_probes(p_ids, slots, self.rank, self.world)
-        ids, dd = scan_partitions(idx.store, xq, slots, k, self.metric)
-        return gather_and_merge(ids, dd, k, self.metric, self.group)
+        return scan_partitions(idx.store, xq, slots, k, self.metric)
 
     def search(self, x: torch.Tensor, search_params: SearchParams) -> SearchResult:
         res = SearchResult()

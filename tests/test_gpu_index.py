@@ -339,3 +339,36 @@ def test_aps_needs_two_candidates():
     sp.k, sp.recall_target, sp.initial_search_fraction = 5, 0.9, 0.01  # int(8 * 0.01) = 0 -> 1 candidate
     with pytest.raises(RuntimeError):
         idx.search(torch.randn(3, 16), sp)
+
+
+# ------------------------------------------------------------------ sharded lists, simulated on one GPU
+@pytest.mark.parametrize("metric", ["l2", "ip"])
+def test_sharded_partials_merge_to_unsharded_result(metric):
+    """the W per-shard partial top-k lists (lists owned round-robin by partition id), merged by
+    qk_merge_topk, are bit-identical to the unsharded search. All W shards are held by one process here; the
+    collective that moves the partials is covered by tests/test_sharded_gloo.py and test_gpu_sharded.py."""
+    qb = _qb()
+    from quake_b200 import clustering, sharded
+    torch.manual_seed(1234)
+    n, d, nlist, W = 30000, 96, 48, 4
+    x = torch.randn(n, d)
+    bp = qb.IndexBuildParams()
+    bp.nlist, bp.metric = nlist, metric
+    full = qb.QuakeIndex()
+    full.build(x, torch.arange(n, dtype=torch.int64) + 3, bp)
+    torch.manual_seed(4321)
+    q = torch.randn(100, d)
+    sp = qb.SearchParams()
+    sp.k, sp.nprobe = 10, 12
+    want = full.search(q, sp)
+    xq = clustering.pad_rows(q, full.store.device)
+    parts = []
+    for r in range(W):
+        sh = sharded.ShardedQuakeIndex(rank=r, world=W)
+        sh.shard_from(full)
+        assert sh.local.store.nlist == len(range(r, nlist, W))
+        parts.append(sh.search_partial(xq, sp))
+    pi = torch.stack([p[0] for p in parts]).contiguous()
+    pd = torch.stack([p[1] for p in parts]).contiguous()
+    mi, md = sharded.merge_partials_device(pd, pi, 10, full.metric)
+    assert torch.equal(mi.cpu(), want.ids) and torch.equal(md.cpu(), want.distances)
