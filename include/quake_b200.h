@@ -59,6 +59,8 @@ typedef struct qk_store {
     float          max_row_norm; /* upper bound on the L2 norm of any stored row (see qk_max_row_norm)*/
     const float*   row_norms;    /* [rows] squared L2 norm of every row (see qk_row_sqnorms); l2 only */
     int64_t        num_rows;     /* rows allocated behind `vectors` (bounds of the TMA tensor map)       */
+    int64_t        flat_row0;    /* single-list stores (num_lists == 1): first arena row of the list ...  */
+    int64_t        flat_rows;    /* ... and its length (host-known copy; 0 otherwise)                     */
 } qk_store_t;
 
 #define QK_SEGMENT_ROWS 4096

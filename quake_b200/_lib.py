@@ -41,6 +41,8 @@ class QkStore(C.Structure):
         ("max_row_norm", C.c_float),
         ("row_norms", vp),
         ("num_rows", C.c_int64),
+        ("flat_row0", C.c_int64),
+        ("flat_rows", C.c_int64),
     ]
 
 

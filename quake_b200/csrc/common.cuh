@@ -169,25 +169,27 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// Spins until the phase with the given parity has completed. A wait that lasts longer than any legitimate one
+// Waits until the phase with the given parity has completed. try_wait carries a suspend-time hint, so a waiting warp
+// is parked by the hardware instead of spinning through the issue slots of the warps that have work (16 warps share
+// 4 schedulers here, and most of them are waiting at any time). A wait that lasts longer than any legitimate one
 // (seconds) means a pipeline protocol error: report where and trap instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t done = 0;
     const uint32_t a = smem_u32(bar);
     uint32_t spins = 0;
     while (!done) {
-        if (++spins == (1u << 26)) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(a), "r"(parity), "r"(1000000u)  // up to 1 ms per attempt
+            : "memory");
+        if (!done && ++spins == 4000u) {
             printf("quake_b200: mbarrier wait timed out: block %d warp %d lane %d barrier@%u parity %u\n", blockIdx.x,
                    threadIdx.x >> 5, threadIdx.x & 31, a & 0xffffu, parity);
             __trap();
         }
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done)
-            : "r"(a), "r"(parity)
-            : "memory");
     }
 }
 // 1-D bulk copy global -> shared, completion signalled on an mbarrier (bytes % 16 == 0, 16B aligned).

@@ -45,6 +45,9 @@ struct ScanPlan {
     size_t off_pair_seg, off_seg_count, off_seg_fill, off_seg_start, off_item_start, off_seg_pairs, off_items,
         off_ctrl, off_gthr, off_flags, off_qcount, off_qbuf, total;
     int qcap;     // entries of the per-query candidate buffer
+    int sample;   // rows sampled per query for the threshold seed (0: no seeding)
+    int flat_seed;  // every query samples the same rows (single-list store): seed scores as one small GEMM
+    size_t off_skeys;
 };
 
 static constexpr int SCAN_DC = 128;     // floats of a row staged per pipeline unit
@@ -146,6 +149,21 @@ static int make_plan(const qk_store_t* st, int64_t Q, int nprobe, int k, ScanPla
     p->off_gthr = o;       o = align_up(o + (size_t)Q * 4, 256);
     p->qcap = candidate_buffer_cap(p->kc);
     p->off_qbuf = o;       o = align_up(o + (size_t)Q * p->qcap * 8, 256);
+    // threshold seeds from a sample of the query's first probed rows: about 8 * kc of them (pass rate of the seed
+    // ~ 1/8), bounded by the read traffic it costs -- unless the whole store is small enough to sit in L2 (a flat
+    // index / the centroid list, shared by every query)
+    {
+        int sample = 32;
+        while (sample < 1024 && sample < 8 * p->kc) sample <<= 1;
+        const size_t store_bytes = (size_t)st->num_rows * st->pitch * sizeof(float);
+        if (store_bytes > ((size_t)32 << 20))
+            while (sample > 32 && (size_t)Q * sample * p->dp * sizeof(float) > ((size_t)96 << 20)) sample >>= 1;
+        p->flat_seed = (st->num_lists == 1 && nprobe == 1) ? 1 : 0;
+        if (sample < p->kc || (!p->flat_seed && (size_t)2 * (p->dp + sample) * sizeof(float) > 48 * 1024)) sample = 0;
+        p->sample = sample;
+        p->off_skeys = o;
+        if (p->flat_seed && sample) o = align_up(o + (size_t)Q * sample * 4, 256);
+    }
     p->total = o;
     return QK_OK;
 }
@@ -424,6 +442,103 @@ __global__ void __launch_bounds__(256) seed_thresholds_kernel(const float* __res
     }
 }
 
+// Flat stores (one list: a flat index, the centroid list of the coarse scan, the k-means assign): every query
+// samples the SAME rows -- the first `sample` rows of the list -- so the seed scores are one small dense
+// [Q x sample x d] contraction: a register-tiled FP32 kernel (64 queries x 64 rows per CTA, 4 x 4 per thread)
+// writes the keys, a second kernel selects the kc-th smallest per query.
+template <bool kIP>
+__global__ void __launch_bounds__(256) seed_scores_flat_kernel(const float* __restrict__ vecs, int64_t pitch,
+                                                               const float* __restrict__ norms, int d,
+                                                               const float* __restrict__ queries, int64_t q_pitch, int64_t Q,
+                                                               int64_t row0, int nrows, int sample,
+                                                               uint32_t* __restrict__ skeys) {
+    __shared__ float qs[32][65];  // [k][query]
+    __shared__ float rs[32][65];  // [k][row]
+    const int tid = threadIdx.x;
+    const int64_t qb = (int64_t)blockIdx.x * 64;
+    const int rb = blockIdx.y * 64;
+    const int tq = tid & 15, tr = tid >> 4;  // thread tile: queries tq*4.., rows tr*4..
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int k0 = 0; k0 < d; k0 += 32) {
+        // 64 x 32 floats each: thread loads 8 + 8 scalars (row-major sources, coalesced over k)
+        for (int e = tid; e < 64 * 32; e += 256) {
+            const int r = e >> 5, k = e & 31;
+            const int64_t q = qb + r;
+            qs[k][r] = (q < Q && k0 + k < d) ? queries[q * q_pitch + k0 + k] : 0.f;
+            const int row = rb + r;
+            rs[k][r] = (row < nrows && row < sample && k0 + k < d) ? vecs[(row0 + row) * pitch + k0 + k] : 0.f;
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int k = 0; k < 32; ++k) {
+            float a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { a[i] = qs[k][tq * 4 + i]; b[i] = rs[k][tr * 4 + i]; }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int64_t q = qb + tq * 4 + i;
+        if (q >= Q) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int row = rb + tr * 4 + j;
+            if (row >= sample) continue;
+            uint32_t key = KEY_MAX;
+            if (row < nrows) key = f2key(kIP ? -acc[i][j] : fmaf(-2.f, acc[i][j], norms[row0 + row]));
+            skeys[q * sample + row] = key;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) seed_select_flat_kernel(const uint32_t* __restrict__ skeys, int sample, int have,
+                                                               const float* __restrict__ queries, int64_t q_pitch, int d,
+                                                               int64_t Q, int kc, float max_row_norm, float rel_margin,
+                                                               uint32_t* __restrict__ gthr) {
+    const int lane = threadIdx.x & 31;
+    const int64_t q = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (q >= Q || have < kc) return;
+    uint32_t kreg[32];
+#pragma unroll
+    for (int s2 = 0; s2 < 32; ++s2) {
+        const int i = s2 * 32 + lane;
+        kreg[s2] = i < have ? skeys[q * sample + i] : KEY_MAX;
+    }
+    const int nslot = (have + 31) >> 5;
+    float qq = 0.f;
+    for (int i = lane; i < d; i += 32) {
+        const float x = queries[q * q_pitch + i];
+        qq = fmaf(x, x, qq);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) qq += __shfl_xor_sync(0xffffffffu, qq, o);
+    uint32_t lo = 0;
+#pragma unroll 1
+    for (int bit = 31; bit >= 0; --bit) {
+        const uint32_t cand = lo | (1u << bit);
+        int c = 0;
+#pragma unroll
+        for (int s2 = 0; s2 < 32; ++s2)
+            if (s2 < nslot) c += __popc(__ballot_sync(0xffffffffu, kreg[s2] < cand));
+        if (c < kc) lo = cand;
+    }
+    if (lane == 0 && lo < KEY_MAX) {
+        const float t = key2f(lo);
+        const float margin = __fadd_ru(__fmul_ru(rel_margin, __fmul_ru(sqrtf(qq), max_row_norm)), fabsf(t) * 9.5367431640625e-07f);
+        const float tm = __fadd_ru(t, margin);
+        if (tm == tm) atomicMin(gthr + q, f2key(tm));
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // 4. the scan (filter) kernel
 // ------------------------------------------------------------------------------------------------
@@ -440,6 +555,7 @@ struct ScanArgs {
     uint64_t* qbuf;    // [Q][qcap] candidates: key << 32 | arena row; unwritten slots are 0xff..ff
     int P, kc, gq, nq;
     int qcap;
+    int dbg;  // profiling aid (QK_SCAN_DBG): skip pipeline stages to find the floor of the others; results are invalid
 };
 
 // One d-chunk (<= 128 floats) of one 64-row tile for NT query slots per lane: 4 rows x NT queries x float4
@@ -1356,21 +1472,32 @@ int qk::scan_partitions_impl(const qk_store_t* st, const float* queries, int64_t
                                                                               seg_count, gthr, false);
     }
     QK_CUDA(cudaGetLastError());
-    {
-        // threshold seeds from a sample of the query's first probed rows: about 8 * kc of them (pass rate of the
-        // seed ~ 1/8), bounded by the read traffic it costs -- unless the whole store is small enough to sit in
-        // L2 (a flat index / the centroid list, shared by every query)
-        int sample = 32;
-        while (sample < 1024 && sample < 8 * p.kc) sample <<= 1;
-        const size_t store_bytes = (size_t)st->num_rows * st->pitch * sizeof(float);
-        if (store_bytes > ((size_t)32 << 20))
-            while (sample > 32 && (size_t)Q * sample * p.dp * sizeof(float) > ((size_t)96 << 20)) sample >>= 1;
-        const size_t ssm = (size_t)2 * (p.dp + sample) * sizeof(float);
-        if (sample >= p.kc && ssm <= 48 * 1024) {
-            const bool mma_path = (g_scan_variant == 0) && p.dp <= 128;
-            const float rel_margin = 4.f * (float)(st->d + 8) * 5.9604645e-08f + (mma_path ? 4.f * 7.62939453125e-06f : 0.f);
+    if (p.sample) {
+        const int sample = p.sample;
+        const bool mma_path = (g_scan_variant == 0) && p.dp <= 128;
+        const float rel_margin = 4.f * (float)(st->d + 8) * 5.9604645e-08f + (mma_path ? 4.f * 7.62939453125e-06f : 0.f);
+        const bool ip = metric == QK_METRIC_INNER_PRODUCT;
+        if (p.flat_seed) {
+            // the single list's first rows (its segments are consecutive in the arena); host-known geometry
+            if (st->flat_rows > 0) {
+                uint32_t* skeys = (uint32_t*)(ws + p.off_skeys);
+                const int have = (int)(st->flat_rows < sample ? st->flat_rows : sample);
+                dim3 grid((unsigned)((Q + 63) / 64), (unsigned)((have + 63) / 64));
+                if (ip)
+                    seed_scores_flat_kernel<true><<<grid, 256, 0, stream>>>(st->vectors, st->pitch, st->row_norms, st->d, queries,
+                                                                            q_pitch, Q, st->flat_row0, (int)st->flat_rows, sample, skeys);
+                else
+                    seed_scores_flat_kernel<false><<<grid, 256, 0, stream>>>(st->vectors, st->pitch, st->row_norms, st->d, queries,
+                                                                             q_pitch, Q, st->flat_row0, (int)st->flat_rows, sample, skeys);
+                QK_CUDA(cudaGetLastError());
+                seed_select_flat_kernel<<<(unsigned)((Q + 7) / 8), 256, 0, stream>>>(skeys, sample, have, queries, q_pitch, st->d, Q,
+                                                                                     p.kc, st->max_row_norm, rel_margin, gthr);
+                QK_CUDA(cudaGetLastError());
+            }
+        } else {
+            const size_t ssm = (size_t)2 * (p.dp + sample) * sizeof(float);
             const unsigned grid = (unsigned)((Q + 1) / 2);
-            if (metric == QK_METRIC_INNER_PRODUCT)
+            if (ip)
                 seed_thresholds_kernel<true><<<grid, 256, ssm, stream>>>(st->vectors, st->pitch, st->row_norms, st->d, p.dp,
                                                                          queries, q_pitch, Q, pair_seg, p.P, st->seg_row0,
                                                                          st->seg_rows, p.kc, sample, st->max_row_norm,
@@ -1398,6 +1525,11 @@ int qk::scan_partitions_impl(const qk_store_t* st, const float* queries, int64_t
     sa.seg_pairs = seg_pairs; sa.items = items; sa.ctrl = ctrl;
     sa.gthr = gthr; sa.qcount = qcount; sa.qbuf = qbuf;
     sa.P = p.P; sa.kc = p.kc; sa.gq = p.gq; sa.nq = p.nq; sa.qcap = p.qcap;
+    {
+        static int dbg = -1;
+        if (dbg < 0) { const char* e = getenv("QK_SCAN_DBG"); dbg = e ? atoi(e) : 0; }
+        sa.dbg = dbg;
+    }
     CUtensorMap vmap;
     // d <= 128: tensor-core filter (tcgen05, 3xTF32 split); otherwise the FP32-pipe kernel. QK_SCAN_PATH=ffma
     // forces the latter (tests cross-check the two).

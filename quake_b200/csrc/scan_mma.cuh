@@ -160,23 +160,23 @@ __device__ __forceinline__ float key2lim(uint32_t t) { return t == KEY_MAX ? INF
 template <bool kIP>
 __global__ void __launch_bounds__(MMA_THREADS, 1) scan_mma_kernel(const ScanArgs a, const __grid_constant__ CUtensorMap vmap) {
     constexpr int TM = MMA_TM, NS = MMA_STAGES, NB = MMA_NB, ND = MMA_ND;
-    static_assert(640 + MMA_ND * sizeof(MmaDesc) <= MMA_SMEM_HEADER, "descriptor ring");
+    static_assert(MMA_STAGES <= 16 && 768 + MMA_ND * sizeof(MmaDesc) <= MMA_SMEM_HEADER, "descriptor ring");
     extern __shared__ __align__(16) unsigned char smem_dyn[];
     unsigned char* smem_raw = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
     uint64_t* a_full = bars;           // [NS] producer (tx)                 -> split warps, MMA issuer
-    uint64_t* a_empty = bars + 8;      // [NS] 4 split warps + MMA commit    -> producer
-    uint64_t* alo_full = bars + 16;    // [NS] 4 split warps                 -> MMA issuer
-    uint64_t* b_ready = bars + 28;     // [NB] 4 split warps (b_lo written)  -> MMA issuer
-    uint64_t* b_empty = bars + 32;     // [NB] MMA commit                    -> producer
-    uint64_t* i_full = bars + 36;      // [ND] producer (descriptor written) -> every consumer warp
-    uint64_t* i_empty = bars + 44;     // [ND] 13 consumer warps             -> producer
-    uint64_t* d_full = bars + 52;      // [2]  MMA commit                    -> epilogue group
-    uint64_t* d_empty = bars + 54;     // [2]  4 epilogue warps              -> MMA issuer
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + 456);
-    volatile uint32_t* ep_done = reinterpret_cast<volatile uint32_t*>(smem_raw + 460);       // epilogue warps that left
-    volatile unsigned long long* mbox = reinterpret_cast<volatile unsigned long long*>(smem_raw + 512);  // [8] refresh requests
-    MmaDesc* descs = reinterpret_cast<MmaDesc*>(smem_raw + 640);    // [ND]
+    uint64_t* a_empty = bars + 16;     // [NS] 4 split warps + MMA commit    -> producer
+    uint64_t* alo_full = bars + 32;   // [NS] 4 split warps                 -> MMA issuer
+    uint64_t* b_ready = bars + 48;     // [NB] 4 split warps (b_lo written)  -> MMA issuer
+    uint64_t* b_empty = bars + 50;     // [NB] MMA commit                    -> producer
+    uint64_t* i_full = bars + 52;      // [ND] producer (descriptor written) -> every consumer warp
+    uint64_t* i_empty = bars + 60;     // [ND] 13 consumer warps             -> producer
+    uint64_t* d_full = bars + 68;      // [2]  MMA commit                    -> epilogue group
+    uint64_t* d_empty = bars + 70;     // [2]  4 epilogue warps              -> MMA issuer
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + 640);
+    volatile uint32_t* ep_done = reinterpret_cast<volatile uint32_t*>(smem_raw + 644);       // epilogue warps that left
+    volatile unsigned long long* mbox = reinterpret_cast<volatile unsigned long long*>(smem_raw + 704);  // [8] refresh requests
+    MmaDesc* descs = reinterpret_cast<MmaDesc*>(smem_raw + 768);    // [ND]
     unsigned char* As = smem_raw + MMA_SMEM_HEADER;                 // [NS][128 rows][128 B]
     unsigned char* Bs = As + (size_t)NS * MMA_BOX_BYTES;            // [NB][4 boxes][hi: 32 rows | lo: 32 rows][128 B]
     uint32_t* hists = reinterpret_cast<uint32_t*>(Bs + (size_t)NB * 4 * MMA_BBOX_BYTES);  // [2 refresh warps][256]
@@ -314,7 +314,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) scan_mma_kernel(const ScanArgs
                     const int ksteps = min(4, (dp - b * MMA_BOX + 7) >> 3);
 #pragma unroll
                     for (int kk = 0; kk < 4; ++kk) {
-                        if (kk < ksteps) {  // a K-step advances both start addresses by 32 B (2 descriptor units)
+                        if (kk < ksteps && !(a.dbg & 2)) {  // a K-step advances both start addresses by 32 B (2 descriptor units)
                             umma_ss(tmem_d, da0 + 2 * kk, db0 + 2 * kk, IDESC64, (b | kk) ? 1u : 0u);
                             umma_ts(tmem_d, talo + kk * 8, db0 + 2 * kk, IDESC32, 1u);
                         }
@@ -390,6 +390,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) scan_mma_kernel(const ScanArgs
                     mbar_wait(a_full + st, (U / NS) & 1u);
                     const unsigned char* rowp = As + (size_t)st * MMA_BOX_BYTES + r * 128;
                     uint32_t v[32];
+                    if (!(a.dbg & 4))
 #pragma unroll
                     for (int cc = 0; cc < 8; ++cc) {
                         const float4 x = *reinterpret_cast<const float4*>(rowp + ((cc ^ (r & 7)) << 4));
@@ -398,7 +399,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) scan_mma_kernel(const ScanArgs
                         v[4 * cc + 2] = __float_as_uint(tf32_lo(x.z));
                         v[4 * cc + 3] = __float_as_uint(tf32_lo(x.w));
                     }
-                    tmem_st32(tmem + MMA_TMEM_ALO + st * MMA_BOX + ((uint32_t)(q4 * 32) << 16), v);
+                    if (!(a.dbg & 4)) tmem_st32(tmem + MMA_TMEM_ALO + st * MMA_BOX + ((uint32_t)(q4 * 32) << 16), v);
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) { mbar_arrive(alo_full + st); mbar_arrive(a_empty + st); }
@@ -449,6 +450,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) scan_mma_kernel(const ScanArgs
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(d_empty + eg);
+                if (a.dbg & 1) continue;
                 // ---- scores of this thread's row against the 32 query slots; bit g of pm: the score passes
                 uint32_t pm = 0;
 #pragma unroll
