@@ -38,6 +38,42 @@ def _device() -> torch.device:
 
 LAST_SCAN_STATS = None  # set QK_SCAN_STATS=1: int32[4] device tensor of the last qk_scan_partitions call
 
+# Fixed-nprobe searches are replayed from a CUDA graph captured per (batch size, k, nprobe, index version): the
+# step is ~20 short launches, and the gaps between them cost as much as a kernel. QK_GRAPH=0 (or GRAPHS_ENABLED =
+# False) keeps every call eager -- bench.py does that while it times individual kernels with events.
+GRAPHS_ENABLED = os.environ.get("QK_GRAPH", "1") != "0"
+_MAX_PLANS = 8
+_capturing = False
+
+
+class _SearchPlan:
+    """One captured search: static input buffer -> static output buffers."""
+
+    def __init__(self, index: "QuakeIndex", Q: int, sp: SearchParams):
+        global _capturing
+        dev = index.store.device
+        self.xq = torch.zeros((Q, index.store.pitch), dtype=torch.float32, device=dev)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream())
+        _capturing = True
+        try:
+            with torch.cuda.stream(side):
+                for _ in range(2):  # warm-up outside the capture: lazy tables, function attributes, allocator pools
+                    index._search_core(self.xq, sp)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self.ids, self.dist, self.p_ids = index._search_core(self.xq, sp)
+        finally:
+            _capturing = False
+
+    def run(self, xq: torch.Tensor):
+        if xq.data_ptr() != self.xq.data_ptr():
+            self.xq.copy_(xq, non_blocking=True)
+        self.graph.replay()
+        return self.ids, self.dist, self.p_ids
+
 
 def scan_partitions(store: PartitionStore, xq: torch.Tensor, probe_slots: torch.Tensor, k: int, metric: int,
                     want_rows: bool = False):
@@ -156,7 +192,13 @@ class QuakeIndex:
         if x.dim() != 2 or int(x.shape[1]) != self.store.d:
             raise RuntimeError(f"[QuakeIndex::search] queries must be [Q, {self.store.d}]")
         out_dev = x.device
-        xq = clustering.pad_rows(x, self.store.device)
+        use_aps = self.parent is not None and float(search_params.recall_target) > 0.0 and not bool(search_params.batched_scan)
+        if GRAPHS_ENABLED and not use_aps and self.current_level == 0 and x.dtype == torch.float32:
+            # straight into the plan's static input buffer (one H2D copy when x is a host tensor)
+            xq = self._plan(int(x.shape[0]), search_params).xq
+            xq[:, : self.store.d].copy_(x, non_blocking=True)
+        else:
+            xq = clustering.pad_rows(x, self.store.device)
         ids, dist, parent_info = self._search_device(xq, search_params, tinfo)
         res.ids = ids.to(out_dev)
         res.distances = dist.to(out_dev)
@@ -165,43 +207,77 @@ class QuakeIndex:
         tinfo.total_time_ns = int((time.perf_counter() - t0) * 1e9)
         return res
 
+    def _flat_probe(self, Q: int) -> torch.Tensor:
+        """[Q, nlist] probe table of a flat index: every query scans every partition (query_coordinator.cpp:624-626)."""
+        key = (Q, self.store.version)
+        if getattr(self, "_flat_probe_cache", (None, None))[0] != key:
+            self.store.tables()
+            key = (Q, self.store.version)
+            slots = torch.tensor([self.store.pid_slot[int(p)] for p in self.store.partition_ids()], dtype=torch.int32,
+                                 device=self.store.device)
+            self._flat_probe_cache = (key, slots[None, :].expand(Q, -1).contiguous())
+        return self._flat_probe_cache[1]
+
+    def _search_core(self, xq: torch.Tensor, sp: SearchParams):
+        """Fixed-nprobe search, launches only (capturable in a CUDA graph): coarse scan -> slot map -> partition scan.
+        Returns (ids, distances, probed partition ids or None)."""
+        Q = int(xq.shape[0])
+        k = int(sp.k) if sp is not None and int(sp.k) > 0 else 1
+        if self.parent is None:
+            ids, dist = scan_partitions(self.store, xq, self._flat_probe(Q), k, self.metric)
+            return ids, dist, None
+        psp = SearchParams()
+        psp.batched_scan = True
+        psp.k = min(int(sp.nprobe), self.nlist())
+        p_ids, _p_dist, _ = self.parent._search_device(xq, psp)
+        _, table = self.store.tables()
+        slots = torch.empty(p_ids.shape, dtype=torch.int32, device=xq.device)
+        check(_lib.load().qk_map_ids_to_slots(ptr(p_ids), p_ids.numel(), ptr(table), table.numel(), ptr(slots), _stream()))
+        ids, dist = scan_partitions(self.store, xq, slots, k, self.metric)
+        return ids, dist, p_ids
+
+    def _plan(self, Q: int, sp: SearchParams) -> "_SearchPlan":
+        plans = self.__dict__.setdefault("_plans", {})
+        self.store.tables()  # settles store.version
+        pv = self.parent.store.version if self.parent is not None and self.parent.store is not None else -1
+        if self.parent is not None:
+            self.parent.store.tables()
+            pv = self.parent.store.version
+        key = (Q, int(sp.k), int(sp.nprobe), self.metric, self.store.version, pv)
+        plan = plans.get(key)
+        if plan is None:
+            for old_key in [kk for kk in plans if kk[4:] != key[4:]]:  # the index changed: drop stale plans
+                del plans[old_key]
+            while len(plans) >= _MAX_PLANS:
+                del plans[next(iter(plans))]
+            plan = plans[key] = _SearchPlan(self, Q, sp)
+        return plan
+
     def _search_device(self, xq: torch.Tensor, sp: SearchParams, tinfo: SearchTimingInfo | None = None,
                        want_rows: bool = False):
         """Device-resident search: xq [Q, pitch] on the index's device -> (ids, distances, parent timing) device
-        tensors; with want_rows (flat index only) the arena rows of the results replace the timing."""
+        tensors; with want_rows (flat index only) the arena rows of the results replace the timing.
+        Graph-replayed searches return the plan's static output buffers (valid until the next search)."""
         Q = int(xq.shape[0])
         k = int(sp.k) if sp is not None and int(sp.k) > 0 else 1
-        dev = xq.device
         parent_info = SearchTimingInfo()
-        if self.parent is None:
-            # flat: every query scans all partitions (query_coordinator.cpp:624-626)
-            _, table = self.store.tables()
-            pids = self.store.partition_ids()
-            slots = torch.tensor([self.store.pid_slot[int(p)] for p in pids], dtype=torch.int32, device=dev)
-            probe = slots[None, :].expand(Q, -1).contiguous()
-            if want_rows:
-                return scan_partitions(self.store, xq, probe, k, self.metric, want_rows=True)
-            ids, dist = scan_partitions(self.store, xq, probe, k, self.metric)
-            return ids, dist, parent_info
-        nlist = self.nlist()
-        use_aps = float(sp.recall_target) > 0.0 and not bool(sp.batched_scan)
-        psp = SearchParams()
-        psp.batched_scan = True
-        psp.recall_target = sp.recall_target
+        if want_rows:
+            if self.parent is not None:
+                raise RuntimeError("quake_b200: result rows are only available from a flat index")
+            return scan_partitions(self.store, xq, self._flat_probe(Q), k, self.metric, want_rows=True)
+        use_aps = self.parent is not None and float(sp.recall_target) > 0.0 and not bool(sp.batched_scan)
         if use_aps:
+            nlist = self.nlist()
+            psp = SearchParams()
+            psp.batched_scan = True
+            psp.recall_target = sp.recall_target
             psp.k = max(int(nlist * float(sp.initial_search_fraction)), 1)  # query_coordinator.cpp:636-639
-        else:
-            psp.k = min(int(sp.nprobe), nlist)
-        t1 = time.perf_counter()
-        p_ids, _p_dist, p_rows = self.parent._search_device(xq, psp, want_rows=use_aps)
-        parent_info.n_queries = Q
-        parent_info.n_clusters = self.parent.nlist()
-        _, table = self.store.tables()
-        lib = _lib.load()
-        slots = torch.empty(p_ids.shape, dtype=torch.int32, device=dev)
-        check(lib.qk_map_ids_to_slots(ptr(p_ids), p_ids.numel(), ptr(table), table.numel(), ptr(slots), _stream()))
-        parent_info.total_time_ns = int((time.perf_counter() - t1) * 1e9)
-        if use_aps:
+            t1 = time.perf_counter()
+            p_ids, _p_dist, p_rows = self.parent._search_device(xq, psp, want_rows=True)
+            _, table = self.store.tables()
+            slots = torch.empty(p_ids.shape, dtype=torch.int32, device=xq.device)
+            check(_lib.load().qk_map_ids_to_slots(ptr(p_ids), p_ids.numel(), ptr(table), table.numel(), ptr(slots), _stream()))
+            parent_info.total_time_ns = int((time.perf_counter() - t1) * 1e9)
             if self.parent.parent is not None:
                 raise RuntimeError("quake_b200: APS needs a flat parent (two-level index)")
             ids, dist, scanned = aps.adaptive_scan(self, xq, p_rows, slots, sp)
@@ -209,9 +285,19 @@ class QuakeIndex:
             if tinfo is not None:
                 tinfo.partitions_scanned = int(scanned.sum().item())
         else:
-            ids, dist = scan_partitions(self.store, xq, slots, k, self.metric)
-        if self.maintenance_policy_params is not None and self.current_level == 0:
-            self._record_hits(p_ids)
+            t1 = time.perf_counter()
+            if GRAPHS_ENABLED and not _capturing and self.current_level == 0:
+                ids, dist, p_ids = self._plan(Q, sp).run(xq)
+                if p_ids is not None:
+                    p_ids = p_ids.clone()  # the hit window below outlives the plan's static buffer
+            else:
+                ids, dist, p_ids = self._search_core(xq, sp)
+            parent_info.total_time_ns = int((time.perf_counter() - t1) * 1e9)
+        if self.parent is not None:
+            parent_info.n_queries = Q
+            parent_info.n_clusters = self.parent.nlist()
+            if self.maintenance_policy_params is not None and self.current_level == 0:
+                self._record_hits(p_ids)
         return ids, dist, parent_info
 
     def _record_hits(self, p_ids: torch.Tensor) -> None:

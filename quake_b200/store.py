@@ -49,6 +49,7 @@ class PartitionStore:
         self.curr_list_id = 0
         self.max_row_norm = 0.0
         self._dirty = True
+        self.version = 0  # bumped by every mutation; search plans (CUDA graphs) are keyed by it
         self._cache = {}
 
     # ------------------------------------------------------------------ basic queries
@@ -352,6 +353,7 @@ class PartitionStore:
         if self._dirty:
             self._cache = {}
             self._dirty = False
+            self.version += 1
         if key in self._cache:
             return self._cache[key]
         nslots = self.slot_pid.size
