@@ -61,6 +61,7 @@ static constexpr int SCAN_THREADS = 32 * (SCAN_COMPUTE_WARPS + SCAN_SELECT_WARPS
 static constexpr int SCAN_MAX_NQ = 4;   // query-chunk ring depth
 static constexpr int MERGE_THREADS = 256;
 static constexpr int MERGE_SORT_CAP = 4096;
+static constexpr int MERGE_COMPACT_CAP = 512;
 static constexpr size_t SCAN_SMEM_LIMIT = 227 * 1024;
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -186,6 +187,18 @@ __global__ void expand_pairs_kernel(const int32_t* __restrict__ probe, int64_t Q
         int seg = -1;
         if (l >= 0 && l < num_lists && list_nseg[l] > 0) seg = list_seg0[l];
         pair_seg[q * P + j] = seg;  // P == nprobe here
+        if (seg >= 0) atomicAdd(&seg_count[seg], 1);
+    } else if (nprobe == 1) {
+        // one probed list per query (flat index / coarse scan): one thread per (query, segment slot)
+        int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        if (i >= Q * P) return;
+        int64_t q = i / P;
+        int s2 = (int)(i - q * P);
+        if (s2 == 0) gthr[q] = KEY_MAX;
+        int l = probe[q];
+        int seg = -1;
+        if (l >= 0 && l < num_lists && s2 < list_nseg[l]) seg = list_seg0[l] + s2;
+        pair_seg[i] = seg;
         if (seg >= 0) atomicAdd(&seg_count[seg], 1);
     } else {
         // one thread per query, sequential over its probes
@@ -991,7 +1004,10 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_refine_kernel(const Merge
     uint64_t* rkey = reinterpret_cast<uint64_t*>(qs + ((a.d + 3) & ~3));   // [kcp] (distkey<<32 | slot)
     int64_t* rid = reinterpret_cast<int64_t*>(rkey + kcp);                 // [kcp]
     uint32_t* rrow = reinterpret_cast<uint32_t*>(rid + kcp);               // [kcp]
-    __shared__ int s_n, s_tot;
+    __shared__ int s_n, s_tot, s_m;
+    __shared__ uint32_t s_T;
+    __shared__ uint32_t s_hist[256];
+    __shared__ uint64_t cbuf[MERGE_COMPACT_CAP];
     __shared__ double s_qn;
 
     const int64_t q = blockIdx.x;
@@ -1044,9 +1060,40 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_refine_kernel(const Merge
     bool rescan = overflow || a.force_rescan;
     int nc = 0;
     if (!rescan) {
-        const int np = next_pow2(ns > 1 ? ns : 1);
-        for (int i = ns + tid; i < np; i += blockDim.x) sbuf[i] = COMP_MAX;
-        block_bitonic_sort(sbuf, np, [](uint64_t x, uint64_t y) { return x < y; });
+        // The kc smallest composites (key << 32 | row), sorted. With many survivors a full sort is wasteful: one
+        // warp radix-selects the kc-th smallest key T, everything with key <= T is compacted (kc entries plus ties)
+        // and only that is sorted.
+        bool compacted = false;
+        if (ns > 4 * a.kc && ns > 256 && a.kc <= MERGE_COMPACT_CAP / 2) {
+            if (tid < 32) {
+                const uint64_t* sb = sbuf;
+                const uint32_t t = radix_select([sb](int i) { return (uint32_t)(sb[i] >> 32); }, ns, a.kc, s_hist, tid);
+                if (tid == 0) { s_T = t; s_m = 0; }
+            }
+            __syncthreads();
+            const uint32_t T = s_T;
+            for (int i = tid; i < ns; i += blockDim.x) {
+                const uint64_t v = sbuf[i];
+                if ((uint32_t)(v >> 32) <= T) {
+                    const int pos = atomicAdd(&s_m, 1);
+                    if (pos < MERGE_COMPACT_CAP) cbuf[pos] = v;
+                }
+            }
+            __syncthreads();
+            const int m = s_m;
+            if (m <= MERGE_COMPACT_CAP) {  // else: a pile of equal keys, fall back to the full sort
+                const int np = next_pow2(m > 1 ? m : 1);
+                for (int i = m + tid; i < np; i += blockDim.x) cbuf[i] = COMP_MAX;
+                block_bitonic_sort(cbuf, np, [](uint64_t x, uint64_t y) { return x < y; });
+                sbuf = cbuf;
+                compacted = true;
+            }
+        }
+        if (!compacted) {
+            const int np = next_pow2(ns > 1 ? ns : 1);
+            for (int i = ns + tid; i < np; i += blockDim.x) sbuf[i] = COMP_MAX;
+            block_bitonic_sort(sbuf, np, [](uint64_t x, uint64_t y) { return x < y; });
+        }
         nc = ns < a.kc ? ns : a.kc;
         // ---- exact refine in the reference's summation order
         // eight lanes per candidate, one per accumulator of the reference's 8-wide loop
@@ -1466,6 +1513,11 @@ int qk::scan_partitions_impl(const qk_store_t* st, const float* queries, int64_t
         expand_pairs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(probe_lists, Q, nprobe, p.P, st->list_seg0,
                                                                               st->list_nseg, st->num_lists, pair_seg,
                                                                               seg_count, gthr, true);
+    } else if (nprobe == 1) {
+        int64_t n = Q * p.P;
+        expand_pairs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(probe_lists, Q, nprobe, p.P, st->list_seg0,
+                                                                              st->list_nseg, st->num_lists, pair_seg,
+                                                                              seg_count, gthr, false);
     } else {
         expand_pairs_kernel<<<(unsigned)((Q + 127) / 128), 128, 0, stream>>>(probe_lists, Q, nprobe, p.P, st->list_seg0,
                                                                               st->list_nseg, st->num_lists, pair_seg,

@@ -335,6 +335,9 @@ class PartitionStore:
         IVF lists are short and numerous, so the default cut (QK_SEGMENT_ROWS) leaves them whole. A store of a
         few long lists (a flat index / the centroid list is ONE list) is cut finer until the batch yields a few
         items per SM."""
+        import os
+        if os.environ.get("QK_SEG_LEN"):
+            return int(os.environ["QK_SEG_LEN"])
         if num_queries * nprobe < 1024:
             return 256
         if self.nlist > 16 or self.list_size.size == 0:
@@ -342,7 +345,7 @@ class PartitionStore:
         chunks = max(1, (num_queries + 31) // 32) * min(self.nlist, nprobe)
         longest = max(int(self.list_size.max()), 1)
         seg_len = _MAX_SEGMENT_ROWS
-        while seg_len > 256 and chunks * ((longest + seg_len - 1) // seg_len) < 4 * 148:
+        while seg_len > 256 and chunks * ((longest + seg_len - 1) // seg_len) < 222:  # ~1.5 items per SM (measured best)
             seg_len //= 2
         return seg_len
 
