@@ -44,8 +44,9 @@ static constexpr int MMA_THREADS = 32 * 16;
 static constexpr int MMA_SMEM_HEADER = 4096;   // mbarriers, mailboxes, descriptor ring
 static constexpr int MMA_REFRESH_CAP = 1024;   // candidates a refresh looks at (any subset gives a valid bound)
 static constexpr int MMA_TMEM_COLS = 512;
-static constexpr int MMA_TMEM_D = 0;          // 2 accumulator buffers x 64 columns (a.b_hi | a_hi.b_lo)
-static constexpr int MMA_TMEM_ALO = 128;      // MMA_STAGES a_lo boxes x 32 columns
+static constexpr int MMA_NACC = 4;            // accumulator buffers: the epilogue may lag the MMAs by that many tiles
+static constexpr int MMA_TMEM_D = 0;          // MMA_NACC accumulator buffers x 64 columns (a.b_hi | a_hi.b_lo)
+static constexpr int MMA_TMEM_ALO = 256;      // MMA_STAGES a_lo boxes x 32 columns
 
 struct MmaDesc {  // published in shared memory by the producer warp for every work item in flight
     WorkItem w;
@@ -171,8 +172,8 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) scan_mma_kernel(const ScanArgs
     uint64_t* b_empty = bars + 50;     // [NB] MMA commit                    -> producer
     uint64_t* i_full = bars + 52;      // [ND] producer (descriptor written) -> every consumer warp
     uint64_t* i_empty = bars + 60;     // [ND] 13 consumer warps             -> producer
-    uint64_t* d_full = bars + 68;      // [2]  MMA commit                    -> epilogue group
-    uint64_t* d_empty = bars + 70;     // [2]  4 epilogue warps              -> MMA issuer
+    uint64_t* d_full = bars + 68;      // [NACC] MMA commit                  -> epilogue group
+    uint64_t* d_empty = bars + 72;     // [NACC] 4 epilogue warps            -> MMA issuer
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + 640);
     volatile uint32_t* ep_done = reinterpret_cast<volatile uint32_t*>(smem_raw + 644);       // epilogue warps that left
     volatile unsigned long long* mbox = reinterpret_cast<volatile unsigned long long*>(smem_raw + 704);  // [8] refresh requests
@@ -189,7 +190,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) scan_mma_kernel(const ScanArgs
         for (int s = 0; s < NS; ++s) { mbar_init(a_full + s, 1); mbar_init(a_empty + s, 5); mbar_init(alo_full + s, 4); }
         for (int s = 0; s < NB; ++s) { mbar_init(b_ready + s, 4); mbar_init(b_empty + s, 1); }
         for (int s = 0; s < ND; ++s) { mbar_init(i_full + s, 1); mbar_init(i_empty + s, 13); }
-        for (int s = 0; s < 2; ++s) { mbar_init(d_full + s, 1); mbar_init(d_empty + s, 4); }
+        for (int s = 0; s < MMA_NACC; ++s) { mbar_init(d_full + s, 1); mbar_init(d_empty + s, 4); }
         mbar_fence_init();
         *ep_done = 0;
         for (int s = 0; s < 8; ++s) mbox[s] = 0ull;
@@ -296,18 +297,14 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) scan_mma_kernel(const ScanArgs
             const uint32_t bs = smem_u32(Bs + (size_t)ib * 4 * MMA_BBOX_BYTES);
             const int ntiles = (d.nrows + TM - 1) / TM;
             for (int tile = 0; tile < ntiles; ++tile, ++T) {
-                const int db = T & 1u;
-                mbar_wait(d_empty + db, ((T >> 1) & 1u) ^ 1u);
+                const int db = T % MMA_NACC;
+                mbar_wait(d_empty + db, ((T / MMA_NACC) & 1u) ^ 1u);
                 const uint32_t tmem_d = tmem + MMA_TMEM_D + db * (2 * MMA_NQ);
-                // The split warps take the boxes in order and wait for the TMA data themselves, so the a_lo
-                // barrier of the tile's LAST box covers every box of the tile: one wait per tile.
-                {
-                    const uint32_t ul = U + nbox - 1;
-                    mbar_wait(alo_full + ul % NS, (ul / NS) & 1u);
-                }
-                tc_fence_after();
-                for (int b = 0; b < nbox; ++b) {
-                    const int st = (U + b) % NS;
+                for (int b = 0; b < nbox; ++b, ++U) {
+                    const int st = U % NS;
+                    // the split warps waited for the TMA data of this box themselves: a_lo ready => a_hi ready
+                    mbar_wait(alo_full + st, (U / NS) & 1u);
+                    tc_fence_after();
                     const uint64_t da0 = umma_desc_sw128(smem_u32(As + (size_t)st * MMA_BOX_BYTES));
                     const uint64_t db0 = umma_desc_sw128(bs + b * MMA_BBOX_BYTES);
                     const uint32_t talo = tmem + MMA_TMEM_ALO + st * MMA_BOX;
@@ -319,11 +316,9 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) scan_mma_kernel(const ScanArgs
                             umma_ts(tmem_d, talo + kk * 8, db0 + 2 * kk, IDESC32, 1u);
                         }
                     }
+                    umma_commit(a_empty + st);  // the row box (and its a_lo columns) may be refilled
                 }
-                // the row boxes (and their a_lo columns) may be refilled once these MMAs have completed
-                for (int b = 0; b < nbox; ++b) umma_commit(a_empty + (U + b) % NS);
                 umma_commit(d_full + db);
-                U += nbox;
             }
             umma_commit(b_empty + ib);
         }
@@ -432,11 +427,12 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) scan_mma_kernel(const ScanArgs
                 const uint32_t g_now = my_q >= 0 ? __ldcg(a.gthr + my_q) : KEY_MAX;
                 float nrm = 0.f;
                 if (!kIP && r < tr) nrm = __ldg(a.norms + d.row0 + (int64_t)tile * TM + r);
-                mbar_wait(d_full + eg, (T >> 1) & 1u);
+                const int db = T % MMA_NACC;  // group eg sees the buffers with db & 1 == eg
+                mbar_wait(d_full + db, (T / MMA_NACC) & 1u);
                 tc_fence_after();
                 uint32_t v[32];  // dot = (a_hi + a_lo) . b_hi [columns 0-31] + a_hi . b_lo [columns 32-63]
                 {
-                    const uint32_t td = tmem + MMA_TMEM_D + eg * (2 * MMA_NQ) + ((uint32_t)(q4 * 32) << 16);
+                    const uint32_t td = tmem + MMA_TMEM_D + db * (2 * MMA_NQ) + ((uint32_t)(q4 * 32) << 16);
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
                         uint32_t x[16], y[16];
@@ -449,7 +445,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) scan_mma_kernel(const ScanArgs
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(d_empty + eg);
+                if (lane == 0) mbar_arrive(d_empty + db);
                 if (a.dbg & 1) continue;
                 // ---- scores of this thread's row against the 32 query slots; bit g of pm: the score passes
                 uint32_t pm = 0;
