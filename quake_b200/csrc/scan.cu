@@ -90,8 +90,12 @@ static_assert(256 + SCAN_MAX_NQ * sizeof(ItemDesc) <= SCAN_SMEM_HEADER, "header"
 // appends and several pairs of one query can be in flight, hence the slack. Overflow is not an error: the query
 // is handed to the exact re-scan.
 static int candidate_buffer_cap(int kc) {
-    int c = 32 * kc;
-    if (c < 2048) c = 2048;
+    // small k: thresholds converge within a few hundred appends. Large k needs many more rows before a useful
+    // threshold exists (the kc-th best of what was seen so far) and floods the refresh warps meanwhile: give it room
+    // (8 B per entry) rather than pay the exact re-scan.
+    int c = kc <= 32 ? 2048 : 256 * kc;
+    if (c > 32768) c = 32768;
+    if (c < 32 * kc) c = 32 * kc;
     if (c > 65536) c = 65536;
     return c;
 }
@@ -157,8 +161,14 @@ static int make_plan(const qk_store_t* st, int64_t Q, int nprobe, int k, ScanPla
         int sample = 32;
         while (sample < 1024 && sample < 8 * p->kc) sample <<= 1;
         const size_t store_bytes = (size_t)st->num_rows * st->pitch * sizeof(float);
-        if (store_bytes > ((size_t)32 << 20))
-            while (sample > 32 && (size_t)Q * sample * p->dp * sizeof(float) > ((size_t)96 << 20)) sample >>= 1;
+        if (store_bytes > ((size_t)32 << 20)) {
+            // budget: 96 MB, or a tenth of what the scan itself is expected to stream for this batch
+            const double lists = (double)(Q * (int64_t)nprobe < st->num_lists ? Q * (int64_t)nprobe : st->num_lists);
+            const double scan_bytes = lists * ((double)st->num_rows / (st->num_lists > 0 ? st->num_lists : 1)) * p->dp * 4.0;
+            size_t budget = (size_t)96 << 20;
+            if (scan_bytes / 10.0 > (double)budget) budget = (size_t)(scan_bytes / 10.0);
+            while (sample > 32 && sample / 2 >= p->kc && (size_t)Q * sample * p->dp * sizeof(float) > budget) sample >>= 1;
+        }
         p->flat_seed = (st->num_lists == 1 && nprobe == 1) ? 1 : 0;
         if (sample < p->kc || (!p->flat_seed && (size_t)2 * (p->dp + sample) * sizeof(float) > 48 * 1024)) sample = 0;
         p->sample = sample;

@@ -522,8 +522,11 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) scan_mma_kernel(const ScanArgs
                 const int q = (int)(req >> 32) - 1;
                 int fill = (int)(uint32_t)req;
                 if (fill > qcap) fill = qcap;
-                // the most recent entries carry the tightest keys; any subset yields a valid upper bound
-                const int n = fill < MMA_REFRESH_CAP ? fill : MMA_REFRESH_CAP;
+                // the most recent entries carry the tightest keys; any subset yields a valid upper bound, and a
+                // short one keeps the refresh rate up when appends come fast
+                int ncap = 4 * kc > 256 ? 4 * kc : 256;
+                if (ncap > MMA_REFRESH_CAP) ncap = MMA_REFRESH_CAP;
+                const int n = fill < ncap ? fill : ncap;
                 const unsigned long long* qb = reinterpret_cast<const unsigned long long*>(a.qbuf) + (size_t)q * qcap + (fill - n);
                 for (int base = 0; base < n; base += 256) {
                     unsigned long long e[8];
