@@ -31,6 +31,16 @@
 
 namespace qk {
 
+static int g_scan_variant = -1;  // 0: tensor-core filter for d <= 128 (default), 1: FP32-pipe filter everywhere
+static int g_force_rescan = 0;
+static void read_scan_env() {
+    if (g_scan_variant >= 0) return;
+    const char* e = getenv("QK_SCAN_PATH");
+    g_scan_variant = (e && strcmp(e, "ffma") == 0) ? 1 : 0;
+    const char* f = getenv("QK_FORCE_RESCAN");
+    g_force_rescan = f ? atoi(f) : 0;
+}
+
 // ------------------------------------------------------------------------------------------------
 // plan
 // ------------------------------------------------------------------------------------------------
@@ -48,6 +58,8 @@ struct ScanPlan {
     int sample;   // rows sampled per query for the threshold seed (0: no seeding)
     int flat_seed;  // every query samples the same rows (single-list store): seed scores as one small GEMM
     size_t off_skeys;
+    int dense;    // flat store, small enough: the filter writes every score, one select per query replaces thresholds
+    size_t off_dense;
 };
 
 static constexpr int SCAN_DC = 128;     // floats of a row staged per pipeline unit
@@ -111,6 +123,7 @@ static size_t scan_smem_bytes(int dp, int kc, int gq, int nq) {
 }
 
 static int make_plan(const qk_store_t* st, int64_t Q, int nprobe, int k, ScanPlan* p) {
+    read_scan_env();
     QK_REQUIRE(k >= 1 && k <= QK_MAX_K, "k=%d out of range [1, %d]", k, QK_MAX_K);
     QK_REQUIRE(st->d >= 1 && st->pitch >= st->d && st->pitch % 4 == 0, "bad store d=%d pitch=%lld", st->d,
                (long long)st->pitch);
@@ -172,8 +185,15 @@ static int make_plan(const qk_store_t* st, int64_t Q, int nprobe, int k, ScanPla
         p->flat_seed = (st->num_lists == 1 && nprobe == 1) ? 1 : 0;
         if (sample < p->kc || (!p->flat_seed && (size_t)2 * (p->dp + sample) * sizeof(float) > 48 * 1024)) sample = 0;
         p->sample = sample;
+        // dense mode: [Q x rows] keys, at most 512 MB and at most 16384 rows (the select keeps a query's keys in smem)
+        p->dense = (p->flat_seed && g_scan_variant == 0 && p->dp <= 128 && Q <= 8192 && st->flat_rows >= p->kc && st->flat_rows <= 16384 &&
+                    (size_t)Q * (size_t)st->flat_rows * 4 <= ((size_t)512 << 20) && getenv("QK_NO_DENSE") == nullptr)
+                       ? 1 : 0;
+        if (p->dense) p->sample = sample = 0;
         p->off_skeys = o;
         if (p->flat_seed && sample) o = align_up(o + (size_t)Q * sample * 4, 256);
+        p->off_dense = o;
+        if (p->dense) o = align_up(o + (size_t)Q * (size_t)st->flat_rows * 4, 256);
     }
     p->total = o;
     return QK_OK;
@@ -562,6 +582,76 @@ __global__ void __launch_bounds__(256) seed_select_flat_kernel(const uint32_t* _
     }
 }
 
+// Dense mode (flat stores whose [Q x rows] score matrix is small: the coarse centroid scan): the filter kernel
+// stores the key of every (query, row); one CTA per query then radix-selects the kc-th smallest key T and emits the
+// rows with key <= T as that query's candidates -- the same candidate-buffer contract merge_refine expects
+// (qcount = candidates, gthr = T), without thresholds, atomics or refresh in the filter.
+__global__ void __launch_bounds__(256) dense_select_kernel(const uint32_t* __restrict__ dense, int rows, long long row0,
+                                                           int kc, int qcap, uint32_t* __restrict__ gthr,
+                                                           int32_t* __restrict__ qcount, uint64_t* __restrict__ qbuf) {
+    extern __shared__ uint32_t dkeys[];  // [rows]
+    __shared__ uint32_t hist[256];
+    __shared__ uint32_t s_prefix, s_need;
+    __shared__ int s_m;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int64_t q = blockIdx.x;
+    const uint32_t* src = dense + (size_t)q * rows;
+    for (int i = tid; i < rows; i += 256) dkeys[i] = src[i];
+    if (tid == 0) { s_prefix = 0; s_need = (uint32_t)kc; s_m = 0; }
+    __syncthreads();
+    for (int pass = 3; pass >= 0; --pass) {
+        hist[tid] = 0;
+        __syncthreads();
+        const uint32_t prefix = s_prefix;
+        const int sh = 8 * pass;
+        for (int i = tid; i < rows; i += 256) {
+            const uint32_t key = dkeys[i];
+            if (pass == 3 || (key >> (sh + 8)) == (prefix >> (sh + 8))) atomicAdd(&hist[(key >> sh) & 255u], 1u);
+        }
+        __syncthreads();
+        if (tid < 32) {  // lane l owns bins 8l .. 8l+7
+            uint32_t h[8], sum = 0;
+#pragma unroll
+            for (int b = 0; b < 8; ++b) { h[b] = hist[lane * 8 + b]; sum += h[b]; }
+            uint32_t incl = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += y;
+            }
+            const uint32_t need = s_need;
+            const unsigned owner = __ballot_sync(0xffffffffu, incl >= need);
+            const int ol = __ffs(owner) - 1;
+            if (lane == ol) {
+                uint32_t before = incl - sum;
+                int bin = 0;
+#pragma unroll
+                for (int b = 0; b < 8; ++b) {
+                    if (before + h[b] >= need) { bin = lane * 8 + b; break; }
+                    before += h[b];
+                }
+                s_prefix = prefix | ((uint32_t)bin << sh);
+                s_need = need - before;
+            }
+        }
+        __syncthreads();
+    }
+    const uint32_t T = s_prefix;
+    uint64_t* qb = qbuf + (size_t)q * qcap;
+    for (int i = tid; i < rows; i += 256) {
+        const uint32_t key = dkeys[i];
+        if (key <= T) {
+            const int pos = atomicAdd(&s_m, 1);
+            if (pos < qcap) qb[pos] = ((uint64_t)key << 32) | (uint32_t)(row0 + i);
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        qcount[q] = s_m;
+        gthr[q] = T;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // 4. the scan (filter) kernel
 // ------------------------------------------------------------------------------------------------
@@ -578,6 +668,9 @@ struct ScanArgs {
     uint64_t* qbuf;    // [Q][qcap] candidates: key << 32 | arena row; unwritten slots are 0xff..ff
     int P, kc, gq, nq;
     int qcap;
+    uint32_t* dense;      // dense mode: [Q x dense_rows] filter keys of every (query, row); null otherwise
+    long long dense_row0;
+    int dense_rows;
     int dbg;  // profiling aid (QK_SCAN_DBG): skip pipeline stages to find the floor of the others; results are invalid
 };
 
@@ -1001,6 +1094,7 @@ struct MergeArgs {
     float* out_dist;
     int64_t* out_rows;
     int force_rescan;
+    int sort_cap;  // survivors the shared-memory sort buffer holds (a power of two; more => exact re-scan)
     const int32_t* seg_rows;
     int rank_squared;  // l2 only: order by the squared distance (k-means assign: faiss Top1 on squared l2)
 };
@@ -1008,8 +1102,8 @@ struct MergeArgs {
 template <bool kIP>
 __global__ void __launch_bounds__(MERGE_THREADS) merge_refine_kernel(const MergeArgs a) {
     extern __shared__ __align__(16) unsigned char msm[];
-    uint64_t* sbuf = reinterpret_cast<uint64_t*>(msm);                     // [MERGE_SORT_CAP]
-    float* qs = reinterpret_cast<float*>(sbuf + MERGE_SORT_CAP);           // [d]
+    uint64_t* sbuf = reinterpret_cast<uint64_t*>(msm);                     // [sort_cap]
+    float* qs = reinterpret_cast<float*>(sbuf + a.sort_cap);               // [d]
     const int kcp = next_pow2(a.kc);
     uint64_t* rkey = reinterpret_cast<uint64_t*>(qs + ((a.d + 3) & ~3));   // [kcp] (distkey<<32 | slot)
     int64_t* rid = reinterpret_cast<int64_t*>(rkey + kcp);                 // [kcp]
@@ -1048,7 +1142,7 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_refine_kernel(const Merge
             const uint32_t key = (uint32_t)(v >> 32);
             if (key > gthr || key == KEY_MAX) continue;
             const int pos = atomicAdd(&s_n, 1);
-            if (pos < MERGE_SORT_CAP) sbuf[pos] = v;
+            if (pos < a.sort_cap) sbuf[pos] = v;
             else overflow = true;
         }
     }
@@ -1382,9 +1476,6 @@ __global__ void __launch_bounds__(256) exact_rescan_kernel(const MergeArgs a, co
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-static int g_scan_variant = -1;
-static int g_force_rescan = 0;
-
 // optional per-launch timing of the filter kernel (qk_profile_*): CUDA events recorded on the launch
 // stream right around scan_kernel, read back by the caller after it has synchronised.
 struct ProfileRecord {
@@ -1492,12 +1583,6 @@ int qk::scan_partitions_impl(const qk_store_t* st, const float* queries, int64_t
         set_error("workspace too small: need %zu bytes, have %zu", p.total, workspace_bytes);
         return QK_ERR_WORKSPACE;
     }
-    if (g_scan_variant < 0) {
-        const char* e = getenv("QK_SCAN_PATH");
-        g_scan_variant = (e && strcmp(e, "ffma") == 0) ? 1 : 0;
-        const char* f = getenv("QK_FORCE_RESCAN");
-        g_force_rescan = f ? atoi(f) : 0;
-    }
     char* ws = (char*)workspace;
     int32_t* pair_seg = (int32_t*)(ws + p.off_pair_seg);
     int32_t* seg_count = (int32_t*)(ws + p.off_seg_count);
@@ -1516,7 +1601,7 @@ int qk::scan_partitions_impl(const qk_store_t* st, const float* queries, int64_t
 
     // seg_count, seg_fill, flags, qcount, ctrl are contiguous: one memset; candidate slots start as +inf
     QK_CUDA(cudaMemsetAsync(ws + p.off_seg_count, 0, p.off_seg_start - p.off_seg_count, stream));
-    QK_CUDA(cudaMemsetAsync(qbuf, 0xff, (size_t)Q * p.qcap * 8, stream));
+    if (!p.dense) QK_CUDA(cudaMemsetAsync(qbuf, 0xff, (size_t)Q * p.qcap * 8, stream));
     const bool single = (p.P == nprobe);
     if (single) {
         int64_t n = Q * nprobe;
@@ -1591,6 +1676,9 @@ int qk::scan_partitions_impl(const qk_store_t* st, const float* queries, int64_t
         static int dbg = -1;
         if (dbg < 0) { const char* e = getenv("QK_SCAN_DBG"); dbg = e ? atoi(e) : 0; }
         sa.dbg = dbg;
+        sa.dense = p.dense ? (uint32_t*)(ws + p.off_dense) : nullptr;
+        sa.dense_row0 = st->flat_row0;
+        sa.dense_rows = (int)st->flat_rows;
     }
     CUtensorMap vmap;
     // d <= 128: tensor-core filter (tcgen05, 3xTF32 split); otherwise the FP32-pipe kernel. QK_SCAN_PATH=ffma
@@ -1608,6 +1696,14 @@ int qk::scan_partitions_impl(const qk_store_t* st, const float* queries, int64_t
     rc = launch_scan(sa, vmap, metric, p.smem, use_mma, stream);
     if (rc) return rc;
     if (rec) QK_CUDA(cudaEventRecord(rec->stop, stream));
+    if (p.dense) {
+        const size_t dsm = (size_t)st->flat_rows * sizeof(uint32_t);
+        if (dsm > 48 * 1024)
+            QK_CUDA(cudaFuncSetAttribute(dense_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm));
+        dense_select_kernel<<<(unsigned)Q, 256, dsm, stream>>>(sa.dense, (int)st->flat_rows, st->flat_row0, p.kc, p.qcap, gthr,
+                                                               qcount, qbuf);
+        QK_CUDA(cudaGetLastError());
+    }
 
     MergeArgs ma;
     ma.vecs = st->vectors; ma.pitch = st->pitch; ma.ids = st->ids; ma.d = st->d;
@@ -1624,7 +1720,11 @@ int qk::scan_partitions_impl(const qk_store_t* st, const float* queries, int64_t
     {
         int kcp = 1;
         while (kcp < p.kc) kcp <<= 1;
-        size_t msmem = MERGE_SORT_CAP * 8 + (size_t)((st->d + 3) & ~3) * 4 + (size_t)kcp * (8 + 8 + 4) + 16;
+        // the sort buffer never needs more than the candidate buffer holds; small buffers let more CTAs share an SM
+        int sort_cap = MERGE_SORT_CAP;
+        while (sort_cap / 2 >= p.qcap && sort_cap > 256) sort_cap >>= 1;
+        ma.sort_cap = sort_cap;
+        size_t msmem = (size_t)sort_cap * 8 + (size_t)((st->d + 3) & ~3) * 4 + (size_t)kcp * (8 + 8 + 4) + 16;
         if (metric == QK_METRIC_INNER_PRODUCT) {
             QK_CUDA(cudaFuncSetAttribute(merge_refine_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem));
             merge_refine_kernel<true><<<(unsigned)Q, MERGE_THREADS, msmem, stream>>>(ma);

@@ -462,6 +462,15 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) scan_mma_kernel(const ScanArgs
                         pm |= (sc <= lim[j]) ? (1u << g) : 0u;
                     }
                 }
+                if (a.dense) {  // dense mode: every score goes out, the per-query select follows the kernel
+                    if (r < tr) {
+                        const long long lrow = d.row0 + (long long)tile * TM + r - a.dense_row0;
+#pragma unroll
+                        for (int g = 0; g < MMA_NQ; ++g)
+                            if (g < g_cnt) a.dense[(size_t)dq[g] * a.dense_rows + lrow] = f2key(__uint_as_float(v[g]));
+                    }
+                    continue;
+                }
                 pm &= gvalid;
                 if (r >= tr) pm = 0;
                 // ---- survivors: one atomic each (issued four at a time), then the entry stores
