@@ -32,9 +32,9 @@ sys.path.insert(0, ROOT)
 
 WORKLOAD = {"name": "C2: 1M x 128 f32 randn, nlist=4096, Q=1024, k=10, l2, nprobe=64",
             "N": 1_000_000, "d": 128, "nlist": 4096, "Q": 1024, "k": 10, "nprobe": 64, "metric": "l2", "niter": 5}
-# kernels of ours per search step: coarse scan (expand, 2 seed, prefix, scatter, scan, merge, rescan) + slot map +
-# partition scan (expand, seed, prefix, scatter, scan, merge, rescan); memsets and the hit-window copy not counted
-LAUNCHES_PER_STEP = 16
+# kernels of ours per search step: coarse scan (expand, prefix, scatter, scan, dense select, merge, rescan) + slot
+# map + partition scan (expand, seed, prefix, scatter, scan, merge, rescan); memsets and the hit-window copy not counted
+LAUNCHES_PER_STEP = 15
 METRIC = "search_qps_k10_d128"
 UNIT = "queries/s"
 
@@ -385,7 +385,7 @@ def run_b200(args):
                        "k": W["k"], "metric": W["metric"], "parallelism": f"replicas x{world}" if world > 1 else "1 gpu",
                        "l2_policy": "index (512 MB of lists) larger than L2; no flush between steps",
                        "build_s": round(build_s, 2), "parity": parity, "scan_stats": scan_stats},
-            "roofline": {"bound": "hbm", "kernel": "scan_kernel (partition-scan filter)", "achieved": achieved,
+            "roofline": {"bound": "hbm", "kernel": "scan_mma_kernel (partition-scan filter, tcgen05)", "achieved": achieved,
                          "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None, "traffic": traffic,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
                          "per_query_list_bytes_per_launch": pair_bytes, "kernel_ms": scan_ms_avg,

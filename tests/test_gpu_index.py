@@ -372,3 +372,36 @@ def test_sharded_partials_merge_to_unsharded_result(metric):
     pd = torch.stack([p[1] for p in parts]).contiguous()
     mi, md = sharded.merge_partials_device(pd, pi, 10, full.metric)
     assert torch.equal(mi.cpu(), want.ids) and torch.equal(md.cpu(), want.distances)
+
+
+def test_graph_replayed_search_equals_eager_and_tracks_updates():
+    """Fixed-nprobe searches replay a CUDA graph captured per (batch size, k, nprobe, index version): same answer
+    as the eager launches, results handed to the caller are copies (not the plan's static buffers), and a
+    mutation of the index invalidates the plan."""
+    qb = _qb()
+    from quake_b200 import index as qidx
+    torch.manual_seed(5)
+    n, d = 20000, 64
+    x = torch.randn(n, d)
+    bp = qb.IndexBuildParams()
+    bp.nlist = 40
+    idx = qb.QuakeIndex()
+    idx.build(x, torch.arange(n, dtype=torch.int64), bp)
+    q = torch.randn(128, d)
+    sp = qb.SearchParams()
+    sp.k, sp.nprobe = 10, 6
+    qidx.GRAPHS_ENABLED = False
+    try:
+        eager = idx.search(q, sp)
+    finally:
+        qidx.GRAPHS_ENABLED = True
+    r1 = idx.search(q, sp)
+    r2 = idx.search(torch.randn(128, d), sp)  # same plan, other queries
+    r3 = idx.search(q, sp)
+    assert torch.equal(r1.ids, eager.ids) and torch.equal(r1.distances, eager.distances)
+    assert torch.equal(r3.ids, r1.ids) and not torch.equal(r2.ids, r1.ids)
+    # mutation: the new vectors (copies of the queries) must be found by the next search
+    idx.add(q.clone(), torch.arange(n, n + 128, dtype=torch.int64))
+    r4 = idx.search(q, sp)
+    assert torch.equal(r4.ids[:, 0], torch.arange(n, n + 128, dtype=torch.int64))
+    assert float(r4.distances[:, 0].abs().max()) == 0.0

@@ -137,3 +137,35 @@ def test_fp32_pipe_kernel_path():
     env = dict(os.environ, QK_SCAN_PATH="ffma")
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, cwd=root)
     assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
+
+
+def test_large_k_many_probes_no_rescan():
+    """k = 100 over 32 probed lists of ~600 rows: thresholds converge slowly for large k, the candidate buffers must
+    absorb that without sending queries to the exhaustive re-scan (and the answer is still the oracle's)."""
+    import os
+    from quake_b200 import index as qidx
+    sizes = np.full(48, 600)
+    st, lists = _make_store(sizes, 128, seed=21)
+    os.environ["QK_SCAN_STATS"] = "1"
+    try:
+        _check(st, lists, Q=256, nprobe=32, k=100, metric="l2", seed=22)
+        stats = qidx.LAST_SCAN_STATS.cpu().tolist()
+    finally:
+        os.environ.pop("QK_SCAN_STATS")
+    assert stats[0] == 0, f"{stats[0]} queries took the exact re-scan"
+
+
+def test_flat_store_threshold_path_matches_dense_path():
+    """A single-list store is scanned in dense mode by default (every key stored, one select per query);
+    QK_NO_DENSE=1 forces the threshold/seed path over the same cases."""
+    import subprocess, sys, os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import sys; sys.path.insert(0, %r);"
+            "import numpy as np, tests.test_gpu_scan as t;"
+            "st, lists = t._make_store(np.array([5000]), 128, seed=31);"
+            "assert t._check(st, lists, Q=300, nprobe=1, k=64, metric='l2', seed=1) == 0;"
+            "assert t._check(st, lists, Q=300, nprobe=1, k=10, metric='ip', seed=2) == 0; print('ok')") % (root,)
+    for env_extra in ({}, {"QK_NO_DENSE": "1"}):
+        env = dict(os.environ, **env_extra)
+        out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, cwd=root)
+        assert out.returncode == 0 and "ok" in out.stdout, (env_extra, out.stderr[-2000:])
