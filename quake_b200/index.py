@@ -428,18 +428,11 @@ class QuakeIndex:
         d = self.store.d
         pid_t = torch.tensor(pids, dtype=torch.int64)
         cents = clustering.pad_rows(self.parent.get(pid_t.to(dev)), dev)
-        vecs, vids = [], []
-        for p in pids:
-            v, i = self.store.get_list(p, padded=True)
-            vecs.append(v)
-            vids.append(i)
-        allv = torch.cat(vecs).contiguous()
-        alli = torch.cat(vids).contiguous()
+        rows = self.store.rows_of(pids)
+        allv = self.store.vectors.index_select(0, rows)
+        alli = self.store.ids.index_select(0, rows)
         new_c, counts, nv, ni = clustering.kmeans_refine(cents, d, allv, alli, self.metric, int(iterations))
-        counts_h = counts.cpu().numpy()
-        offs = np.concatenate([[0], np.cumsum(counts_h)])
-        for j, p in enumerate(pids):
-            self.store.set_list(p, nv[offs[j]:offs[j + 1], :d], ni[offs[j]:offs[j + 1]])
+        self.store.replace_lists(pids, counts.cpu().numpy(), nv, ni)
         self.parent.modify(pid_t, new_c[:, :d])
 
     def maintenance(self) -> MaintenanceTimingInfo:

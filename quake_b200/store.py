@@ -314,6 +314,41 @@ class PartitionStore:
         self.list_size[s] = n
         self._dirty = True
 
+    def rows_of(self, pids) -> torch.Tensor:
+        """Arena rows of the members of the given partitions, partition by partition (device int64)."""
+        slots = np.array([self.pid_slot[int(p)] for p in pids], dtype=np.int64)
+        sz = torch.from_numpy(self.list_size[slots]).to(self.device)
+        r0 = torch.from_numpy(self.list_row0[slots]).to(self.device)
+        n = int(self.list_size[slots].sum())
+        if n == 0:
+            return torch.zeros(0, dtype=torch.int64, device=self.device)
+        starts = torch.cumsum(sz, 0) - sz
+        return torch.arange(n, dtype=torch.int64, device=self.device) + torch.repeat_interleave(r0 - starts, sz)
+
+    def replace_lists(self, pids, counts: np.ndarray, vecs: torch.Tensor, ids: torch.Tensor) -> None:
+        """Replace the content of several lists at once: list pids[j] receives rows
+        vecs[offs[j]:offs[j+1]] (kmeans_refine_partitions hands back all rebuilt partitions together). The rows
+        are a permutation of vectors already in the store, so the row-norm bound is unchanged."""
+        slots = np.array([self.pid_slot[int(p)] for p in pids], dtype=np.int64)
+        counts = np.asarray(counts, dtype=np.int64)
+        self.list_size[slots] = 0
+        for j in np.nonzero(counts > self.list_cap[slots])[0]:  # the few lists that outgrow their slack
+            self._grow_list(int(slots[j]), int(counts[j] + max(16, counts[j] // 8)))
+        n = int(counts.sum())
+        if n:
+            cnt_d = torch.from_numpy(counts).to(self.device)
+            r0 = torch.from_numpy(self.list_row0[slots]).to(self.device)
+            starts = torch.cumsum(cnt_d, 0) - cnt_d
+            dst = torch.arange(n, dtype=torch.int64, device=self.device) + torch.repeat_interleave(r0 - starts, cnt_d)
+            vecs = vecs.contiguous()
+            check(_lib.load().qk_scatter_rows(ptr(vecs), vecs.stride(0), ptr(ids.contiguous()), None, ptr(dst), n, self.d,
+                                              ptr(self.vectors), self.pitch, ptr(self.ids), _stream()))
+            xn = torch.empty(n, dtype=torch.float32, device=self.device)
+            check(_lib.load().qk_row_sqnorms(ptr(vecs), n, vecs.stride(0), self.d, ptr(xn), _stream()))
+            self.norms[dst] = xn
+        self.list_size[slots] = counts
+        self._dirty = True
+
     def compact(self) -> None:
         """Rewrite the arena without dead space (lists keep their content order)."""
         pids = self.partition_ids()
