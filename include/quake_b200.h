@@ -61,6 +61,8 @@ typedef struct qk_store {
     int64_t        num_rows;     /* rows allocated behind `vectors` (bounds of the TMA tensor map)       */
     int64_t        flat_row0;    /* single-list stores (num_lists == 1): first arena row of the list ...  */
     int64_t        flat_rows;    /* ... and its length (host-known copy; 0 otherwise)                     */
+    int32_t        max_segment_rows; /* largest seg_rows entry (host-known; 0 = unknown)                   */
+    int32_t        reserved_;
 } qk_store_t;
 
 #define QK_SEGMENT_ROWS 4096

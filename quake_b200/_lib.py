@@ -43,6 +43,8 @@ class QkStore(C.Structure):
         ("num_rows", C.c_int64),
         ("flat_row0", C.c_int64),
         ("flat_rows", C.c_int64),
+        ("max_segment_rows", C.c_int32),
+        ("reserved_", C.c_int32),
     ]
 
 

@@ -14,9 +14,9 @@ import torch
 from . import _lib
 from ._lib import check, ptr
 
-_FIRST_ROUND = 4   # probe ranks scanned in the first round; doubles every round up to _MAX_ROUND
-_MAX_ROUND = 32
-_MAX_PSEUDO = 1 << 16  # pseudo-queries (query, rank) per scan call
+_FIRST_ROUND = 4   # probe ranks scanned in the first round
+_MAX_ROUND = 128   # ... doubling every round while most queries are still active
+_MAX_PSEUDO = 1 << 17  # pseudo-queries (query, rank) per scan call
 
 _beta_tables: dict = {}
 
@@ -88,8 +88,12 @@ def adaptive_scan(index, xq: torch.Tensor, cand_rows: torch.Tensor, slots: torch
                                  int(bool(sp.use_precomputed)), ptr(run_ids), ptr(run_dist), ptr(run_cnt), ptr(radius),
                                  ptr(have), ptr(probs), ptr(done), ptr(scanned), ptr(still), _stream()))
         p += r_eff
-        R = min(2 * R, _MAX_ROUND)
-        if int(still.item()) == 0:   # one host read per round: how many queries go on
+        n_still = int(still.item())   # one host read per round: how many queries go on
+        if n_still == 0:
             break
+        # every round streams the probed lists again: while most queries are still going, bigger rounds cost less than
+        # the ranks a finishing query over-scans; once most have stopped, keep the round size
+        if 2 * n_still > Qa:
+            R = min(2 * R, _MAX_ROUND)
         active = torch.nonzero(done == 0).reshape(-1).to(torch.int32)
     return run_ids, run_dist, scanned

@@ -573,6 +573,7 @@ extern "C" int qk_kmeans_assign(const float* points, int64_t n, int64_t point_pi
     st.num_rows = K;
     st.flat_row0 = 0;
     st.flat_rows = K;
+    st.max_segment_rows = 0;
     for (int64_t b = 0; b < n; b += B) {
         const int64_t cnt = (n - b) < B ? (n - b) : B;
         rc = scan_partitions_impl(&st, points + b * point_pitch, cnt, point_pitch, probe, 1, metric, 1, ids, dist, rows,

@@ -166,6 +166,11 @@ static int make_plan(const qk_store_t* st, int64_t Q, int nprobe, int k, ScanPla
     p->off_items = o;      o = align_up(o + max_items * sizeof(WorkItem), 256);
     p->off_gthr = o;       o = align_up(o + (size_t)Q * 4, 256);
     p->qcap = candidate_buffer_cap(p->kc);
+    if (st->max_segment_rows > 0) {
+        // a query never appends more rows than it scans
+        const int64_t bound = ((int64_t)p->P * st->max_segment_rows + 63) / 64 * 64;
+        if (bound < p->qcap) p->qcap = (int)(bound < 64 ? 64 : bound);
+    }
     p->off_qbuf = o;       o = align_up(o + (size_t)Q * p->qcap * 8, 256);
     // threshold seeds from a sample of the query's first probed rows: about 8 * kc of them (pass rate of the seed
     // ~ 1/8), bounded by the read traffic it costs -- unless the whole store is small enough to sit in L2 (a flat

@@ -200,8 +200,23 @@ class QuakeIndex:
         else:
             xq = clustering.pad_rows(x, self.store.device)
         ids, dist, parent_info = self._search_device(xq, search_params, tinfo)
-        res.ids = ids.to(out_dev)
-        res.distances = dist.to(out_dev)
+        if out_dev.type == "cpu":
+            # both results through pinned staging buffers, one synchronisation
+            k = int(ids.shape[1])
+            stage = self.__dict__.setdefault("_host_stage", {})
+            key = (int(ids.shape[0]), k)
+            if key not in stage:
+                if len(stage) >= _MAX_PLANS:
+                    stage.clear()
+                stage[key] = (torch.empty(key, dtype=torch.int64).pin_memory(), torch.empty(key, dtype=torch.float32).pin_memory())
+            h_ids, h_dist = stage[key]
+            h_ids.copy_(ids, non_blocking=True)
+            h_dist.copy_(dist, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            res.ids, res.distances = h_ids.clone(), h_dist.clone()
+        else:
+            res.ids = ids.to(out_dev, copy=True)
+            res.distances = dist.to(out_dev, copy=True)
         tinfo.n_queries = int(x.shape[0])
         tinfo.parent_info = parent_info
         tinfo.total_time_ns = int((time.perf_counter() - t0) * 1e9)

@@ -432,6 +432,7 @@ class PartitionStore:
         st.num_rows = int(self.vectors.shape[0])
         st.flat_row0 = int(self.list_row0[0]) if nslots == 1 else 0
         st.flat_rows = int(self.list_size[0]) if nslots == 1 else 0
+        st.max_segment_rows = int(seg_rows.max()) if S else 0
         st._keepalive = t  # the struct holds raw pointers into these tensors
         self._cache[key] = (st, t["id_to_slot"])
         return self._cache[key]

@@ -44,7 +44,7 @@ def test_store_struct_layout_matches_header():
     body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
     fields = re.findall(r"(\w+)\s*;", body)
     assert fields == [f[0] for f in QkStore._fields_]
-    assert ctypes.sizeof(QkStore) == 112
+    assert ctypes.sizeof(QkStore) == 120
 
 
 def test_no_gpu_means_loud_failure():
