@@ -188,8 +188,8 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) scan_mma_kernel(const ScanArgs
     const int nbox = (dp + MMA_BOX - 1) / MMA_BOX;  // 1..4
     if (tid == 0) {
         for (int s = 0; s < NS; ++s) { mbar_init(a_full + s, 1); mbar_init(a_empty + s, 5); mbar_init(alo_full + s, 4); }
-        for (int s = 0; s < NB; ++s) { mbar_init(b_ready + s, 4); mbar_init(b_empty + s, 1); }
-        for (int s = 0; s < ND; ++s) { mbar_init(i_full + s, 1); mbar_init(i_empty + s, 13); }
+        for (int s = 0; s < NB; ++s) { mbar_init(b_ready + s, 4); mbar_init(b_empty + s, 2); }
+        for (int s = 0; s < ND; ++s) { mbar_init(i_full + s, 1); mbar_init(i_empty + s, 14); }
         for (int s = 0; s < MMA_NACC; ++s) { mbar_init(d_full + s, 1); mbar_init(d_empty + s, 4); }
         mbar_fence_init();
         *ep_done = 0;
@@ -281,8 +281,12 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) scan_mma_kernel(const ScanArgs
             i4 = i5;
             live = next_live;
         }
-    } else if (warp == 1) {
-        // ===================================================================== MMA issuer
+    } else if (warp == 1 || warp == 15) {
+        // ===================================================================== MMA issuers
+        // Issuer mi takes the tiles with (T & 1) == mi. tcgen05.commit only tracks the issuing thread's own MMAs: the
+        // row boxes and the accumulator of a tile are released by the issuer that consumed them, the B slot of an item
+        // by both (count 2).
+        const int mi = warp == 1 ? 0 : 1;
         constexpr uint32_t IDESC64 = umma_idesc_tf32(MMA_TM, 2 * MMA_NQ);  // a_hi . [b_hi | b_lo]
         constexpr uint32_t IDESC32 = umma_idesc_tf32(MMA_TM, MMA_NQ);      // a_lo . b_hi
         uint32_t T = 0, U = 0;
@@ -298,6 +302,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) scan_mma_kernel(const ScanArgs
             const int ntiles = (d.nrows + TM - 1) / TM;
             for (int tile = 0; tile < ntiles; ++tile, ++T) {
                 const int db = T % MMA_NACC;
+                if ((int)(T & 1u) != mi) { U += nbox; continue; }
                 mbar_wait(d_empty + db, ((T / MMA_NACC) & 1u) ^ 1u);
                 const uint32_t tmem_d = tmem + MMA_TMEM_D + db * (2 * MMA_NQ);
                 for (int b = 0; b < nbox; ++b, ++U) {
@@ -517,14 +522,13 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) scan_mma_kernel(const ScanArgs
         if (lane == 0) atomicAdd(const_cast<uint32_t*>(ep_done), 1u);
     } else {
         // ===================================================================== threshold refresh (off the critical path)
-        const int rw = warp - 14;  // serves the mailboxes of epilogue warps 4*rw .. 4*rw+3
-        uint32_t* hist = hists + rw * 256;
-        uint32_t* keys = rscratch + rw * MMA_REFRESH_CAP;
+        uint32_t* hist = hists;
+        uint32_t* keys = rscratch;
         const int qcap = a.qcap;
         for (;;) {
             bool did = false;
-            for (int i = 0; i < 4; ++i) {
-                volatile unsigned long long* mb = mbox + rw * 4 + i;
+            for (int i = 0; i < 8; ++i) {
+                volatile unsigned long long* mb = mbox + i;
                 const unsigned long long req = *mb;
                 if (req == 0ull) continue;  // warp-uniform: every lane read the same word
                 did = true;
