@@ -63,7 +63,8 @@ class _SearchPlan:
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
             self.graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph):
+            # thread_local: other threads (e.g. the NCCL watchdog of a multi-rank job) may touch the CUDA runtime
+            with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
                 self.ids, self.dist, self.p_ids = index._search_core(self.xq, sp)
         finally:
             _capturing = False
