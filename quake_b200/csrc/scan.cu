@@ -31,6 +31,8 @@
 
 namespace qk {
 
+static cudaStream_t g_side_stream = nullptr;  // fork/join partner of the caller's stream (threshold seeds)
+static cudaEvent_t g_ev_fork = nullptr, g_ev_join = nullptr;
 static int g_scan_variant = -1;  // 0: tensor-core filter for d <= 128 (default), 1: FP32-pipe filter everywhere
 static int g_force_rescan = 0;
 static void read_scan_env() {
@@ -1198,10 +1200,24 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_refine_kernel(const Merge
                 compacted = true;
             }
         }
-        if (!compacted) {
-            const int np = next_pow2(ns > 1 ? ns : 1);
-            for (int i = ns + tid; i < np; i += blockDim.x) sbuf[i] = COMP_MAX;
-            block_bitonic_sort(sbuf, np, [](uint64_t x, uint64_t y) { return x < y; });
+        uint32_t a_key = 0;  // filter key of the kc-th best candidate (only meaningful when ns >= kc)
+        if (!compacted && ns <= a.kc) {
+            // every survivor is refined anyway (dense mode hands over exactly kc + ties): no order needed among
+            // them, only the largest filter key for the proof
+            if (tid == 0) s_T = 0;
+            __syncthreads();
+            uint32_t mx = 0;
+            for (int i = tid; i < ns; i += blockDim.x) mx = max(mx, (uint32_t)(sbuf[i] >> 32));
+            if (mx) atomicMax(&s_T, mx);
+            __syncthreads();
+            a_key = s_T;
+        } else {
+            if (!compacted) {
+                const int np = next_pow2(ns > 1 ? ns : 1);
+                for (int i = ns + tid; i < np; i += blockDim.x) sbuf[i] = COMP_MAX;
+                block_bitonic_sort(sbuf, np, [](uint64_t x, uint64_t y) { return x < y; });
+            }
+            a_key = (uint32_t)(sbuf[a.kc - 1] >> 32);
         }
         nc = ns < a.kc ? ns : a.kc;
         // ---- exact refine in the reference's summation order
@@ -1235,7 +1251,7 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_refine_kernel(const Merge
         if (ns >= a.kc && nc >= 1) {  // ns < kc: every probed row was a survivor, nothing was rejected
             if (tid == 0) {
                 const int kk = a.k < nc ? a.k : nc;
-                const float a_score = key2f((uint32_t)(sbuf[a.kc - 1] >> 32));  // filter score of the kc-th candidate
+                const float a_score = key2f(a_key);  // filter score of the kc-th candidate
                 const float rk = key2f((uint32_t)(rkey[kk - 1] >> 32));         // exact k-th (l2: distance, ip: -ip)
                 const double qn = s_qn, qnorm = sqrt(qn), U = (double)a.max_row_norm;
                 const double eps = 5.960464477539063e-08;  // 2^-24
@@ -1624,6 +1640,21 @@ int qk::scan_partitions_impl(const qk_store_t* st, const float* queries, int64_t
                                                                               seg_count, gthr, false);
     }
     QK_CUDA(cudaGetLastError());
+    // The seeds only need the pair table; the grouping kernels (prefix, scatter) only the histogram: run them side by
+    // side (fork / join through a second stream -- inside a CUDA-graph capture this becomes two parallel branches).
+    bool forked = false;
+    cudaStream_t seed_stream = stream;
+    if (p.sample) {
+        if (!g_side_stream) {
+            QK_CUDA(cudaStreamCreateWithFlags(&g_side_stream, cudaStreamNonBlocking));
+            QK_CUDA(cudaEventCreateWithFlags(&g_ev_fork, cudaEventDisableTiming));
+            QK_CUDA(cudaEventCreateWithFlags(&g_ev_join, cudaEventDisableTiming));
+        }
+        QK_CUDA(cudaEventRecord(g_ev_fork, stream));
+        QK_CUDA(cudaStreamWaitEvent(g_side_stream, g_ev_fork, 0));
+        seed_stream = g_side_stream;
+        forked = true;
+    }
     if (p.sample) {
         const int sample = p.sample;
         const bool mma_path = (g_scan_variant == 0) && p.dp <= 128;
@@ -1636,13 +1667,13 @@ int qk::scan_partitions_impl(const qk_store_t* st, const float* queries, int64_t
                 const int have = (int)(st->flat_rows < sample ? st->flat_rows : sample);
                 dim3 grid((unsigned)((Q + 63) / 64), (unsigned)((have + 63) / 64));
                 if (ip)
-                    seed_scores_flat_kernel<true><<<grid, 256, 0, stream>>>(st->vectors, st->pitch, st->row_norms, st->d, queries,
+                    seed_scores_flat_kernel<true><<<grid, 256, 0, seed_stream>>>(st->vectors, st->pitch, st->row_norms, st->d, queries,
                                                                             q_pitch, Q, st->flat_row0, (int)st->flat_rows, sample, skeys);
                 else
-                    seed_scores_flat_kernel<false><<<grid, 256, 0, stream>>>(st->vectors, st->pitch, st->row_norms, st->d, queries,
+                    seed_scores_flat_kernel<false><<<grid, 256, 0, seed_stream>>>(st->vectors, st->pitch, st->row_norms, st->d, queries,
                                                                              q_pitch, Q, st->flat_row0, (int)st->flat_rows, sample, skeys);
                 QK_CUDA(cudaGetLastError());
-                seed_select_flat_kernel<<<(unsigned)((Q + 7) / 8), 256, 0, stream>>>(skeys, sample, have, queries, q_pitch, st->d, Q,
+                seed_select_flat_kernel<<<(unsigned)((Q + 7) / 8), 256, 0, seed_stream>>>(skeys, sample, have, queries, q_pitch, st->d, Q,
                                                                                      p.kc, st->max_row_norm, rel_margin, gthr);
                 QK_CUDA(cudaGetLastError());
             }
@@ -1650,18 +1681,19 @@ int qk::scan_partitions_impl(const qk_store_t* st, const float* queries, int64_t
             const size_t ssm = (size_t)2 * (p.dp + sample) * sizeof(float);
             const unsigned grid = (unsigned)((Q + 1) / 2);
             if (ip)
-                seed_thresholds_kernel<true><<<grid, 256, ssm, stream>>>(st->vectors, st->pitch, st->row_norms, st->d, p.dp,
+                seed_thresholds_kernel<true><<<grid, 256, ssm, seed_stream>>>(st->vectors, st->pitch, st->row_norms, st->d, p.dp,
                                                                          queries, q_pitch, Q, pair_seg, p.P, st->seg_row0,
                                                                          st->seg_rows, p.kc, sample, st->max_row_norm,
                                                                          rel_margin, gthr);
             else
-                seed_thresholds_kernel<false><<<grid, 256, ssm, stream>>>(st->vectors, st->pitch, st->row_norms, st->d, p.dp,
+                seed_thresholds_kernel<false><<<grid, 256, ssm, seed_stream>>>(st->vectors, st->pitch, st->row_norms, st->d, p.dp,
                                                                           queries, q_pitch, Q, pair_seg, p.P, st->seg_row0,
                                                                           st->seg_rows, p.kc, sample, st->max_row_norm,
                                                                           rel_margin, gthr);
             QK_CUDA(cudaGetLastError());
         }
     }
+    if (forked) QK_CUDA(cudaEventRecord(g_ev_join, g_side_stream));
     prefix_segments_kernel<<<1, 1024, 0, stream>>>(seg_count, S, p.gq, seg_start, item_start, ctrl);
     QK_CUDA(cudaGetLastError());
     {
@@ -1685,6 +1717,7 @@ int qk::scan_partitions_impl(const qk_store_t* st, const float* queries, int64_t
         sa.dense_row0 = st->flat_row0;
         sa.dense_rows = (int)st->flat_rows;
     }
+    if (forked) QK_CUDA(cudaStreamWaitEvent(stream, g_ev_join, 0));
     CUtensorMap vmap;
     // d <= 128: tensor-core filter (tcgen05, 3xTF32 split); otherwise the FP32-pipe kernel. QK_SCAN_PATH=ffma
     // forces the latter (tests cross-check the two).
