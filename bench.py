@@ -48,12 +48,13 @@ def parse_args():
     ap.add_argument("--nprobe", type=int, default=WORKLOAD["nprobe"])
     ap.add_argument("--n", type=int, default=WORKLOAD["N"], help="override N (debug only; the line says so)")
     ap.add_argument("--nlist", type=int, default=WORKLOAD["nlist"])
+    ap.add_argument("--q", type=int, default=WORKLOAD["Q"], help="override the batch size (debug only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
 
 def workload_name(W):
-    tag = "C2" if (W["N"], W["nlist"]) == (1_000_000, 4096) else "reduced (debug)"
+    tag = "C2" if (W["N"], W["nlist"], W["Q"], W["nprobe"]) == (1_000_000, 4096, 1024, 64) else "modified (debug)"
     return (f"{tag}: {W['N']} x {W['d']} f32 randn, nlist={W['nlist']}, Q={W['Q']}, k={W['k']}, {W['metric']}, "
             f"nprobe={W['nprobe']}")
 
@@ -249,7 +250,7 @@ def run_b200(args):
     import ctypes as C
     lib = _lib.load()
 
-    W = dict(WORKLOAD, N=args.n, nlist=args.nlist, nprobe=args.nprobe)
+    W = dict(WORKLOAD, N=args.n, nlist=args.nlist, nprobe=args.nprobe, Q=args.q)
     W["name"] = workload_name(W)
     x, xq_h = make_data(W["N"], W["d"], W["Q"], rank)
     ids = torch.arange(W["N"], dtype=torch.int64)
