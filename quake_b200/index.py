@@ -43,6 +43,7 @@ LAST_SCAN_STATS = None  # set QK_SCAN_STATS=1: int32[4] device tensor of the las
 # False) keeps every call eager -- bench.py does that while it times individual kernels with events.
 GRAPHS_ENABLED = os.environ.get("QK_GRAPH", "1") != "0"
 _MAX_PLANS = 8
+_GRAPH_MAX_Q = 16384  # larger batches run eagerly: their launches are long, and a plan pins its whole workspace
 _capturing = False
 
 
@@ -194,7 +195,8 @@ class QuakeIndex:
             raise RuntimeError(f"[QuakeIndex::search] queries must be [Q, {self.store.d}]")
         out_dev = x.device
         use_aps = self.parent is not None and float(search_params.recall_target) > 0.0 and not bool(search_params.batched_scan)
-        if GRAPHS_ENABLED and not use_aps and self.current_level == 0 and x.dtype == torch.float32:
+        if (GRAPHS_ENABLED and not use_aps and self.current_level == 0 and x.dtype == torch.float32
+                and int(x.shape[0]) <= _GRAPH_MAX_Q):
             # straight into the plan's static input buffer (one H2D copy when x is a host tensor)
             xq = self._plan(int(x.shape[0]), search_params).xq
             xq[:, : self.store.d].copy_(x, non_blocking=True)
@@ -302,7 +304,7 @@ class QuakeIndex:
                 tinfo.partitions_scanned = int(scanned.sum().item())
         else:
             t1 = time.perf_counter()
-            if GRAPHS_ENABLED and not _capturing and self.current_level == 0:
+            if GRAPHS_ENABLED and not _capturing and self.current_level == 0 and Q <= _GRAPH_MAX_Q:
                 ids, dist, p_ids = self._plan(Q, sp).run(xq)
                 if p_ids is not None:
                     p_ids = p_ids.clone()  # the hit window below outlives the plan's static buffer
