@@ -12,6 +12,15 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (B200, sm_100a); run with -m gpu")
+    # the native library is built in-tree and git-ignored: on a fresh checkout build it (nvcc cross-compiles
+    # without a GPU) so that the ABI tests have something to load
+    lib = os.path.join(ROOT, "quake_b200", "lib", "libquake_b200.so")
+    if not os.path.exists(lib):
+        try:
+            import __graft_entry__ as entry
+            entry.build_cuda()
+        except Exception as e:  # pragma: no cover -- the ABI tests will then say what is missing
+            print(f"[conftest] could not build {lib}: {e!r}")
 
 
 def pytest_collection_modifyitems(config, items):
