@@ -69,6 +69,12 @@ class _SearchPlan:
                 self.ids, self.dist, self.p_ids = index._search_core(self.xq, sp)
         finally:
             _capturing = False
+        # everything outside the graph's private pool whose address the graph baked in lives as long as the plan: the
+        # flat probe tables (this index's or its parent's) and the stores' segment tables / arenas of this version
+        self.keep = [index._flat_probe(Q) if index.parent is None else None,
+                     index.parent._flat_probe(Q) if index.parent is not None and index.parent.parent is None else None,
+                     index.store.tables_snapshot(),
+                     index.parent.store.tables_snapshot() if index.parent is not None else None]
 
     def run(self, xq: torch.Tensor):
         if xq.data_ptr() != self.xq.data_ptr():
@@ -147,6 +153,7 @@ class QuakeIndex:
             xd = xd.clone()  # the reference deep-copies x (quake_index.cpp:33)
         idd = ids.to(device=dev, dtype=torch.int64).contiguous()
         self.store = PartitionStore(d, dev)
+        self._reset_caches()
         nlist = int(build_params.nlist)
         if nlist > 1:
             s1 = time.perf_counter()
@@ -198,8 +205,12 @@ class QuakeIndex:
         if (GRAPHS_ENABLED and not use_aps and self.current_level == 0 and x.dtype == torch.float32
                 and int(x.shape[0]) <= _GRAPH_MAX_Q):
             # straight into the plan's static input buffer (one H2D copy when x is a host tensor)
-            xq = self._plan(int(x.shape[0]), search_params).xq
-            xq[:, : self.store.d].copy_(x, non_blocking=True)
+            plan = self._plan(int(x.shape[0]), search_params)
+            if plan is not None:
+                xq = plan.xq
+                xq[:, : self.store.d].copy_(x, non_blocking=True)
+            else:
+                xq = clustering.pad_rows(x, self.store.device)
         else:
             xq = clustering.pad_rows(x, self.store.device)
         ids, dist, parent_info = self._search_device(xq, search_params, tinfo)
@@ -226,15 +237,28 @@ class QuakeIndex:
         return res
 
     def _flat_probe(self, Q: int) -> torch.Tensor:
-        """[Q, nlist] probe table of a flat index: every query scans every partition (query_coordinator.cpp:624-626)."""
-        key = (Q, self.store.version)
-        if getattr(self, "_flat_probe_cache", (None, None))[0] != key:
-            self.store.tables()
-            key = (Q, self.store.version)
+        """[Q, nlist] probe table of a flat index: every query scans every partition (query_coordinator.cpp:624-626).
+        One tensor per batch size for the current store version; captured plans keep their own reference."""
+        self.store.tables()
+        ver = (self.store.uid, self.store.version)
+        cache = self.__dict__.setdefault("_flat_probe_cache", {})
+        if cache.get("version") != ver:
+            cache.clear()
+            cache["version"] = ver
+        if Q not in cache:
+            if len(cache) > 16:
+                for kk in [kk for kk in cache if kk != "version"]:
+                    del cache[kk]
             slots = torch.tensor([self.store.pid_slot[int(p)] for p in self.store.partition_ids()], dtype=torch.int32,
                                  device=self.store.device)
-            self._flat_probe_cache = (key, slots[None, :].expand(Q, -1).contiguous())
-        return self._flat_probe_cache[1]
+            cache[Q] = slots[None, :].expand(Q, -1).contiguous()
+        return cache[Q]
+
+    def _reset_caches(self) -> None:
+        """build() / load() install a new store: captured plans, probe tables and staging buffers of the old one go."""
+        self.__dict__.pop("_plans", None)
+        self.__dict__.pop("_flat_probe_cache", None)
+        self.__dict__.pop("_host_stage", None)
 
     def _search_core(self, xq: torch.Tensor, sp: SearchParams):
         """Fixed-nprobe search, launches only (capturable in a CUDA graph): coarse scan -> slot map -> partition scan.
@@ -257,18 +281,27 @@ class QuakeIndex:
     def _plan(self, Q: int, sp: SearchParams) -> "_SearchPlan":
         plans = self.__dict__.setdefault("_plans", {})
         self.store.tables()  # settles store.version
-        pv = self.parent.store.version if self.parent is not None and self.parent.store is not None else -1
+        pv = (-1, -1)
         if self.parent is not None:
             self.parent.store.tables()
-            pv = self.parent.store.version
-        key = (Q, int(sp.k), int(sp.nprobe), self.metric, self.store.version, pv)
+            pv = (self.parent.store.uid, self.parent.store.version)
+        # store.uid is process-unique: a rebuilt / reloaded index never matches a plan of its previous store
+        key = (Q, int(sp.k), int(sp.nprobe), self.metric, self.store.uid, self.store.version, pv)
         plan = plans.get(key)
         if plan is None:
             for old_key in [kk for kk in plans if kk[4:] != key[4:]]:  # the index changed: drop stale plans
                 del plans[old_key]
             while len(plans) >= _MAX_PLANS:
-                del plans[next(iter(plans))]
-            plan = plans[key] = _SearchPlan(self, Q, sp)
+                del plans[next(iter(plans))]  # least recently used first (hits are re-inserted below)
+            try:
+                plan = _SearchPlan(self, Q, sp)
+            except RuntimeError:
+                # capture failed (e.g. out of memory for the plan's private pool): this batch runs eagerly
+                torch.cuda.synchronize()
+                return None
+            plans[key] = plan
+        else:
+            plans[key] = plans.pop(key)  # LRU order
         return plan
 
     def _search_device(self, xq: torch.Tensor, sp: SearchParams, tinfo: SearchTimingInfo | None = None,
@@ -304,8 +337,11 @@ class QuakeIndex:
                 tinfo.partitions_scanned = int(scanned.sum().item())
         else:
             t1 = time.perf_counter()
+            plan = None
             if GRAPHS_ENABLED and not _capturing and self.current_level == 0 and Q <= _GRAPH_MAX_Q:
-                ids, dist, p_ids = self._plan(Q, sp).run(xq)
+                plan = self._plan(Q, sp)
+            if plan is not None:
+                ids, dist, p_ids = plan.run(xq)
                 if p_ids is not None:
                     p_ids = p_ids.clone()  # the hit window below outlives the plan's static buffer
             else:
@@ -524,6 +560,7 @@ class QuakeIndex:
                 elif key == "level":
                     self.current_level = int(val)
         self._load_partitions(os.path.join(dir_path, "partitions"), dev)
+        self._reset_caches()
         pdir = os.path.join(dir_path, "parent")
         if os.path.isdir(pdir):
             self.parent = QuakeIndex()

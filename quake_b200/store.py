@@ -31,8 +31,13 @@ def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+_NEXT_UID = [0]
+
+
 class PartitionStore:
     def __init__(self, d: int, device: torch.device):
+        _NEXT_UID[0] += 1
+        self.uid = _NEXT_UID[0]  # process-unique: (uid, version) identifies one state of one store
         self.d = int(d)
         self.pitch = _round_up(self.d, 4)
         self.device = device
@@ -256,7 +261,7 @@ class PartitionStore:
         rows = rows[rows >= 0]
         if rows.numel() == 0:
             return 0
-        rows_h = np.sort(rows.cpu().numpy())
+        rows_h = np.unique(rows.cpu().numpy())  # sorted; the reference collects the ids in a std::set (partition_manager.cpp:306-310)
         order = np.argsort(self.list_row0, kind="stable")
         starts = self.list_row0[order]
         li = order[np.searchsorted(starts, rows_h, side="right") - 1]
@@ -383,6 +388,10 @@ class PartitionStore:
         while seg_len > 256 and chunks * ((longest + seg_len - 1) // seg_len) < 222:  # ~1.5 items per SM (measured best)
             seg_len //= 2
         return seg_len
+
+    def tables_snapshot(self):
+        """References to everything a kernel launch of the current version reads: keeps it alive for a captured graph."""
+        return (self.vectors, self.ids, self.norms, dict(self._cache))
 
     def tables(self, seg_len: int = _MAX_SEGMENT_ROWS):
         """(QkStore struct, id_to_slot tensor) for scan segments of `seg_len` rows; rebuilt lazily after any

@@ -172,3 +172,24 @@ def test_against_live_reference(quake_ref):
         a, b = quake_ref.shim.scan_list(x[0], y, ids, 7, m)
         oi, od = orc.scan_list(x[0], y, ids, 7, m)
         assert a.tolist() == oi.tolist() and np.array_equal(b.numpy(), od)
+
+
+def test_avx512_golden_set_has_the_same_ids():
+    """tests/golden/search_avx512.npz comes from an AVX-512 build of the unmodified reference (the ISA its own
+    -march=native build uses on the survey host), search.npz from the AVX2 build the refine kernel reproduces bit for
+    bit: identical ids, distances equal to ~1e-7 relative (16-lane instead of 8-lane summation)."""
+    A = np.load(os.path.join(GOLDEN, "search.npz"))
+    B = np.load(os.path.join(GOLDEN, "search_avx512.npz"))
+    checked = 0
+    for key in B.files:
+        if key.startswith("d128") or key.endswith("_cfg") or key.endswith("_q"):
+            continue
+        a, b = A[key], B[key]
+        if key.endswith("_ids"):
+            assert np.array_equal(a, b), key
+        else:
+            fin = np.isfinite(a)
+            assert np.array_equal(a[~fin], b[~fin])
+            assert np.allclose(a[fin], b[fin], rtol=1e-6, atol=0), key
+        checked += 1
+    assert checked == 20
