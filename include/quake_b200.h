@@ -70,6 +70,9 @@ typedef struct qk_store {
 /* ---- library info ------------------------------------------------------------------------- */
 const char* qk_version(void);
 const char* qk_last_error(void);
+/* Kernels launched by this library since it was loaded (host-side launches; a CUDA-graph replay launches the kernels
+ * that were counted while it was captured). Measurement aid: bench.py's gpu_launches. */
+long long qk_launch_count(void);
 /* Host call. Fails unless the current device is compute capability 10.x. */
 int qk_device_check(int* sm_count, int* cc_major, int* cc_minor);
 
@@ -81,7 +84,10 @@ int qk_device_check(int* sm_count, int* cc_major, int* cc_minor);
  * [Q x k], best first, L2 distances are Euclidean (sqrt) (list_scanning.h:260), missing slots are
  * id -1 and +inf (l2) / -inf (ip) (query_coordinator.cpp:589-601).
  *
- * probe_lists: [Q x nprobe] int32 list slots in probe order, -1 = skip (query_coordinator.cpp:540).
+ * probe_lists: [Q x nprobe] int32 list slots in probe order, -1 = skip (query_coordinator.cpp:540). May be NULL for a
+ *              store with ONE list and nprobe = 1 ("flat mode": a flat index, the centroid list of the coarse scan --
+ *              every query scans the whole list, query_coordinator.cpp:624-626); the work items are then generated
+ *              inside the scan kernel and no grouping kernels run.
  * out_rows   : optional [Q x k] int64 arena row of each result (-1 where padded).
  * stats      : optional device int32[4]: {queries that took the exact re-scan path, largest number of
  *              candidates any query appended, total candidates appended (low, high 32 bits)}.
@@ -94,6 +100,22 @@ int qk_scan_partitions(const qk_store_t* store,
                        int64_t* out_ids, float* out_distances, int64_t* out_rows,
                        void* workspace, size_t workspace_bytes,
                        int32_t* stats, void* stream);
+
+/* Two-level fixed-nprobe search in one call. Replaces QueryCoordinator::search for recall_target <= 0
+ * (src/cpp/src/query_coordinator.cpp:612-657): coarse scan of the flat parent (top-min(nprobe, nlist) centroids per
+ * query, :628-645) -> partition ids -> list slots (id_to_slot, the partitions_.at(pid) lookup) -> scan of the probed
+ * lists -> top-k. `parent` must be a single-list store whose ids are the partition ids. shard_world > 1 scans only the
+ * partitions with id % shard_world == shard_rank (lists sharded over GPUs, partition_manager.cpp:599-602): the result
+ * is then this shard's PARTIAL top-k. out_probe_ids: optional [Q x min(nprobe, nlist)] int64, the probed partition
+ * ids in rank order (the hit window of the maintenance policy reads them). */
+size_t qk_search_ivf_workspace_bytes(const qk_store_t* parent, const qk_store_t* store, int64_t num_queries,
+                                     int nprobe, int k);
+int qk_search_ivf(const qk_store_t* parent, const qk_store_t* store,
+                  const int32_t* id_to_slot, int64_t table_size,
+                  const float* queries, int64_t num_queries, int64_t query_pitch,
+                  int nprobe, int metric, int k, int shard_rank, int shard_world,
+                  int64_t* out_ids, float* out_distances, int64_t* out_probe_ids,
+                  void* workspace, size_t workspace_bytes, int32_t* stats, void* stream);
 
 /* Measurement aid (bench.py): while profiling is on, every qk_scan_partitions call records a CUDA-event
  * pair on its stream right around the filter ("scan") kernel -- the dominant kernel of the path. Read the
@@ -125,6 +147,25 @@ int qk_row_sqnorms(const float* rows, int64_t n, int64_t pitch, int d, float* ou
 int qk_merge_topk(const float* part_distances, const int64_t* part_ids, int num_parts,
                   int64_t num_queries, int k, int metric,
                   int64_t* out_ids, float* out_distances, void* stream);
+
+/* ---- shard exchange over NVLink peer memory (lists sharded over the GPUs of one box) ------------------
+ * Replaces, across GPUs, the merge of per-core partial results into the global TopkBuffer
+ * (src/cpp/src/query_coordinator.cpp:167-173): every rank pushes its [Q x k] partial top-k straight into every
+ * peer's buffer (remote stores + one flag per CTA), waits for the peers' pushes and merges -- ONE kernel per rank, no
+ * NCCL call on the query path; the result is identical on every rank and bit-identical to the unsharded search.
+ * A peer buffer is cudaMalloc'ed by qk_peer_alloc (HOST call; also returns its 64-byte CUDA IPC handle, which the
+ * caller distributes to the other ranks, e.g. with one all-gather at set-up time) and opened on the other ranks with
+ * qk_peer_open. peer_buffers: HOST array of `world` device pointers, entry `rank` being the local buffer; all of
+ * qk_peer_buffer_bytes(Q, k, world) bytes. Collective: every rank must call it the same number of times with the
+ * same Q, k, world. The exchange counter lives in the buffer, so the call can be captured in a CUDA graph. */
+size_t qk_peer_buffer_bytes(int64_t num_queries, int k, int world);
+int qk_peer_alloc(size_t bytes, void** dev_ptr, void* ipc_handle_64);
+int qk_peer_open(const void* ipc_handle_64, void** dev_ptr);
+int qk_peer_close(void* dev_ptr);
+int qk_peer_free(void* dev_ptr);
+int qk_exchange_merge_topk(const int64_t* ids, const float* distances, int64_t num_queries, int k, int metric,
+                           int rank, int world, void* const* peer_buffers,
+                           int64_t* out_ids, float* out_distances, void* stream);
 
 /* ---- Adaptive Partition Scanning (recall_target > 0) ----------------------------------------------
  * Replaces the APS part of QueryCoordinator::serial_scan (src/cpp/src/query_coordinator.cpp:521-579) and the
@@ -160,7 +201,7 @@ int qk_aps_advance(const int32_t* active, int64_t num_active, int R, int p0, int
  * kmeans_refine_partitions (clustering.cpp:152-159): nearest centroid per point, ties to the lowest
  * centroid index. out_distances (optional): Euclidean distance / inner product to the chosen centroid.
  * Runs on the partition-scan kernel (centroids as a flat store, points as queries, k = 1), so the
- * argmin is decided in the reference's exact per-pair arithmetic. Host-synchronises once. */
+ * argmin is decided in the reference's exact per-pair arithmetic. Asynchronous on `stream` (no host synchronisation). */
 size_t qk_kmeans_assign_workspace_bytes(int64_t n, int64_t num_centroids, int d);
 int qk_kmeans_assign(const float* points, int64_t n, int64_t point_pitch, int d,
                      const float* centroids, int64_t num_centroids, int64_t centroid_pitch,

@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libquake_b200.so")
+LIB_PATH = os.environ.get("QK_LIB_PATH") or os.path.join(_HERE, "lib", "libquake_b200.so")  # QK_LIB_PATH: profiling builds
 
 QK_METRIC_INNER_PRODUCT = 0
 QK_METRIC_L2 = 1
@@ -52,11 +52,18 @@ class QkStore(C.Structure):
 PROTOTYPES = {
     "qk_version": (C.c_char_p, []),
     "qk_last_error": (C.c_char_p, []),
+    "qk_launch_count": (C.c_longlong, []),
     "qk_device_check": (C.c_int, [c_i32p, c_i32p, c_i32p]),
     "qk_scan_workspace_bytes": (C.c_size_t, [C.POINTER(QkStore), C.c_int64, C.c_int, C.c_int]),
     "qk_scan_partitions": (
         C.c_int,
         [C.POINTER(QkStore), vp, C.c_int64, C.c_int64, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, C.c_size_t, vp, vp],
+    ),
+    "qk_search_ivf_workspace_bytes": (C.c_size_t, [C.POINTER(QkStore), C.POINTER(QkStore), C.c_int64, C.c_int, C.c_int]),
+    "qk_search_ivf": (
+        C.c_int,
+        [C.POINTER(QkStore), C.POINTER(QkStore), vp, C.c_int64, vp, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int,
+         C.c_int, vp, vp, vp, vp, C.c_size_t, vp, vp],
     ),
     "qk_profile_begin": (C.c_int, [C.c_int]),
     "qk_profile_count": (C.c_int, []),
@@ -66,6 +73,12 @@ PROTOTYPES = {
     "qk_max_row_norm": (C.c_int, [vp, C.c_int64, C.c_int64, C.c_int, vp, vp]),
     "qk_row_sqnorms": (C.c_int, [vp, C.c_int64, C.c_int64, C.c_int, vp, vp]),
     "qk_merge_topk": (C.c_int, [vp, vp, C.c_int, C.c_int64, C.c_int, C.c_int, vp, vp, vp]),
+    "qk_peer_buffer_bytes": (C.c_size_t, [C.c_int64, C.c_int, C.c_int]),
+    "qk_peer_alloc": (C.c_int, [C.c_size_t, C.POINTER(vp), vp]),
+    "qk_peer_open": (C.c_int, [vp, C.POINTER(vp)]),
+    "qk_peer_close": (C.c_int, [vp]),
+    "qk_peer_free": (C.c_int, [vp]),
+    "qk_exchange_merge_topk": (C.c_int, [vp, vp, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(vp), vp, vp, vp]),
     "qk_host_beta_table": (C.c_int, [C.c_int, C.POINTER(C.c_double)]),
     "qk_aps_boundary_distances": (C.c_int, [vp, C.c_int64, C.c_int64, C.c_int, vp, C.c_int64, vp, C.c_int, C.c_int, vp, vp]),
     "qk_aps_advance": (

@@ -3,6 +3,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <atomic>
 
 namespace qk {
 static thread_local char g_err[1024] = "";
@@ -16,20 +17,27 @@ int cuda_fail(cudaError_t e, const char* what) {
     set_error("CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
     return QK_ERR_CUDA;
 }
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+long long launches() { return g_launches.load(std::memory_order_relaxed); }
 int sm_count() {
-    static int n = 0;
-    if (n == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-        if (n <= 0) n = 148;
+    static int n[64] = {0};  // per device ordinal
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) return 148;
+    if (n[dev] == 0) {
+        int v = 0;
+        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+        n[dev] = v > 0 ? v : 148;
     }
-    return n;
+    return n[dev];
 }
 }  // namespace qk
 
 extern "C" const char* qk_version(void) { return "quake_b200 0.1.0 (sm_100a)"; }
 extern "C" const char* qk_last_error(void) { return qk::g_err; }
+namespace qk { long long launches(); }
+extern "C" long long qk_launch_count(void) { return qk::launches(); }
 
 extern "C" int qk_device_check(int* sms, int* cc_major, int* cc_minor) {
     int dev = 0, n = 0;

@@ -338,7 +338,7 @@ extern "C" int qk_aps_boundary_distances(const float* queries, int64_t Q, int64_
     aps_boundary_kernel<<<(unsigned)((pairs + 31) / 32), 256, 0, stream>>>(queries, Q, q_pitch, d, centroids, centroid_pitch,
                                                                           cand_rows, m, metric == QK_METRIC_L2 ? 1 : 0,
                                                                           out_boundary);
-    QK_CUDA(cudaGetLastError());
+    QK_LAUNCHED();
     return QK_OK;
 }
 
@@ -362,6 +362,6 @@ extern "C" int qk_aps_advance(const int32_t* active, int64_t num_active, int R, 
     const size_t smem = (size_t)3 * k * (sizeof(int64_t) + sizeof(uint32_t));
     QK_CUDA(cudaMemsetAsync(still_active, 0, sizeof(int32_t), stream));
     aps_advance_kernel<<<(unsigned)num_active, APS_THREADS, smem, stream>>>(a);
-    QK_CUDA(cudaGetLastError());
+    QK_LAUNCHED();
     return QK_OK;
 }

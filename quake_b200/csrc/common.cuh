@@ -33,12 +33,30 @@ int cuda_fail(cudaError_t e, const char* what);
 
 int sm_count();
 
-// qk_scan_partitions with one more knob: rank_squared != 0 orders l2 results by the squared distance
-// (used by the k-means assign, where faiss's Top1 handler compares squared distances).
+// every kernel launch of the library is followed by QK_LAUNCHED(): launch-error check + the launch counter that
+// qk_launch_count() reports (bench.py's gpu_launches)
+void count_launch();
+#define QK_LAUNCHED()                          \
+    do {                                       \
+        ::qk::count_launch();                  \
+        QK_CUDA(cudaGetLastError());           \
+    } while (0)
+
+// qk_scan_partitions with more knobs (library-internal callers: k-means assign, qk_search_ivf)
+struct ScanExtras {
+    int rank_squared = 0;                    // l2: order results by the squared distance (k-means assign: faiss's Top1
+                                             // handler compares squared distances)
+    const float* max_row_norm_dev = nullptr; // the store's norm bound lives on the device (overrides store->max_row_norm)
+    const int64_t* probe_ids = nullptr;      // probes given as partition ids [Q x nprobe] (probe_lists == NULL) ...
+    const int32_t* id_to_slot = nullptr;     // ... mapped through this dense table
+    int64_t table_size = 0;
+    int shard_rank = 0, shard_world = 1;     // shard_world > 1: scan only the partitions with id % world == rank
+};
+// probe_lists == NULL and probe_ids == NULL: flat mode -- the store has ONE list and every query scans it.
 int scan_partitions_impl(const qk_store_t* st, const float* queries, int64_t Q, int64_t q_pitch,
                          const int32_t* probe_lists, int nprobe, int metric, int k, int64_t* out_ids, float* out_dist,
                          int64_t* out_rows, void* workspace, size_t workspace_bytes, int32_t* stats, void* stream,
-                         int rank_squared);
+                         const ScanExtras& extras);
 
 // ---------------------------------------------------------------------------------------------
 // order-preserving float <-> uint32 keys (ascending float order == ascending unsigned order)

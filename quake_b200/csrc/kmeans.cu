@@ -351,16 +351,16 @@ extern "C" int qk_partition_by_assignment(const int32_t* assign, int64_t n, int6
     QK_CUDA(cudaMemsetAsync(counts, 0, (size_t)K * 8, stream));
     if (n > 0) {
         assign_hist_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(assign, n, K, counts);
-        QK_CUDA(cudaGetLastError());
+        QK_LAUNCHED();
     }
     offsets_kernel<<<1, 1024, 0, stream>>>(counts, K, out_offsets, cursor);
-    QK_CUDA(cudaGetLastError());
+    QK_LAUNCHED();
     if (n > 0) {
         assign_scatter_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(assign, n, K, out_offsets, cursor, out_order);
-        QK_CUDA(cudaGetLastError());
+        QK_LAUNCHED();
         int grid = (int)(K < 65535 ? K : 65535);
         sort_lists_kernel<<<grid, 256, 0, stream>>>(out_offsets, K, out_order, scratch);
-        QK_CUDA(cudaGetLastError());
+        QK_LAUNCHED();
     }
     return QK_OK;
 }
@@ -373,7 +373,7 @@ extern "C" int qk_kmeans_accumulate(const float* points, int64_t point_pitch, in
     int threads = d < 32 ? 32 : (d > 256 ? 256 : (d + 31) / 32 * 32);
     int grid = (int)(K < 65535 ? K : 65535);
     accumulate_kernel<<<grid, threads, 0, stream>>>(points, point_pitch, d, order, offsets, K, out_sums, out_pitch);
-    QK_CUDA(cudaGetLastError());
+    QK_LAUNCHED();
     return QK_OK;
 }
 
@@ -385,7 +385,7 @@ extern "C" int qk_gather_rows(const float* src, int64_t src_pitch, const int64_t
     int64_t threads = n * 32;
     gather_rows_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(src, src_pitch, src_ids, order, n, d, dst,
                                                                                dst_pitch, dst_ids);
-    QK_CUDA(cudaGetLastError());
+    QK_LAUNCHED();
     return QK_OK;
 }
 
@@ -398,7 +398,7 @@ extern "C" int qk_scatter_rows(const float* src, int64_t src_pitch, const int64_
     int64_t threads = n * 32;
     scatter_rows_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(src, src_pitch, src_ids, order, dst_rows, n,
                                                                                 d, dst, dst_pitch, dst_ids);
-    QK_CUDA(cudaGetLastError());
+    QK_LAUNCHED();
     return QK_OK;
 }
 
@@ -408,7 +408,7 @@ extern "C" int qk_normalize_rows(float* rows, int64_t n, int64_t pitch, int d, v
     if (n == 0) return QK_OK;
     int64_t threads = n * 32;
     normalize_rows_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(rows, n, pitch, d);
-    QK_CUDA(cudaGetLastError());
+    QK_LAUNCHED();
     return QK_OK;
 }
 
@@ -418,7 +418,7 @@ extern "C" int qk_row_sqnorms(const float* rows, int64_t n, int64_t pitch, int d
     if (n == 0) return QK_OK;
     int64_t threads = n * 32;
     row_sqnorms_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(rows, n, pitch, d, out);
-    QK_CUDA(cudaGetLastError());
+    QK_LAUNCHED();
     return QK_OK;
 }
 
@@ -428,7 +428,7 @@ extern "C" int qk_max_row_norm(const float* rows, int64_t n, int64_t pitch, int 
     if (n == 0) return QK_OK;
     int64_t threads = n * 32;
     max_row_norm_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(rows, n, pitch, d, out);
-    QK_CUDA(cudaGetLastError());
+    QK_LAUNCHED();
     return QK_OK;
 }
 
@@ -438,7 +438,7 @@ extern "C" int qk_map_ids_to_slots(const int64_t* ids, int64_t n, const int32_t*
     QK_REQUIRE(ids && id_to_slot && out_slots, "bad argument");
     if (n == 0) return QK_OK;
     map_ids_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(ids, n, id_to_slot, table_size, out_slots);
-    QK_CUDA(cudaGetLastError());
+    QK_LAUNCHED();
     return QK_OK;
 }
 
@@ -458,7 +458,7 @@ extern "C" int qk_merge_topk(const float* part_distances, const int64_t* part_id
         QK_CUDA(cudaFuncSetAttribute(merge_topk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         merge_topk_kernel<false><<<(unsigned)Q, 256, smem, stream>>>(part_distances, part_ids, num_parts, Q, k, out_ids, out_distances);
     }
-    QK_CUDA(cudaGetLastError());
+    QK_LAUNCHED();
     return QK_OK;
 }
 
@@ -480,6 +480,8 @@ int assign_layout(int64_t n, int64_t K, int d, AssignLayout* L) {
     st.num_lists = 1;
     st.num_segments = L->nseg;
     st.max_list_segments = L->nseg;
+    st.num_rows = K;   // the plan (dense mode, seed sample) depends on the list's geometry: same fields as the real store
+    st.flat_rows = K;
     L->scan_bytes = qk_scan_workspace_bytes(&st, B, 1, 1);
     if (L->scan_bytes == 0) return QK_ERR_INVALID_ARGUMENT;
     size_t o = 0;
@@ -545,16 +547,13 @@ extern "C" int qk_kmeans_assign(const float* points, int64_t n, int64_t point_pi
         int64_t m = B > L.nseg ? B : L.nseg;
         assign_tables_kernel<<<(unsigned)((m + 255) / 256), 256, 0, stream>>>(K, L.nseg, seg_row0, seg_rows, list_seg0,
                                                                                list_nseg, probe, B, norm);
-        QK_CUDA(cudaGetLastError());
+        QK_LAUNCHED();
     }
     rc = qk_max_row_norm(centroids, K, centroid_pitch, d, norm, stream);
     if (rc) return rc;
     float* cnorms = (float*)(ws + L.off_cnorms);
     rc = qk_row_sqnorms(centroids, K, centroid_pitch, d, cnorms, stream);
     if (rc) return rc;
-    float h_norm = 0.f;  // the bound is a host-side field of the store
-    QK_CUDA(cudaMemcpyAsync(&h_norm, norm, 4, cudaMemcpyDeviceToHost, stream));
-    QK_CUDA(cudaStreamSynchronize(stream));
     qk_store_t st;
     memset(&st, 0, sizeof(st));
     st.vectors = centroids;
@@ -568,7 +567,7 @@ extern "C" int qk_kmeans_assign(const float* points, int64_t n, int64_t point_pi
     st.max_list_segments = L.nseg;
     st.seg_row0 = seg_row0;
     st.seg_rows = seg_rows;
-    st.max_row_norm = h_norm;
+    st.max_row_norm = 0.f;  // the bound stays on the device (ScanExtras::max_row_norm_dev): no host synchronisation
     st.row_norms = cnorms;
     st.num_rows = K;
     st.flat_row0 = 0;
@@ -576,12 +575,16 @@ extern "C" int qk_kmeans_assign(const float* points, int64_t n, int64_t point_pi
     st.max_segment_rows = 0;
     for (int64_t b = 0; b < n; b += B) {
         const int64_t cnt = (n - b) < B ? (n - b) : B;
-        rc = scan_partitions_impl(&st, points + b * point_pitch, cnt, point_pitch, probe, 1, metric, 1, ids, dist, rows,
-                                  ws + L.off_scan, L.scan_bytes, nullptr, stream, 1);
+        ScanExtras ex;
+        ex.rank_squared = 1;
+        ex.max_row_norm_dev = norm;
+        // flat mode (no probe table): every point scans the whole centroid list
+        rc = scan_partitions_impl(&st, points + b * point_pitch, cnt, point_pitch, nullptr, 1, metric, 1, ids, dist, rows,
+                                  ws + L.off_scan, L.scan_bytes, nullptr, stream, ex);
         if (rc) return rc;
         assign_finish_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, stream>>>(rows, dist, cnt, out_assign + b,
                                                                                 out_distances ? out_distances + b : nullptr);
-        QK_CUDA(cudaGetLastError());
+        QK_LAUNCHED();
     }
     return QK_OK;
 }

@@ -1,0 +1,684 @@
+// Per-query candidate selection, exact refine, proof and (rare) exact re-scan -- included by scan.cu.
+//
+// Second half of the filter -> refine split: one CTA per query
+//   1. candidates: the survivors the filter kernel appended to the query's buffer (IVF stores), or -- dense mode,
+//      the coarse centroid scan -- the query's row of the [Q x rows] filter-key matrix; a block-wide radix select
+//      keeps the kc best by filter key (plus ties)
+//   2. exact refine of those in the REFERENCE'S summation order (common.cuh: ref_pair_distance_g8), sorted by
+//      (distance, id): TopkBuffer's order (/root/reference/src/cpp/include/list_scanning.h:151-203) with ties
+//      resolved by ascending id
+//   3. proof, from the filter's rounding-error bound, that no rejected row can enter the top-k
+//   4. if the proof fails (ties at the boundary, duplicates, buffer overflow): the same CTA re-scans the query's
+//      probed rows exhaustively in exact arithmetic (the reference's own loop, list_scanning.h:241-311)
+// Steps 1-4 used to be four launches (dense_select, merge_refine, exact_rescan + the flags hand-off); they are one.
+#pragma once
+
+namespace qk {
+
+static constexpr int MERGE_THREADS = 256;
+static constexpr int MERGE_SORT_CAP = 4096;   // survivors gathered per query before the select (more => exact re-scan)
+static constexpr int MERGE_RANK_SORT_MAX = 256;  // candidate counts up to this are ordered by a one-pass rank sort
+
+// ------------------------------------------------------------------------------------------------
+// block-wide bitonic sort of n (power of two) uint64 keys in shared memory (large k only)
+// ------------------------------------------------------------------------------------------------
+template <typename Less>
+__device__ void block_bitonic_sort(uint64_t* s, int n, Less less) {
+    for (int size = 2; size <= n; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            __syncthreads();
+            for (int i = threadIdx.x; i < (n >> 1); i += blockDim.x) {
+                int lo = 2 * i - (i & (stride - 1));
+                int hi = lo + stride;
+                bool up = ((lo & size) == 0);
+                uint64_t x = s[lo], y = s[hi];
+                bool sw = up ? less(y, x) : less(x, y);
+                if (sw) { s[lo] = y; s[hi] = x; }
+            }
+        }
+    }
+    __syncthreads();
+}
+
+__host__ __device__ __forceinline__ int next_pow2(int x) {
+    int p = 1;
+    while (p < x) p <<= 1;
+    return p;
+}
+
+struct MergeArgs {
+    const float* vecs;
+    int64_t pitch;
+    const int64_t* ids;
+    int d;
+    const int64_t* seg_row0;
+    const int32_t* seg_rows;
+    const float* queries;
+    int64_t q_pitch;
+    const int32_t* pair_seg;   // [Q x P] segments probed by every query (-1 = none); unused when flat_nseg > 0
+    int flat_nseg;             // single-list store scanned without a probe table: every query probes segments 0..flat_nseg-1
+    const uint32_t* gthr;
+    const uint64_t* qbuf;
+    const int32_t* qcount;
+    int qcap;
+    int32_t* flags;
+    int32_t* ctrl;
+    int P, kc, k;
+    float max_row_norm;
+    const float* max_row_norm_dev;  // optional: the bound lives on the device (k-means assign); overrides max_row_norm
+    double filter_gam;  // extra relative error bound of the filter's dot products (tensor-core path), vs |q||v|
+    int64_t* out_ids;
+    float* out_dist;
+    int64_t* out_rows;
+    int force_rescan;
+    int sort_cap;      // survivors the shared-memory gather buffer holds (more => exact re-scan)
+    int rank_squared;  // l2 only: order by the squared distance (k-means assign: faiss Top1 on squared l2)
+    // dense mode (dense_refine_kernel)
+    const uint32_t* dense;  // [Q x dense_rows] filter keys
+    int dense_rows;
+    long long dense_row0;
+};
+
+struct RescanSmem {
+    unsigned hist[256];
+    int scan[256];
+    unsigned prefix, need, less, eq_total;
+    unsigned long long prefix64;
+    int base_lt, base_eq;
+};
+
+// segment j of query q's probe list, or -1
+__device__ __forceinline__ int probed_segment(const MergeArgs& a, int64_t q, int j) {
+    if (a.flat_nseg > 0) return j < a.flat_nseg ? j : -1;
+    return a.pair_seg[q * a.P + j];
+}
+__device__ __forceinline__ int probed_slots(const MergeArgs& a) { return a.flat_nseg > 0 ? a.flat_nseg : a.P; }
+
+// ------------------------------------------------------------------------------------------------
+// The kc entries with the smallest 32-bit keys among entry_at(i) = key << 32 | row, i < n (n >= kc), written to
+// out[0..kc) in no particular order; *t_out = the largest selected key (every entry left out has a key >= it).
+// Exactly kc entries are selected: ties at the boundary are broken by position, which is fine for a FILTER -- the
+// proof downstream only needs "everything rejected has a filter key >= T".
+//
+// Filter keys of one query share their leading bits (scores of similar magnitude), so a plain MSB-first radix pass
+// would pile every key into one or two histogram bins (serialised shared-memory atomics: most of the old 16 us
+// dense_select). Two scans of the data instead of six:
+//   1. histogram of the TOP 8 bits of v = key - kmin over the range [kmin, kmax] the caller measured while it staged
+//      the data (the keys spread over all 256 bins); per-warp histograms, summed; the bin b* holding rank kc
+//   2. one scan: entries below b* go straight to `out`, entries in b* to a small boundary list
+//   3. the boundary list (n / 256-ish entries) is ranked by counting; the `need` smallest complete the selection
+// Returns kc, or -1 when the boundary list overflows SELECT_BOUNDARY_CAP (masses of equal keys: exact re-scan).
+// `whist` = (MERGE_THREADS / 32) x 256 words, `sc` = 4 words, `blist` = SELECT_BOUNDARY_CAP entries.
+// ------------------------------------------------------------------------------------------------
+static constexpr int SELECT_BOUNDARY_CAP = 512;
+template <typename EntryAt>
+__device__ int block_select_smallest(EntryAt entry_at, int n, int kc, uint32_t kmin, uint32_t kmax, uint64_t* out,
+                                     uint32_t* t_out, unsigned* whist, unsigned* sc, uint64_t* blist) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NW = MERGE_THREADS / 32;
+    const uint32_t range = kmax - kmin;
+    const int hi = 32 - __clz(range);  // significant bits of v = key - kmin (0: all keys equal)
+    const int sh = hi > 8 ? hi - 8 : 0;
+    for (int i = tid; i < NW * 256; i += MERGE_THREADS) whist[i] = 0;
+    if (tid == 0) { sc[2] = 0u; sc[3] = 0u; }
+    __syncthreads();
+    for (int i = tid; i < n; i += MERGE_THREADS) {
+        const uint32_t v = (uint32_t)(entry_at(i) >> 32) - kmin;
+        atomicAdd(&whist[warp * 256 + (v >> sh)], 1u);
+    }
+    __syncthreads();
+    if (tid < 256) {
+        unsigned t = 0;
+#pragma unroll
+        for (int ww = 0; ww < NW; ++ww) t += whist[ww * 256 + tid];
+        whist[tid] = t;  // column tid is only touched by this thread
+    }
+    __syncthreads();
+    if (tid < 32) {  // lane l owns bins 8l .. 8l+7
+        uint32_t h[8], sum = 0;
+#pragma unroll
+        for (int b = 0; b < 8; ++b) { h[b] = whist[lane * 8 + b]; sum += h[b]; }
+        uint32_t incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += y;
+        }
+        const unsigned owner = __ballot_sync(0xffffffffu, incl >= (uint32_t)kc);
+        const int ol = __ffs(owner) - 1;
+        if (lane == ol) {
+            uint32_t before = incl - sum;
+            int bin = 0;
+#pragma unroll
+            for (int b = 0; b < 8; ++b) {
+                if (before + h[b] >= (uint32_t)kc) { bin = lane * 8 + b; break; }
+                before += h[b];
+            }
+            sc[0] = (uint32_t)bin;  // b*
+            sc[1] = before;         // entries in the bins below b*: all selected
+        }
+    }
+    __syncthreads();
+    const uint32_t bstar = sc[0];
+    const int before = (int)sc[1];
+    for (int i = tid; i < n; i += MERGE_THREADS) {
+        const uint64_t e = entry_at(i);
+        const uint32_t bin = ((uint32_t)(e >> 32) - kmin) >> sh;
+        if (bin < bstar) {
+            out[atomicAdd(&sc[2], 1u)] = e;
+        } else if (bin == bstar) {
+            const unsigned pos = atomicAdd(&sc[3], 1u);
+            if (pos < (unsigned)SELECT_BOUNDARY_CAP) blist[pos] = e;
+        }
+    }
+    __syncthreads();
+    const int nb = (int)sc[3];
+    if (nb > SELECT_BOUNDARY_CAP) return -1;
+    const int need = kc - before;  // 1 .. nb
+    for (int i = tid; i < nb; i += MERGE_THREADS) {
+        const uint64_t e = blist[i];
+        const uint32_t ke = (uint32_t)(e >> 32);
+        int rank = 0;
+        for (int j = 0; j < nb; ++j) {
+            const uint32_t kj = (uint32_t)(blist[j] >> 32);
+            rank += (kj < ke || (kj == ke && j < i)) ? 1 : 0;
+        }
+        if (rank < need) out[before + rank] = e;
+        if (rank == need - 1) *t_out = ke;
+    }
+    __syncthreads();
+    return kc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// exhaustive exact re-scan of one query (radix select on exact distance keys), output written here
+// ------------------------------------------------------------------------------------------------
+template <bool kIP>
+__device__ void exact_rescan_body(const MergeArgs& a, int64_t q, const float* qs, uint64_t* rkey, int64_t* rid,
+                                  uint32_t* rrow, RescanSmem& sm) {
+    const int kp = next_pow2(a.k);
+    const int tid = threadIdx.x;
+    const float inf_pad = kIP ? -INFINITY : INFINITY;
+    const int nslots = probed_slots(a);
+    int64_t total = 0;
+    for (int j = 0; j < nslots; ++j) {
+        const int seg = probed_segment(a, q, j);
+        if (seg >= 0) total += a.seg_rows[seg];
+    }
+    const int kk = (int)(total < a.k ? total : a.k);
+    __syncthreads();
+    if (tid == 0) { sm.prefix = 0; sm.need = kk; sm.less = 0; }
+    __syncthreads();
+
+    auto dist_key = [&](int64_t row) {
+        const float dist = ref_pair_distance<kIP>(qs, a.vecs + row * a.pitch, a.d);
+        return f2key(kIP ? -dist : (a.rank_squared ? dist : __fsqrt_rn(dist)));
+    };
+    auto id_key = [&](int64_t row) {  // ascending signed id order as unsigned
+        const int64_t id = a.ids ? a.ids[row] : row;
+        return (uint64_t)id ^ 0x8000000000000000ull;
+    };
+
+    if (kk > 0) {
+        // radix select of the kk-th smallest exact key, most significant byte first
+        for (int pass = 3; pass >= 0; --pass) {
+            sm.hist[tid] = 0;
+            __syncthreads();
+            const unsigned prefix = sm.prefix;
+            for (int j = 0; j < nslots; ++j) {
+                const int seg = probed_segment(a, q, j);
+                if (seg < 0) continue;
+                const int64_t r0 = a.seg_row0[seg];
+                const int n = a.seg_rows[seg];
+                for (int r = tid; r < n; r += blockDim.x) {
+                    const uint32_t dk = dist_key(r0 + r);
+                    const bool match = (pass == 3) || ((dk >> (8 * (pass + 1))) == (prefix >> (8 * (pass + 1))));
+                    if (match) atomicAdd(&sm.hist[(dk >> (8 * pass)) & 255u], 1u);
+                }
+            }
+            __syncthreads();
+            if (tid == 0) {
+                unsigned need = sm.need, cum = 0;
+                int b = 0;
+                for (; b < 256; ++b) {
+                    if (cum + sm.hist[b] >= need) break;
+                    cum += sm.hist[b];
+                }
+                sm.prefix = prefix | ((unsigned)b << (8 * pass));
+                sm.need = need - cum;
+                sm.less += cum;
+                sm.eq_total = b < 256 ? sm.hist[b] : 0u;
+            }
+            __syncthreads();
+        }
+        const uint32_t T = sm.prefix;
+        const unsigned n_less = sm.less;        // keys strictly below T
+        const unsigned take_eq = sm.need;       // how many keys equal to T to take
+        const unsigned eq_total = sm.eq_total;  // how many keys equal T
+        __syncthreads();
+        // A distance tie that straddles the k-th boundary is resolved by ascending id (the order the
+        // oracle fixes for the reference's distance-only comparator): radix-select the take_eq-th
+        // smallest id among the rows whose key equals T.
+        uint64_t id_thr = ~0ull;
+        if (eq_total > take_eq) {
+            if (tid == 0) { sm.prefix64 = 0ull; sm.need = take_eq; }
+            __syncthreads();
+            for (int pass = 7; pass >= 0; --pass) {
+                sm.hist[tid] = 0;
+                __syncthreads();
+                const uint64_t prefix = sm.prefix64;
+                for (int j = 0; j < nslots; ++j) {
+                    const int seg = probed_segment(a, q, j);
+                    if (seg < 0) continue;
+                    const int64_t r0 = a.seg_row0[seg];
+                    const int n = a.seg_rows[seg];
+                    for (int r = tid; r < n; r += blockDim.x) {
+                        if (dist_key(r0 + r) != T) continue;
+                        const uint64_t ik = id_key(r0 + r);
+                        const bool match = (pass == 7) || ((ik >> (8 * (pass + 1))) == (prefix >> (8 * (pass + 1))));
+                        if (match) atomicAdd(&sm.hist[(unsigned)(ik >> (8 * pass)) & 255u], 1u);
+                    }
+                }
+                __syncthreads();
+                if (tid == 0) {
+                    unsigned need = sm.need, cum = 0;
+                    int b = 0;
+                    for (; b < 256; ++b) {
+                        if (cum + sm.hist[b] >= need) break;
+                        cum += sm.hist[b];
+                    }
+                    sm.prefix64 = prefix | ((unsigned long long)(b & 255) << (8 * pass));
+                    sm.need = need - cum;
+                }
+                __syncthreads();
+            }
+            id_thr = sm.prefix64;
+        }
+        if (tid == 0) { sm.base_lt = 0; sm.base_eq = 0; }
+        __syncthreads();
+        // deterministic ordered collection
+        for (int j = 0; j < nslots; ++j) {
+            const int seg = probed_segment(a, q, j);
+            if (seg < 0) continue;
+            const int64_t r0 = a.seg_row0[seg];
+            const int n = a.seg_rows[seg];
+            for (int base = 0; base < n; base += blockDim.x) {
+                const int r = base + tid;
+                uint32_t dk = KEY_MAX;
+                bool lt = false, eq = false;
+                if (r < n) {
+                    dk = dist_key(r0 + r);
+                    lt = dk < T;
+                    eq = (dk == T) && (id_key(r0 + r) <= id_thr);
+                }
+                // block exclusive scan of (lt, eq) packed
+                int v = (lt ? 1 : 0) | (eq ? (1 << 16) : 0);
+                sm.scan[tid] = v;
+                __syncthreads();
+                for (int o = 1; o < 256; o <<= 1) {
+                    int t = (tid >= o) ? sm.scan[tid - o] : 0;
+                    __syncthreads();
+                    sm.scan[tid] += t;
+                    __syncthreads();
+                }
+                const int incl = sm.scan[tid];
+                const int excl = incl - v;
+                const int blt = sm.base_lt, beq = sm.base_eq;
+                int slot = -1;
+                if (lt) slot = blt + (excl & 0xffff);
+                else if (eq) {
+                    const int e = beq + (excl >> 16);
+                    if (e < (int)take_eq) slot = (int)n_less + e;
+                }
+                if (slot >= 0 && slot < kp) {
+                    const int64_t row = r0 + r;
+                    rkey[slot] = ((uint64_t)dk << 32) | (uint32_t)slot;
+                    rid[slot] = a.ids ? a.ids[row] : row;
+                    rrow[slot] = (uint32_t)row;
+                }
+                __syncthreads();
+                if (tid == 255) {
+                    sm.base_lt = blt + (incl & 0xffff);
+                    sm.base_eq = beq + (incl >> 16);
+                }
+                __syncthreads();
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = kk + tid; i < kp; i += blockDim.x) rkey[i] = COMP_MAX;
+    const int64_t* ridc = rid;
+    block_bitonic_sort(rkey, kp, [ridc](uint64_t x, uint64_t y) {
+        const uint32_t dx = (uint32_t)(x >> 32), dy = (uint32_t)(y >> 32);
+        if (dx != dy) return dx < dy;
+        if (x == COMP_MAX || y == COMP_MAX) return x < y;
+        return ridc[(uint32_t)x] < ridc[(uint32_t)y];
+    });
+    for (int i = tid; i < a.k; i += blockDim.x) {
+        int64_t id = -1, row = -1;
+        float dist = inf_pad;
+        if (i < kk) {
+            const uint64_t rk = rkey[i];
+            const uint32_t slot = (uint32_t)rk;
+            const float v = key2f((uint32_t)(rk >> 32));
+            dist = kIP ? -v : (a.rank_squared ? __fsqrt_rn(v) : v);
+            id = rid[slot];
+            row = rrow[slot];
+        }
+        a.out_ids[q * a.k + i] = id;
+        a.out_dist[q * a.k + i] = dist;
+        if (a.out_rows) a.out_rows[q * a.k + i] = row;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// refine `m` candidates (composites key << 32 | arena row in cand[0..m), any order, m <= kcp), order them by
+// (exact distance, id), prove that the rejected rows (all of which have filter key > a_key) cannot enter the
+// top-k, emit -- or fall through to the exact re-scan.
+// ------------------------------------------------------------------------------------------------
+struct RefineSmem {
+    float* qs;        // [d padded to 4]
+    uint64_t* rkey;   // [kcp]  exact distance key << 32 | candidate slot
+    int64_t* rid;     // [kcp]
+    uint32_t* rrow;   // [kcp]
+    uint32_t* order;  // [kcp]  candidate slot at every output rank
+    int* rank;        // [kcp]
+};
+
+template <bool kIP>
+__device__ void refine_and_emit(const MergeArgs& a, int64_t q, const uint64_t* cand, int m, uint32_t a_key,
+                                bool have_rejects, bool rescan, const RefineSmem& s, double qn2, RescanSmem& rs,
+                                int* s_flag) {
+    const int tid = threadIdx.x;
+    const int kcp = next_pow2(a.kc);
+    const float inf_pad = kIP ? -INFINITY : INFINITY;
+    int nc = 0;
+    if (!rescan) {
+        nc = m;
+        // ---- exact refine in the reference's summation order: eight lanes per candidate, one per accumulator of
+        //      the reference's 8-wide loop
+        for (int base = 0; base < nc; base += MERGE_THREADS / 8) {
+            const int i = base + (tid >> 3), j = tid & 7;
+            if (i < nc) {  // uniform inside every 8-lane group
+                const uint32_t row = (uint32_t)cand[i];
+                const float dist = ref_pair_distance_g8<kIP>(s.qs, a.vecs + (int64_t)row * a.pitch, a.d, j);
+                if (j == 0) {
+                    // order by the value the reference orders by: sqrt'ed for l2 (list_scanning.h:260)
+                    const uint32_t dk = f2key(kIP ? -dist : (a.rank_squared ? dist : __fsqrt_rn(dist)));
+                    s.rkey[i] = ((uint64_t)dk << 32) | (uint32_t)i;
+                    s.rid[i] = a.ids ? a.ids[row] : (int64_t)row;
+                    s.rrow[i] = row;
+                }
+            }
+        }
+        __syncthreads();
+        if (kcp <= MERGE_RANK_SORT_MAX) {
+            // one-pass rank sort: rank(i) = number of candidates ordered before i; P threads share one candidate
+            const int P = MERGE_THREADS / kcp;  // kcp is a power of two <= 256
+            for (int i = tid; i < kcp; i += MERGE_THREADS) s.rank[i] = 0;
+            __syncthreads();
+            const int i = tid / P, part = tid - i * P;
+            if (i < nc) {
+                const uint64_t ki = s.rkey[i];
+                const uint32_t di = (uint32_t)(ki >> 32);
+                const int64_t idi = s.rid[i];
+                const int span = (nc + P - 1) / P;
+                const int j0 = part * span, j1 = min(nc, j0 + span);
+                int cnt = 0;
+                for (int j = j0; j < j1; ++j) {
+                    const uint32_t dj = (uint32_t)(s.rkey[j] >> 32);
+                    const int64_t idj = s.rid[j];
+                    const bool before = dj < di || (dj == di && (idj < idi || (idj == idi && j < i)));
+                    cnt += before ? 1 : 0;
+                }
+                if (cnt) atomicAdd(&s.rank[i], cnt);
+            }
+            __syncthreads();
+            if (tid < nc) s.order[s.rank[tid]] = (uint32_t)tid;
+            __syncthreads();
+        } else {
+            for (int i = nc + tid; i < kcp; i += MERGE_THREADS) s.rkey[i] = COMP_MAX;
+            const int64_t* ridc = s.rid;
+            block_bitonic_sort(s.rkey, kcp, [ridc](uint64_t x, uint64_t y) {
+                const uint32_t dx = (uint32_t)(x >> 32), dy = (uint32_t)(y >> 32);
+                if (dx != dy) return dx < dy;
+                if (x == COMP_MAX || y == COMP_MAX) return x < y;
+                return ridc[(uint32_t)x] < ridc[(uint32_t)y];
+            });
+            // after the in-place sort rkey[r] carries the slot of rank r in its low word; look the key up through it
+            for (int i = tid; i < nc; i += MERGE_THREADS) s.order[i] = (uint32_t)s.rkey[i];
+            __syncthreads();
+        }
+        // ---- proof that nothing outside the refined set can enter the top-k
+        if (have_rejects && nc >= 1) {
+            if (tid == 0) {
+                const int kk = a.k < nc ? a.k : nc;
+                const float a_score = key2f(a_key);  // every rejected row's filter score is above this
+                // exact k-th (l2: distance, ip: -ip). In the bitonic path rkey is sorted in place (rank r at r); in
+                // the rank-sort path it is indexed by candidate slot.
+                const uint64_t kth = kcp <= MERGE_RANK_SORT_MAX ? s.rkey[s.order[kk - 1]] : s.rkey[kk - 1];
+                const float rk = key2f((uint32_t)(kth >> 32));
+                const double U = (double)(a.max_row_norm_dev ? *a.max_row_norm_dev : a.max_row_norm);
+                const double qn = qn2, qnorm = sqrt(qn);
+                const double eps = 5.960464477539063e-08;  // 2^-24
+                const double gam = (a.d + 8) * eps;
+                const double e2 = (a.d / 8 + 12) * eps;
+                bool ok;
+                if (!kIP) {
+                    const double e1 = gam * U * U + 2.0 * (gam + a.filter_gam) * qnorm * U + 4.0 * eps * fabs((double)a_score);
+                    // lb bounds the reference-order SQUARED distance of every rejected row from below; the
+                    // reference compares sqrt'ed values, and sqrt_rn is monotone, so a rejected row cannot
+                    // tie or beat the k-th as soon as sqrt_rn(round_down(lb)) is strictly above it.
+                    const double lb = (qn * (1.0 - gam) + (double)a_score - e1) * (1.0 - e2);
+                    const float lbf = __double2float_rd(lb);
+                    ok = a.rank_squared ? (lb > (double)rk) : (lbf > 0.f && __fsqrt_rn(lbf) > rk);
+                } else {
+                    // scores are -<q,v>: any rejected v has ip <= -a_score + err; need that below the k-th exact ip
+                    const double err = (gam + a.filter_gam + e2) * qnorm * U + 4.0 * eps * fabs((double)a_score);
+                    ok = (-(double)a_score + err) < -(double)rk;
+                }
+                *s_flag = ok ? 0 : -1;
+            }
+            __syncthreads();
+            rescan = (*s_flag < 0);
+        }
+    }
+    if (rescan) {
+        if (tid == 0) {
+            a.flags[q] = 1;
+            atomicAdd(&a.ctrl[2], 1);
+        }
+        exact_rescan_body<kIP>(a, q, s.qs, s.rkey, s.rid, s.rrow, rs);
+        return;
+    }
+    if (tid == 0) a.flags[q] = 0;
+    for (int i = tid; i < a.k; i += blockDim.x) {
+        int64_t id = -1, row = -1;
+        float dist = inf_pad;
+        if (i < nc) {
+            const uint32_t slot = s.order[i];
+            const float v = key2f((uint32_t)(s.rkey[kcp <= MERGE_RANK_SORT_MAX ? slot : i] >> 32));
+            dist = kIP ? -v : (a.rank_squared ? __fsqrt_rn(v) : v);
+            id = s.rid[slot];
+            row = s.rrow[slot];
+        }
+        a.out_ids[q * a.k + i] = id;
+        a.out_dist[q * a.k + i] = dist;
+        if (a.out_rows) a.out_rows[q * a.k + i] = row;
+    }
+}
+
+// shared-memory carve-up common to both kernels: [front buffer][cbuf kcp u64][qs][rkey][rid][rrow][order][rank]
+__host__ __device__ inline size_t refine_tail_bytes(int d, int kcp) {
+    return (size_t)kcp * 8 + (size_t)((d + 3) & ~3) * 4 + 8 + (size_t)kcp * (8 + 8 + 4 + 4 + 4);
+}
+__device__ __forceinline__ uint64_t* carve_refine(unsigned char* p, int d, int kcp, RefineSmem& s) {
+    uint64_t* cbuf = reinterpret_cast<uint64_t*>(p);
+    s.rkey = cbuf + kcp;
+    s.rid = reinterpret_cast<int64_t*>(s.rkey + kcp);
+    s.rrow = reinterpret_cast<uint32_t*>(s.rid + kcp);
+    s.order = s.rrow + kcp;
+    s.rank = reinterpret_cast<int*>(s.order + kcp);
+    s.qs = reinterpret_cast<float*>(s.rank + kcp);
+    return cbuf;
+}
+
+// ------------------------------------------------------------------------------------------------
+// IVF stores: candidates from the per-query buffers the filter kernel appended to
+// ------------------------------------------------------------------------------------------------
+template <bool kIP>
+__global__ void __launch_bounds__(MERGE_THREADS, 5) merge_refine_kernel(const MergeArgs a) {
+    extern __shared__ __align__(16) unsigned char msm[];
+    uint64_t* sbuf = reinterpret_cast<uint64_t*>(msm);  // [sort_cap]
+    const int kcp = next_pow2(a.kc);
+    RefineSmem s;
+    uint64_t* cbuf = carve_refine(msm + (size_t)a.sort_cap * 8, a.d, kcp, s);
+    __shared__ RescanSmem rs;
+    __shared__ unsigned s_whist[(MERGE_THREADS / 32) * 256];
+    __shared__ uint64_t s_blist[SELECT_BOUNDARY_CAP];
+    __shared__ int s_n, s_tot, s_flag;
+    __shared__ unsigned s_sc[4], s_mm[2], s_T;
+    __shared__ double s_qn;
+
+    const int64_t q = blockIdx.x;
+    const int tid = threadIdx.x;
+    if (tid == 0) { s_n = 0; s_tot = 0; s_mm[0] = 0xffffffffu; s_mm[1] = 0u; }
+    for (int i = tid; i < a.d; i += blockDim.x) s.qs[i] = a.queries[q * a.q_pitch + i];
+    __syncthreads();
+    if (tid == 0) {
+        double t = 0.0;
+        for (int i = 0; i < a.d; ++i) t += (double)s.qs[i] * (double)s.qs[i];
+        s_qn = t;
+    }
+
+    // ---- gather survivors: appended candidates whose filter key is within the final threshold
+    const uint32_t gthr = a.gthr[q];
+    const int appended = a.qcount[q];
+    if (tid == 0) {  // statistics for qk_scan_partitions' `stats`
+        atomicMax(&a.ctrl[3], appended);
+        atomicAdd(reinterpret_cast<unsigned long long*>(a.ctrl + 4), (unsigned long long)appended);
+    }
+    bool overflow = appended > a.qcap;  // entries were dropped: only the exact re-scan can answer
+    {
+        const int n = appended < a.qcap ? appended : a.qcap;
+        const uint64_t* c = a.qbuf + (size_t)q * a.qcap;
+        uint32_t mn = 0xffffffffu, mx = 0u;
+        for (int i = tid; i < n; i += blockDim.x) {
+            const uint64_t v = c[i];
+            const uint32_t key = (uint32_t)(v >> 32);
+            if (key > gthr || key == KEY_MAX) continue;
+            mn = min(mn, key);
+            mx = max(mx, key);
+            const int pos = atomicAdd(&s_n, 1);
+            if (pos < a.sort_cap) sbuf[pos] = v;
+            else overflow = true;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+            mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        }
+        if ((tid & 31) == 0 && mn <= mx) { atomicMin(&s_mm[0], mn); atomicMax(&s_mm[1], mx); }
+    }
+    overflow = __syncthreads_or(overflow);
+    const int ns = s_n;
+    if (ns < a.kc && !overflow) {
+        // Fewer survivors than candidates wanted is only legitimate when the query probed fewer than kc rows
+        // altogether (every threshold is an upper bound on the kc-th best key). Anything else means a threshold
+        // was too tight (or rows scored NaN): leave the query to the exact re-scan.
+        int total = 0;
+        const int nslots = probed_slots(a);
+        for (int j = tid; j < nslots; j += blockDim.x) {
+            const int seg = probed_segment(a, q, j);
+            if (seg >= 0) total += a.seg_rows[seg];
+        }
+        if (total) atomicAdd(&s_tot, total);
+        __syncthreads();
+        overflow = s_tot > ns;
+    }
+    bool rescan = overflow || a.force_rescan;
+    const uint64_t* cand = sbuf;
+    int m = ns;
+    uint32_t a_key = gthr;  // every row that is not a survivor has a filter key above the final threshold
+    bool have_rejects = ns >= a.kc && gthr != KEY_MAX;
+    if (!rescan && ns > kcp) {
+        // more survivors than the refine holds: keep the kc best by filter key
+        const uint64_t* sb = sbuf;
+        m = block_select_smallest([sb](int i) { return sb[i]; }, ns, a.kc, s_mm[0], s_mm[1], cbuf, &s_T, s_whist, s_sc, s_blist);
+        if (m < 0) { rescan = true; m = 0; }  // a pile of equal filter keys at the boundary
+        cand = cbuf;
+        a_key = s_T;
+        have_rejects = true;
+    }
+    refine_and_emit<kIP>(a, q, cand, m, a_key, have_rejects, rescan, s, s_qn, rs, &s_flag);
+}
+
+// ------------------------------------------------------------------------------------------------
+// dense mode (single-list stores whose [Q x rows] key matrix is small: the coarse centroid scan): the filter stored
+// the key of every (query, row); select the kc best here -- no thresholds, seeds, atomics or buffers in the filter
+// ------------------------------------------------------------------------------------------------
+template <bool kIP>
+__global__ void __launch_bounds__(MERGE_THREADS, 5) dense_refine_kernel(const MergeArgs a) {
+    extern __shared__ __align__(16) unsigned char msm[];
+    uint32_t* dkeys = reinterpret_cast<uint32_t*>(msm);  // [dense_rows rounded up to 2]
+    const int kcp = next_pow2(a.kc);
+    RefineSmem s;
+    uint64_t* cbuf = carve_refine(msm + (size_t)((a.dense_rows + 1) & ~1) * 4, a.d, kcp, s);
+    __shared__ RescanSmem rs;
+    __shared__ unsigned s_whist[(MERGE_THREADS / 32) * 256];
+    __shared__ uint64_t s_blist[SELECT_BOUNDARY_CAP];
+    __shared__ int s_flag;
+    __shared__ unsigned s_sc[4], s_mm[2], s_T, s_valid;
+    __shared__ double s_qn;
+
+    const int64_t q = blockIdx.x;
+    const int tid = threadIdx.x;
+    const int rows = a.dense_rows;
+    const uint32_t* src = a.dense + (size_t)q * rows;
+    if (tid == 0) { s_mm[0] = 0xffffffffu; s_mm[1] = 0u; s_valid = 0u; }
+    for (int i = tid; i < a.d; i += blockDim.x) s.qs[i] = a.queries[q * a.q_pitch + i];
+    __syncthreads();
+    {
+        // stage the query's keys; key range and the number of valid (non-NaN) scores on the way
+        uint32_t mn = 0xffffffffu, mx = 0u, valid = 0;
+        for (int i = tid; i < rows; i += blockDim.x) {
+            const uint32_t key = src[i];
+            dkeys[i] = key;
+            if (key != KEY_MAX) { mn = min(mn, key); mx = max(mx, key); ++valid; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+            mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            valid += __shfl_xor_sync(0xffffffffu, valid, o);
+        }
+        if ((tid & 31) == 0 && valid) { atomicMin(&s_mm[0], mn); atomicMax(&s_mm[1], mx); atomicAdd(&s_valid, valid); }
+    }
+    if (tid == 0) {
+        double t = 0.0;
+        for (int i = 0; i < a.d; ++i) t += (double)s.qs[i] * (double)s.qs[i];
+        s_qn = t;
+    }
+    __syncthreads();
+    bool rescan = a.force_rescan != 0;
+    int m = 0;
+    if ((int)s_valid < a.kc) {
+        rescan = true;  // fewer than kc rows with a valid score
+    } else {
+        // invalid keys (KEY_MAX) are clamped into the top bin: they are never among the kc smallest of >= kc valid ones
+        const uint32_t* dk = dkeys;
+        const uint32_t kmax = s_mm[1];
+        const uint32_t r0 = (uint32_t)a.dense_row0;
+        m = block_select_smallest(
+            [dk, kmax, r0](int i) { const uint32_t key = dk[i]; return ((uint64_t)(key < kmax ? key : kmax) << 32) | (r0 + (uint32_t)i); },
+            rows, a.kc, s_mm[0], kmax, cbuf, &s_T, s_whist, s_sc, s_blist);
+        if (m < 0) { rescan = true; m = 0; }
+    }
+    if (tid == 0) {
+        atomicMax(&a.ctrl[3], m);
+        atomicAdd(reinterpret_cast<unsigned long long*>(a.ctrl + 4), (unsigned long long)m);
+    }
+    refine_and_emit<kIP>(a, q, cbuf, m, s_T, /*have_rejects=*/rows > m, rescan, s, s_qn, rs, &s_flag);
+}
+
+}  // namespace qk

@@ -28,11 +28,10 @@
 #include "common.cuh"
 #include <cstring>
 #include <cstdlib>
+#include <mutex>
 
 namespace qk {
 
-static cudaStream_t g_side_stream = nullptr;  // fork/join partner of the caller's stream (threshold seeds)
-static cudaEvent_t g_ev_fork = nullptr, g_ev_join = nullptr;
 static int g_scan_variant = -1;  // 0: tensor-core filter for d <= 128 (default), 1: FP32-pipe filter everywhere
 static int g_force_rescan = 0;
 static void read_scan_env() {
@@ -73,9 +72,6 @@ static constexpr int SCAN_COMPUTE_WARPS = 8;  // two groups of four
 static constexpr int SCAN_SELECT_WARPS = 7;   // 8 + 7 + 1 producer = 16 warps: 128 registers per thread
 static constexpr int SCAN_THREADS = 32 * (SCAN_COMPUTE_WARPS + SCAN_SELECT_WARPS + 1);
 static constexpr int SCAN_MAX_NQ = 4;   // query-chunk ring depth
-static constexpr int MERGE_THREADS = 256;
-static constexpr int MERGE_SORT_CAP = 4096;
-static constexpr int MERGE_COMPACT_CAP = 512;
 static constexpr size_t SCAN_SMEM_LIMIT = 227 * 1024;
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -124,7 +120,7 @@ static size_t scan_smem_bytes(int dp, int kc, int gq, int nq) {
     return b + 1024;                                                         // slack to align the base to 1 KB
 }
 
-static int make_plan(const qk_store_t* st, int64_t Q, int nprobe, int k, ScanPlan* p) {
+static int make_plan(const qk_store_t* st, int64_t Q, int nprobe, int k, ScanPlan* p, bool allow_dense = true) {
     read_scan_env();
     QK_REQUIRE(k >= 1 && k <= QK_MAX_K, "k=%d out of range [1, %d]", k, QK_MAX_K);
     QK_REQUIRE(st->d >= 1 && st->pitch >= st->d && st->pitch % 4 == 0, "bad store d=%d pitch=%lld", st->d,
@@ -190,17 +186,18 @@ static int make_plan(const qk_store_t* st, int64_t Q, int nprobe, int k, ScanPla
             while (sample > 32 && sample / 2 >= p->kc && (size_t)Q * sample * p->dp * sizeof(float) > budget) sample >>= 1;
         }
         p->flat_seed = (st->num_lists == 1 && nprobe == 1) ? 1 : 0;
-        if (sample < p->kc || (!p->flat_seed && (size_t)2 * (p->dp + sample) * sizeof(float) > 48 * 1024)) sample = 0;
-        p->sample = sample;
-        // dense mode: [Q x rows] keys, at most 512 MB and at most 16384 rows (the select keeps a query's keys in smem)
-        p->dense = (p->flat_seed && g_scan_variant == 0 && p->dp <= 128 && Q <= 8192 && st->flat_rows >= p->kc && st->flat_rows <= 16384 &&
-                    (size_t)Q * (size_t)st->flat_rows * 4 <= ((size_t)512 << 20) && getenv("QK_NO_DENSE") == nullptr)
-                       ? 1 : 0;
-        if (p->dense) p->sample = sample = 0;
+        if (sample < p->kc) sample = 0;
+        // dense mode: [Q x rows] keys, at most 512 MB and at most 16384 rows (the select keeps a query's keys in smem).
+        // Only a flat-mode call (no probe table) uses it; the workspace is sized for either.
+        static const bool no_dense = getenv("QK_NO_DENSE") != nullptr;
+        const bool dense_ok = p->flat_seed && g_scan_variant == 0 && p->dp <= 128 && Q <= 8192 && st->flat_rows >= p->kc &&
+                              st->flat_rows <= 16384 && (size_t)Q * (size_t)st->flat_rows * 4 <= ((size_t)512 << 20) && !no_dense;
+        p->dense = (dense_ok && allow_dense) ? 1 : 0;
+        p->sample = p->dense ? 0 : sample;
         p->off_skeys = o;
         if (p->flat_seed && sample) o = align_up(o + (size_t)Q * sample * 4, 256);
         p->off_dense = o;
-        if (p->dense) o = align_up(o + (size_t)Q * (size_t)st->flat_rows * 4, 256);
+        if (dense_ok) o = align_up(o + (size_t)Q * (size_t)st->flat_rows * 4, 256);
     }
     p->total = o;
     return QK_OK;
@@ -209,7 +206,22 @@ static int make_plan(const qk_store_t* st, int64_t Q, int nprobe, int k, ScanPla
 // ------------------------------------------------------------------------------------------------
 // 1. expand (query, list) -> (query, segment) pairs + histogram
 // ------------------------------------------------------------------------------------------------
-__global__ void expand_pairs_kernel(const int32_t* __restrict__ probe, int64_t Q, int nprobe, int P,
+struct ProbeSource {
+    const int32_t* slots;       // [Q x nprobe] list slots, or null:
+    const int64_t* ids;         // [Q x nprobe] partition ids (the coarse scan's output) mapped through ...
+    const int32_t* id_to_slot;  // ... this dense table (ids outside it, or mapped to < 0, are skipped)
+    int64_t table_size;
+    int shard_rank, shard_world;  // shard_world > 1: only partitions with id % shard_world == shard_rank are scanned
+};
+__device__ __forceinline__ int probe_slot(const ProbeSource& ps, int64_t i) {
+    if (ps.slots) return ps.slots[i];
+    const int64_t id = ps.ids[i];
+    if (id < 0 || id >= ps.table_size) return -1;
+    if (ps.shard_world > 1 && (int)(id % ps.shard_world) != ps.shard_rank) return -1;
+    return ps.id_to_slot[id];
+}
+
+__global__ void expand_pairs_kernel(const ProbeSource probe, int64_t Q, int nprobe, int P,
                                     const int32_t* __restrict__ list_seg0, const int32_t* __restrict__ list_nseg,
                                     int num_lists, int32_t* __restrict__ pair_seg, int32_t* __restrict__ seg_count,
                                     uint32_t* __restrict__ gthr, bool single_segment_lists) {
@@ -220,19 +232,19 @@ __global__ void expand_pairs_kernel(const int32_t* __restrict__ probe, int64_t Q
         int64_t q = i / nprobe;
         int j = (int)(i - q * nprobe);
         if (j == 0) gthr[q] = KEY_MAX;
-        int l = probe[i];
+        int l = probe_slot(probe, i);
         int seg = -1;
         if (l >= 0 && l < num_lists && list_nseg[l] > 0) seg = list_seg0[l];
         pair_seg[q * P + j] = seg;  // P == nprobe here
         if (seg >= 0) atomicAdd(&seg_count[seg], 1);
     } else if (nprobe == 1) {
-        // one probed list per query (flat index / coarse scan): one thread per (query, segment slot)
+        // one probed list per query: one thread per (query, segment slot)
         int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
         if (i >= Q * P) return;
         int64_t q = i / P;
         int s2 = (int)(i - q * P);
         if (s2 == 0) gthr[q] = KEY_MAX;
-        int l = probe[q];
+        int l = probe_slot(probe, q);
         int seg = -1;
         if (l >= 0 && l < num_lists && s2 < list_nseg[l]) seg = list_seg0[l] + s2;
         pair_seg[i] = seg;
@@ -244,7 +256,7 @@ __global__ void expand_pairs_kernel(const int32_t* __restrict__ probe, int64_t Q
         gthr[q] = KEY_MAX;
         int pos = 0;
         for (int j = 0; j < nprobe; ++j) {
-            int l = probe[q * nprobe + j];
+            int l = probe_slot(probe, q * nprobe + j);
             if (l < 0 || l >= num_lists) continue;
             int s0 = list_seg0[l], ns = list_nseg[l];
             for (int s = 0; s < ns && pos < P; ++s) {
@@ -402,11 +414,22 @@ __device__ __forceinline__ uint32_t radix_select(KeyAt key_at, int n, int kc, ui
 // ------------------------------------------------------------------------------------------------
 // 3b. threshold seeds
 // ------------------------------------------------------------------------------------------------
-// One warp per query: the kc-th smallest filter score over a small sample of the query's probed rows (the first
-// `sample` rows of its first probed lists, scored on the FP32 pipe) is an upper bound on the kc-th smallest over
-// all of them, so the scan starts with a useful threshold instead of admitting everything. The sample is scored
-// in different arithmetic than the scan kernel (plain FMA chain vs. split TF32 / FFMA2 tiles), so the bound is
-// widened by more than the two error bounds together.
+// One CTA per query: the kc-th smallest filter score over a small sample of the query's probed rows (the first
+// `sample` rows of its first probed lists, scored on the FP32 pipe) is an upper bound on the kc-th smallest over all
+// of them, so the scan starts with a useful threshold instead of admitting everything. The sample is scored in
+// different arithmetic than the scan kernel (plain FMA chain vs. split TF32 / FFMA2 tiles), so the bound is widened
+// by more than the two error bounds together.
+// The sampled rows are contiguous runs of the arena (one per probed list): they are fetched with TMA bulk copies into
+// shared memory, SEED_CHUNK rows at a time, so the kernel is a stream of a few large asynchronous copies per SM instead
+// of register-limited dependent loads (it was latency-bound: 39-63 us for 67 MB at C2).
+static int seed_chunk_rows(int dp, int sample) {  // rows staged per step: at most 32 KB (64 rows at d = 128)
+    int c = (32 * 1024) / (dp * 4);
+    if (c < 8) c = 8;
+    return sample < c ? sample : c;
+}
+static size_t seed_smem_bytes(int dp, int sample) {
+    return (size_t)seed_chunk_rows(dp, sample) * dp * 4 + (size_t)dp * 4 + (size_t)sample * 8 + 16;
+}
 template <bool kIP>
 __global__ void __launch_bounds__(256) seed_thresholds_kernel(const float* __restrict__ vecs, int64_t pitch,
                                                               const float* __restrict__ norms, int d, int dp,
@@ -414,54 +437,94 @@ __global__ void __launch_bounds__(256) seed_thresholds_kernel(const float* __res
                                                               const int32_t* __restrict__ pair_seg, int P,
                                                               const int64_t* __restrict__ seg_row0,
                                                               const int32_t* __restrict__ seg_rows, int kc, int sample,
-                                                              float max_row_norm, float rel_margin,
+                                                              int chunk_rows, float max_row_norm, float rel_margin,
                                                               uint32_t* __restrict__ gthr) {
-    // two queries per CTA, four warps per query
-    extern __shared__ __align__(16) float seed_sm[];  // [2][dp] queries, then [2][sample] keys
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int grp = warp >> 2, gw = warp & 3;
-    const int64_t q = (int64_t)blockIdx.x * 2 + grp;
-    if (q >= Q) return;  // a whole 4-warp group leaves together: the named barrier below stays consistent
-    float* qs = seed_sm + (size_t)grp * dp;
-    uint32_t* keys = reinterpret_cast<uint32_t*>(seed_sm + (size_t)2 * dp) + (size_t)grp * sample;
-    for (int i = gw * 32 + lane; i < dp; i += 128) qs[i] = i < d ? queries[q * q_pitch + i] : 0.f;
-    asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
-    const float4* q4 = reinterpret_cast<const float4*>(qs);
-    const int dp4 = dp >> 2;
-    // the first `sample` rows of the query's probed segments, in probe order; eight lanes per row (coalesced
-    // 128-byte pieces), eight rows per warp step, the four warps of the group interleaved
-    int have = 0;
-    for (int j = 0; j < P && have < sample; ++j) {
-        const int seg = pair_seg[q * P + j];
-        if (seg < 0) continue;
-        const int take = min(seg_rows[seg], sample - have);
-        const int64_t r0 = seg_row0[seg];
-        for (int i0 = gw * 8; i0 < take; i0 += 32) {
-            const int ia = i0 + (lane >> 3), ib = ia + 4;
-            float acc0 = 0.f, acc1 = 0.f;
-            const float4* va = reinterpret_cast<const float4*>(vecs + (r0 + (ia < take ? ia : 0)) * pitch);
-            const float4* vb = reinterpret_cast<const float4*>(vecs + (r0 + (ib < take ? ib : 0)) * pitch);
-            for (int c = lane & 7; c < dp4; c += 8) {
-                const float4 x = __ldg(va + c), z = __ldg(vb + c), y = q4[c];
-                acc0 = fmaf(x.x, y.x, acc0); acc0 = fmaf(x.y, y.y, acc0);
-                acc0 = fmaf(x.z, y.z, acc0); acc0 = fmaf(x.w, y.w, acc0);
-                acc1 = fmaf(z.x, y.x, acc1); acc1 = fmaf(z.y, y.y, acc1);
-                acc1 = fmaf(z.z, y.z, acc1); acc1 = fmaf(z.w, y.w, acc1);
-            }
+    extern __shared__ __align__(128) unsigned char seed_raw[];
+    float* rows = reinterpret_cast<float*>(seed_raw);                 // [chunk_rows][dp]
+    float* qs = rows + (size_t)chunk_rows * dp;                       // [dp]
+    uint32_t* keys = reinterpret_cast<uint32_t*>(qs + dp);            // [sample]
+    float* nrm = reinterpret_cast<float*>(keys + sample);             // [sample] squared norms of the sampled rows
+    __shared__ int s_start[33];      // exclusive prefix of the sampled rows over the first 32 probes
+    __shared__ long long s_r0[32];   // first arena row of each of them
+    __shared__ __align__(8) uint64_t s_bar;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t q = blockIdx.x;
+    for (int i = tid; i < dp; i += 256) qs[i] = i < d ? queries[q * q_pitch + i] : 0.f;
+    if (warp == 0) {
+        int nrows = 0;
+        long long r0 = 0;
+        if (lane < P) {
+            const int seg = pair_seg[q * P + lane];
+            if (seg >= 0) { nrows = seg_rows[seg]; r0 = seg_row0[seg]; }
+        }
+        int incl = nrows;
 #pragma unroll
-            for (int o = 1; o < 8; o <<= 1) {
-                acc0 += __shfl_xor_sync(0xffffffffu, acc0, o);
-                acc1 += __shfl_xor_sync(0xffffffffu, acc1, o);
-            }
-            if ((lane & 7) == 0) {
-                if (ia < take) keys[have + ia] = f2key(kIP ? -acc0 : fmaf(-2.f, acc0, norms[r0 + ia]));
-                if (ib < take) keys[have + ib] = f2key(kIP ? -acc1 : fmaf(-2.f, acc1, norms[r0 + ib]));
+        for (int o = 1; o < 32; o <<= 1) {
+            const int y = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += y;
+        }
+        s_start[lane] = incl - nrows;
+        s_r0[lane] = r0;
+        if (lane == 31) s_start[32] = incl;
+        if (lane == 0) {
+            mbar_init(&s_bar, 1);
+            mbar_fence_init();
+        }
+    }
+    __syncthreads();
+    const int have = min(s_start[32], sample);
+    const int dp4 = dp >> 2;
+    const uint32_t row_bytes = (uint32_t)dp * 4u;
+    uint32_t phase = 0;
+    for (int base = 0; base < have; base += chunk_rows, phase ^= 1u) {
+        const int cn = min(chunk_rows, have - base);
+
+        if (warp == 0) {
+            // rows [base, base + cn) of the sample: one bulk copy per probed list they touch (contiguous when the arena
+            // has no row padding), else one per row
+            if (lane == 0) mbar_expect_tx(&s_bar, (uint32_t)cn * row_bytes);
+            __syncwarp();
+            const int lo = max(s_start[lane], base), hi = min(s_start[lane + 1], base + cn);
+            if (hi > lo) {
+                const float* src = vecs + (s_r0[lane] + (lo - s_start[lane])) * pitch;
+                float* dst = rows + (size_t)(lo - base) * dp;
+                if (pitch == dp) {
+                    bulk_g2s(dst, src, (uint32_t)(hi - lo) * row_bytes, &s_bar);
+                } else {
+                    for (int r = 0; r < hi - lo; ++r) bulk_g2s(dst + (size_t)r * dp, src + (size_t)r * pitch, row_bytes, &s_bar);
+                }
             }
         }
-        have += take;
+        if (base == 0) {
+            // the rows' squared norms, one coalesced load per sampled row, in flight together with the first bulk copy
+            // (read one by one inside the scoring loop they were a chain of dependent cache misses)
+            if (!kIP) {
+                for (int i = tid; i < have; i += 256) {
+                    int j = 0;
+                    while (j < 31 && i >= s_start[j + 1]) ++j;
+                    nrm[i] = norms[s_r0[j] + (i - s_start[j])];
+                }
+            }
+            __syncthreads();
+        }
+        mbar_wait(&s_bar, phase);
+        // one row per warp step: lane c holds 16-byte chunk c (conflict-free), reduced with shuffles
+        for (int i = warp; i < cn; i += 8) {
+            const float4* rp = reinterpret_cast<const float4*>(rows + (size_t)i * dp);
+            float acc = 0.f;
+            for (int c = lane; c < dp4; c += 32) {
+                const float4 x = rp[c], y = reinterpret_cast<const float4*>(qs)[c];
+                acc = fmaf(x.x, y.x, acc); acc = fmaf(x.y, y.y, acc);
+                acc = fmaf(x.z, y.z, acc); acc = fmaf(x.w, y.w, acc);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if (lane == 0) keys[base + i] = f2key(kIP ? -acc : fmaf(-2.f, acc, nrm[base + i]));
+        }
+        __syncthreads();  // the staging buffer is refilled by the next chunk
     }
-    asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
-    if (gw != 0 || have < kc) return;  // fewer sampled rows than candidates wanted: no bound
+    __syncthreads();
+    if (warp != 0 || have < kc) return;  // fewer sampled rows than candidates wanted: no bound
     // kc-th smallest key of the sample, by bisection on the key bits (keys in registers, 32 per lane at most)
     uint32_t kreg[32];
 #pragma unroll
@@ -552,9 +615,11 @@ __global__ void __launch_bounds__(256) seed_scores_flat_kernel(const float* __re
 
 __global__ void __launch_bounds__(256) seed_select_flat_kernel(const uint32_t* __restrict__ skeys, int sample, int have,
                                                                const float* __restrict__ queries, int64_t q_pitch, int d,
-                                                               int64_t Q, int kc, float max_row_norm, float rel_margin,
+                                                               int64_t Q, int kc, float max_row_norm,
+                                                               const float* __restrict__ max_row_norm_dev, float rel_margin,
                                                                uint32_t* __restrict__ gthr) {
     const int lane = threadIdx.x & 31;
+    if (max_row_norm_dev) max_row_norm = *max_row_norm_dev;
     const int64_t q = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (q >= Q || have < kc) return;
     uint32_t kreg[32];
@@ -589,76 +654,6 @@ __global__ void __launch_bounds__(256) seed_select_flat_kernel(const uint32_t* _
     }
 }
 
-// Dense mode (flat stores whose [Q x rows] score matrix is small: the coarse centroid scan): the filter kernel
-// stores the key of every (query, row); one CTA per query then radix-selects the kc-th smallest key T and emits the
-// rows with key <= T as that query's candidates -- the same candidate-buffer contract merge_refine expects
-// (qcount = candidates, gthr = T), without thresholds, atomics or refresh in the filter.
-__global__ void __launch_bounds__(256) dense_select_kernel(const uint32_t* __restrict__ dense, int rows, long long row0,
-                                                           int kc, int qcap, uint32_t* __restrict__ gthr,
-                                                           int32_t* __restrict__ qcount, uint64_t* __restrict__ qbuf) {
-    extern __shared__ uint32_t dkeys[];  // [rows]
-    __shared__ uint32_t hist[256];
-    __shared__ uint32_t s_prefix, s_need;
-    __shared__ int s_m;
-    const int tid = threadIdx.x, lane = tid & 31;
-    const int64_t q = blockIdx.x;
-    const uint32_t* src = dense + (size_t)q * rows;
-    for (int i = tid; i < rows; i += 256) dkeys[i] = src[i];
-    if (tid == 0) { s_prefix = 0; s_need = (uint32_t)kc; s_m = 0; }
-    __syncthreads();
-    for (int pass = 3; pass >= 0; --pass) {
-        hist[tid] = 0;
-        __syncthreads();
-        const uint32_t prefix = s_prefix;
-        const int sh = 8 * pass;
-        for (int i = tid; i < rows; i += 256) {
-            const uint32_t key = dkeys[i];
-            if (pass == 3 || (key >> (sh + 8)) == (prefix >> (sh + 8))) atomicAdd(&hist[(key >> sh) & 255u], 1u);
-        }
-        __syncthreads();
-        if (tid < 32) {  // lane l owns bins 8l .. 8l+7
-            uint32_t h[8], sum = 0;
-#pragma unroll
-            for (int b = 0; b < 8; ++b) { h[b] = hist[lane * 8 + b]; sum += h[b]; }
-            uint32_t incl = sum;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += y;
-            }
-            const uint32_t need = s_need;
-            const unsigned owner = __ballot_sync(0xffffffffu, incl >= need);
-            const int ol = __ffs(owner) - 1;
-            if (lane == ol) {
-                uint32_t before = incl - sum;
-                int bin = 0;
-#pragma unroll
-                for (int b = 0; b < 8; ++b) {
-                    if (before + h[b] >= need) { bin = lane * 8 + b; break; }
-                    before += h[b];
-                }
-                s_prefix = prefix | ((uint32_t)bin << sh);
-                s_need = need - before;
-            }
-        }
-        __syncthreads();
-    }
-    const uint32_t T = s_prefix;
-    uint64_t* qb = qbuf + (size_t)q * qcap;
-    for (int i = tid; i < rows; i += 256) {
-        const uint32_t key = dkeys[i];
-        if (key <= T) {
-            const int pos = atomicAdd(&s_m, 1);
-            if (pos < qcap) qb[pos] = ((uint64_t)key << 32) | (uint32_t)(row0 + i);
-        }
-    }
-    __syncthreads();
-    if (tid == 0) {
-        qcount[q] = s_m;
-        gthr[q] = T;
-    }
-}
-
 // ------------------------------------------------------------------------------------------------
 // 4. the scan (filter) kernel
 // ------------------------------------------------------------------------------------------------
@@ -678,8 +673,30 @@ struct ScanArgs {
     uint32_t* dense;      // dense mode: [Q x dense_rows] filter keys of every (query, row); null otherwise
     long long dense_row0;
     int dense_rows;
-    int dbg;  // profiling aid (QK_SCAN_DBG): skip pipeline stages to find the floor of the others; results are invalid
+    // flat mode (single-list store scanned without a probe table): the work items are the grid (segment x chunk of gq
+    // consecutive queries), item it = seg * flat_nchunks + chunk, computed in the kernel -- no pair tables, no grouping
+    int flat;
+    int flat_nchunks;
+    int flat_items;
+    int64_t Q;
+    const int64_t* seg_row0;
+    const int32_t* seg_rows;
+    int dbg;  // profiling aid (-DQK_STAGE_DEBUG builds only): skip pipeline stages to find the floor of the others
 };
+#ifdef QK_STAGE_DEBUG
+#define QK_DBG(a, bit) ((a).dbg & (bit))
+#else
+#define QK_DBG(a, bit) 0
+#endif
+
+// Work item `it` of a flat-mode scan (see ScanArgs::flat)
+__device__ __forceinline__ void flat_item(const ScanArgs& a, int it, int& seg, int& g_begin, int& g_cnt) {
+    seg = it / a.flat_nchunks;
+    const int chunk = it - seg * a.flat_nchunks;
+    g_begin = chunk * a.gq;
+    const int64_t left = a.Q - g_begin;
+    g_cnt = (int)(left < a.gq ? left : a.gq);
+}
 
 // One d-chunk (<= 128 floats) of one 64-row tile for NT query slots per lane: 4 rows x NT queries x float4
 // per step. The rows sit in shared memory as the TMA engine wrote them with the 128-byte swizzle: sub-tile b
@@ -765,7 +782,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) scan_kernel(const ScanArgs a,
         // pair ids -> thresholds) of the next items are in flight while the current item is issued:
         //   it3: index reserved for item n+3      m2: WorkItem of item n+2
         //   m1 + pair1: item n+1 and its pair ids  m0 + pair0 + gthr0: item n, complete
-        const int n_items = a.ctrl[1];
+        const int n_items = a.flat ? a.flat_items : a.ctrl[1];
         auto fetch_index = [&]() {
             int it = 0;
             if (lane == 0) it = atomicAdd(&a.ctrl[0], 1);
@@ -774,10 +791,22 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) scan_kernel(const ScanArgs a,
         auto fetch_item = [&](int it) {
             WorkItem w;
             w.seg = -1; w.g_begin = 0; w.g_cnt = 0; w.nrows = 0; w.row0 = 0; w.pad_ = 0;
-            if (it < n_items) w = a.items[it];
+            if (it < n_items) {
+                if (a.flat) {
+                    flat_item(a, it, w.seg, w.g_begin, w.g_cnt);
+                    w.nrows = a.seg_rows[w.seg];
+                    w.row0 = a.seg_row0[w.seg];
+                } else {
+                    w = a.items[it];
+                }
+            }
             return w;
         };
-        auto fetch_pair = [&](const WorkItem& w) { return (w.seg >= 0 && lane < w.g_cnt) ? a.seg_pairs[w.g_begin + lane] : -1; };
+        // pair index = query * P + slot; only the query (pair / P) is ever used downstream
+        auto fetch_pair = [&](const WorkItem& w) {
+            if (w.seg < 0 || lane >= w.g_cnt) return -1;
+            return a.flat ? (w.g_begin + lane) * a.P : a.seg_pairs[w.g_begin + lane];
+        };
         // thresholds move during the kernel (atomicMin from every SM): read them past the non-coherent L1
         auto fetch_gthr = [&](int pair) { return pair >= 0 ? __ldcg(a.gthr + pair / a.P) : KEY_MAX; };
         WorkItem m0 = fetch_item(fetch_index());
@@ -1047,452 +1076,8 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) scan_kernel(const ScanArgs a,
 
 }  // namespace qk
 #include "scan_mma.cuh"
+#include "refine.cuh"
 namespace qk {
-
-// ------------------------------------------------------------------------------------------------
-// block-wide bitonic sort of n (power of two) uint64 keys in shared memory
-// ------------------------------------------------------------------------------------------------
-template <typename Less>
-__device__ void block_bitonic_sort(uint64_t* s, int n, Less less) {
-    for (int size = 2; size <= n; size <<= 1) {
-        for (int stride = size >> 1; stride > 0; stride >>= 1) {
-            __syncthreads();
-            for (int i = threadIdx.x; i < (n >> 1); i += blockDim.x) {
-                int lo = 2 * i - (i & (stride - 1));
-                int hi = lo + stride;
-                bool up = ((lo & size) == 0);
-                uint64_t x = s[lo], y = s[hi];
-                bool sw = up ? less(y, x) : less(x, y);
-                if (sw) { s[lo] = y; s[hi] = x; }
-            }
-        }
-    }
-    __syncthreads();
-}
-
-__device__ __forceinline__ int next_pow2(int x) {
-    int p = 1;
-    while (p < x) p <<= 1;
-    return p;
-}
-
-// ------------------------------------------------------------------------------------------------
-// 5. merge + exact refine, one CTA per query
-// ------------------------------------------------------------------------------------------------
-struct MergeArgs {
-    const float* vecs;
-    int64_t pitch;
-    const int64_t* ids;
-    int d;
-    const int64_t* seg_row0;
-    const float* queries;
-    int64_t q_pitch;
-    const int32_t* pair_seg;
-    const uint32_t* gthr;
-    const uint64_t* qbuf;
-    const int32_t* qcount;
-    int qcap;
-    int32_t* flags;
-    int32_t* ctrl;
-    int P, kc, k;
-    float max_row_norm;
-    double filter_gam;  // extra relative error bound of the filter's dot products (tensor-core path), vs |q||v|
-    int64_t* out_ids;
-    float* out_dist;
-    int64_t* out_rows;
-    int force_rescan;
-    int sort_cap;  // survivors the shared-memory sort buffer holds (a power of two; more => exact re-scan)
-    const int32_t* seg_rows;
-    int rank_squared;  // l2 only: order by the squared distance (k-means assign: faiss Top1 on squared l2)
-};
-
-template <bool kIP>
-__global__ void __launch_bounds__(MERGE_THREADS) merge_refine_kernel(const MergeArgs a) {
-    extern __shared__ __align__(16) unsigned char msm[];
-    uint64_t* sbuf = reinterpret_cast<uint64_t*>(msm);                     // [sort_cap]
-    float* qs = reinterpret_cast<float*>(sbuf + a.sort_cap);               // [d]
-    const int kcp = next_pow2(a.kc);
-    uint64_t* rkey = reinterpret_cast<uint64_t*>(qs + ((a.d + 3) & ~3));   // [kcp] (distkey<<32 | slot)
-    int64_t* rid = reinterpret_cast<int64_t*>(rkey + kcp);                 // [kcp]
-    uint32_t* rrow = reinterpret_cast<uint32_t*>(rid + kcp);               // [kcp]
-    __shared__ int s_n, s_tot, s_m;
-    __shared__ uint32_t s_T;
-    __shared__ uint32_t s_hist[256];
-    __shared__ uint64_t cbuf[MERGE_COMPACT_CAP];
-    __shared__ double s_qn;
-
-    const int64_t q = blockIdx.x;
-    const int tid = threadIdx.x;
-    const float inf_pad = kIP ? -INFINITY : INFINITY;
-    if (tid == 0) { s_n = 0; s_tot = 0; }
-    for (int i = tid; i < a.d; i += blockDim.x) qs[i] = a.queries[q * a.q_pitch + i];
-    __syncthreads();
-    if (tid == 0) {
-        double s = 0.0;
-        for (int i = 0; i < a.d; ++i) s += (double)qs[i] * (double)qs[i];
-        s_qn = s;
-    }
-
-    // ---- gather survivors: appended candidates whose filter key is within the final threshold
-    const uint32_t gthr = a.gthr[q];
-    const int appended = a.qcount[q];
-    if (tid == 0) {  // statistics for qk_scan_partitions' `stats`
-        atomicMax(&a.ctrl[3], appended);
-        atomicAdd(reinterpret_cast<unsigned long long*>(a.ctrl + 4), (unsigned long long)appended);
-    }
-    bool overflow = appended > a.qcap;  // entries were dropped: only the exact re-scan can answer
-    {
-        const int n = appended < a.qcap ? appended : a.qcap;
-        const uint64_t* c = a.qbuf + (size_t)q * a.qcap;
-        for (int i = tid; i < n; i += blockDim.x) {
-            const uint64_t v = c[i];
-            const uint32_t key = (uint32_t)(v >> 32);
-            if (key > gthr || key == KEY_MAX) continue;
-            const int pos = atomicAdd(&s_n, 1);
-            if (pos < a.sort_cap) sbuf[pos] = v;
-            else overflow = true;
-        }
-    }
-    overflow = __syncthreads_or(overflow);
-    int ns = s_n;
-    if (ns < a.kc && !overflow) {
-        // Fewer survivors than candidates wanted is only legitimate when the query probed fewer than kc rows
-        // altogether (every threshold is an upper bound on the kc-th best key). Anything else means a threshold
-        // was too tight: leave the query to the exact re-scan.
-        int total = 0;
-        for (int j = tid; j < a.P; j += blockDim.x) {
-            const int seg = a.pair_seg[q * a.P + j];
-            if (seg >= 0) total += a.seg_rows[seg];
-        }
-        if (total) atomicAdd(&s_tot, total);
-        __syncthreads();
-        overflow = s_tot > ns;
-    }
-    bool rescan = overflow || a.force_rescan;
-    int nc = 0;
-    if (!rescan) {
-        // The kc smallest composites (key << 32 | row), sorted. With many survivors a full sort is wasteful: one
-        // warp radix-selects the kc-th smallest key T, everything with key <= T is compacted (kc entries plus ties)
-        // and only that is sorted.
-        bool compacted = false;
-        if (ns > 4 * a.kc && ns > 256 && a.kc <= MERGE_COMPACT_CAP / 2) {
-            if (tid < 32) {
-                const uint64_t* sb = sbuf;
-                const uint32_t t = radix_select([sb](int i) { return (uint32_t)(sb[i] >> 32); }, ns, a.kc, s_hist, tid);
-                if (tid == 0) { s_T = t; s_m = 0; }
-            }
-            __syncthreads();
-            const uint32_t T = s_T;
-            for (int i = tid; i < ns; i += blockDim.x) {
-                const uint64_t v = sbuf[i];
-                if ((uint32_t)(v >> 32) <= T) {
-                    const int pos = atomicAdd(&s_m, 1);
-                    if (pos < MERGE_COMPACT_CAP) cbuf[pos] = v;
-                }
-            }
-            __syncthreads();
-            const int m = s_m;
-            if (m <= MERGE_COMPACT_CAP) {  // else: a pile of equal keys, fall back to the full sort
-                const int np = next_pow2(m > 1 ? m : 1);
-                for (int i = m + tid; i < np; i += blockDim.x) cbuf[i] = COMP_MAX;
-                block_bitonic_sort(cbuf, np, [](uint64_t x, uint64_t y) { return x < y; });
-                sbuf = cbuf;
-                compacted = true;
-            }
-        }
-        uint32_t a_key = 0;  // filter key of the kc-th best candidate (only meaningful when ns >= kc)
-        if (!compacted && ns <= a.kc) {
-            // every survivor is refined anyway (dense mode hands over exactly kc + ties): no order needed among
-            // them, only the largest filter key for the proof
-            if (tid == 0) s_T = 0;
-            __syncthreads();
-            uint32_t mx = 0;
-            for (int i = tid; i < ns; i += blockDim.x) mx = max(mx, (uint32_t)(sbuf[i] >> 32));
-            if (mx) atomicMax(&s_T, mx);
-            __syncthreads();
-            a_key = s_T;
-        } else {
-            if (!compacted) {
-                const int np = next_pow2(ns > 1 ? ns : 1);
-                for (int i = ns + tid; i < np; i += blockDim.x) sbuf[i] = COMP_MAX;
-                block_bitonic_sort(sbuf, np, [](uint64_t x, uint64_t y) { return x < y; });
-            }
-            a_key = (uint32_t)(sbuf[a.kc - 1] >> 32);
-        }
-        nc = ns < a.kc ? ns : a.kc;
-        // ---- exact refine in the reference's summation order
-        // eight lanes per candidate, one per accumulator of the reference's 8-wide loop
-        for (int base = 0; base < kcp; base += MERGE_THREADS / 8) {
-            const int i = base + (tid >> 3), j = tid & 7;
-            if (i < kcp) {  // uniform inside every 8-lane group
-                if (i < nc) {
-                    const uint32_t row = (uint32_t)sbuf[i];
-                    const float dist = ref_pair_distance_g8<kIP>(qs, a.vecs + (int64_t)row * a.pitch, a.d, j);
-                    if (j == 0) {
-                        // order by the value the reference orders by: sqrt'ed for l2 (list_scanning.h:260)
-                        const uint32_t dk = f2key(kIP ? -dist : (a.rank_squared ? dist : __fsqrt_rn(dist)));
-                        rkey[i] = ((uint64_t)dk << 32) | (uint32_t)i;
-                        rid[i] = a.ids ? a.ids[row] : (int64_t)row;
-                        rrow[i] = row;
-                    }
-                } else if (j == 0) {
-                    rkey[i] = COMP_MAX;
-                }
-            }
-        }
-        const int64_t* ridc = rid;
-        block_bitonic_sort(rkey, kcp, [ridc](uint64_t x, uint64_t y) {
-            const uint32_t dx = (uint32_t)(x >> 32), dy = (uint32_t)(y >> 32);
-            if (dx != dy) return dx < dy;
-            if (x == COMP_MAX || y == COMP_MAX) return x < y;
-            return ridc[(uint32_t)x] < ridc[(uint32_t)y];
-        });
-        // ---- proof that nothing outside the refined set can enter the top-k
-        if (ns >= a.kc && nc >= 1) {  // ns < kc: every probed row was a survivor, nothing was rejected
-            if (tid == 0) {
-                const int kk = a.k < nc ? a.k : nc;
-                const float a_score = key2f(a_key);  // filter score of the kc-th candidate
-                const float rk = key2f((uint32_t)(rkey[kk - 1] >> 32));         // exact k-th (l2: distance, ip: -ip)
-                const double qn = s_qn, qnorm = sqrt(qn), U = (double)a.max_row_norm;
-                const double eps = 5.960464477539063e-08;  // 2^-24
-                const double gam = (a.d + 8) * eps;
-                const double e2 = (a.d / 8 + 12) * eps;
-                bool ok;
-                if (!kIP) {
-                    const double e1 = gam * U * U + 2.0 * (gam + a.filter_gam) * qnorm * U + 4.0 * eps * fabs((double)a_score);
-                    // lb bounds the reference-order SQUARED distance of every rejected row from below; the
-                    // reference compares sqrt'ed values, and sqrt_rn is monotone, so a rejected row cannot
-                    // tie or beat the k-th as soon as sqrt_rn(round_down(lb)) is strictly above it.
-                    const double lb = (qn * (1.0 - gam) + (double)a_score - e1) * (1.0 - e2);
-                    const float lbf = __double2float_rd(lb);
-                    ok = a.rank_squared ? (lb > (double)rk) : (lbf > 0.f && __fsqrt_rn(lbf) > rk);
-                } else {
-                    // scores are -<q,v>: any rejected v has ip <= -a_score + err; need that below the k-th exact ip
-                    const double err = (gam + a.filter_gam + e2) * qnorm * U + 4.0 * eps * fabs((double)a_score);
-                    ok = (-(double)a_score + err) < -(double)rk;
-                }
-                s_n = ok ? 0 : -1;
-            }
-            __syncthreads();
-            rescan = (s_n < 0);
-        }
-    }
-    if (rescan) {
-        if (tid == 0) {
-            a.flags[q] = 1;
-            atomicAdd(&a.ctrl[2], 1);
-        }
-        return;
-    }
-    if (tid == 0) a.flags[q] = 0;
-    for (int i = tid; i < a.k; i += blockDim.x) {
-        int64_t id = -1, row = -1;
-        float dist = inf_pad;
-        if (i < nc) {
-            const uint64_t rk = rkey[i];
-            const uint32_t slot = (uint32_t)rk;
-            const float v = key2f((uint32_t)(rk >> 32));
-            dist = kIP ? -v : (a.rank_squared ? __fsqrt_rn(v) : v);
-            id = rid[slot];
-            row = rrow[slot];
-        }
-        a.out_ids[q * a.k + i] = id;
-        a.out_dist[q * a.k + i] = dist;
-        if (a.out_rows) a.out_rows[q * a.k + i] = row;
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// 6. exhaustive exact re-scan of flagged queries (radix select on exact distance keys)
-// ------------------------------------------------------------------------------------------------
-template <bool kIP>
-__global__ void __launch_bounds__(256) exact_rescan_kernel(const MergeArgs a, const int32_t* __restrict__ seg_rows) {
-    const int64_t q = blockIdx.x;
-    if (a.flags[q] == 0) return;
-    extern __shared__ __align__(16) unsigned char msm[];
-    float* qs = reinterpret_cast<float*>(msm);                                  // [d]
-    const int kp = next_pow2(a.k);
-    uint64_t* rkey = reinterpret_cast<uint64_t*>(qs + ((a.d + 3) & ~3) + 2);     // [kp]
-    rkey = reinterpret_cast<uint64_t*>(((uintptr_t)rkey + 7) & ~(uintptr_t)7);
-    int64_t* rid = reinterpret_cast<int64_t*>(rkey + kp);                       // [kp]
-    uint32_t* rrow = reinterpret_cast<uint32_t*>(rid + kp);                     // [kp]
-    __shared__ unsigned hist[256];
-    __shared__ unsigned s_prefix, s_need, s_less, s_eq_total;
-    __shared__ unsigned long long s_prefix64;
-    __shared__ int s_scan[256];
-    __shared__ int s_base_lt, s_base_eq;
-    const int tid = threadIdx.x;
-    const float inf_pad = kIP ? -INFINITY : INFINITY;
-
-    for (int i = tid; i < a.d; i += blockDim.x) qs[i] = a.queries[q * a.q_pitch + i];
-    int64_t total = 0;
-    for (int j = 0; j < a.P; ++j) {
-        const int seg = a.pair_seg[q * a.P + j];
-        if (seg >= 0) total += seg_rows[seg];
-    }
-    const int kk = (int)(total < a.k ? total : a.k);
-    if (tid == 0) { s_prefix = 0; s_need = kk; s_less = 0; }
-    __syncthreads();
-
-    auto dist_key = [&](int64_t row) {
-        const float dist = ref_pair_distance<kIP>(qs, a.vecs + row * a.pitch, a.d);
-        return f2key(kIP ? -dist : (a.rank_squared ? dist : __fsqrt_rn(dist)));
-    };
-    auto id_key = [&](int64_t row) {  // ascending signed id order as unsigned
-        const int64_t id = a.ids ? a.ids[row] : row;
-        return (uint64_t)id ^ 0x8000000000000000ull;
-    };
-
-    if (kk > 0) {
-        // radix select of the kk-th smallest exact key, most significant byte first
-        for (int pass = 3; pass >= 0; --pass) {
-            hist[tid] = 0;
-            __syncthreads();
-            const unsigned prefix = s_prefix;
-            for (int j = 0; j < a.P; ++j) {
-                const int seg = a.pair_seg[q * a.P + j];
-                if (seg < 0) continue;
-                const int64_t r0 = a.seg_row0[seg];
-                const int n = seg_rows[seg];
-                for (int r = tid; r < n; r += blockDim.x) {
-                    const uint32_t dk = dist_key(r0 + r);
-                    const bool match = (pass == 3) || ((dk >> (8 * (pass + 1))) == (prefix >> (8 * (pass + 1))));
-                    if (match) atomicAdd(&hist[(dk >> (8 * pass)) & 255u], 1u);
-                }
-            }
-            __syncthreads();
-            if (tid == 0) {
-                unsigned need = s_need, cum = 0;
-                int b = 0;
-                for (; b < 256; ++b) {
-                    if (cum + hist[b] >= need) break;
-                    cum += hist[b];
-                }
-                s_prefix = prefix | ((unsigned)b << (8 * pass));
-                s_need = need - cum;
-                s_less += cum;
-                s_eq_total = b < 256 ? hist[b] : 0u;
-            }
-            __syncthreads();
-        }
-        const uint32_t T = s_prefix;
-        const unsigned n_less = s_less;        // keys strictly below T
-        const unsigned take_eq = s_need;       // how many keys equal to T to take
-        const unsigned eq_total = s_eq_total;  // how many keys equal T
-        __syncthreads();
-        // A distance tie that straddles the k-th boundary is resolved by ascending id (the order the
-        // oracle fixes for the reference's distance-only comparator): radix-select the take_eq-th
-        // smallest id among the rows whose key equals T.
-        uint64_t id_thr = ~0ull;
-        if (eq_total > take_eq) {
-            if (tid == 0) { s_prefix64 = 0ull; s_need = take_eq; }
-            __syncthreads();
-            for (int pass = 7; pass >= 0; --pass) {
-                hist[tid] = 0;
-                __syncthreads();
-                const uint64_t prefix = s_prefix64;
-                for (int j = 0; j < a.P; ++j) {
-                    const int seg = a.pair_seg[q * a.P + j];
-                    if (seg < 0) continue;
-                    const int64_t r0 = a.seg_row0[seg];
-                    const int n = seg_rows[seg];
-                    for (int r = tid; r < n; r += blockDim.x) {
-                        if (dist_key(r0 + r) != T) continue;
-                        const uint64_t ik = id_key(r0 + r);
-                        const bool match = (pass == 7) || ((ik >> (8 * (pass + 1))) == (prefix >> (8 * (pass + 1))));
-                        if (match) atomicAdd(&hist[(unsigned)(ik >> (8 * pass)) & 255u], 1u);
-                    }
-                }
-                __syncthreads();
-                if (tid == 0) {
-                    unsigned need = s_need, cum = 0;
-                    int b = 0;
-                    for (; b < 256; ++b) {
-                        if (cum + hist[b] >= need) break;
-                        cum += hist[b];
-                    }
-                    s_prefix64 = prefix | ((unsigned long long)(b & 255) << (8 * pass));
-                    s_need = need - cum;
-                }
-                __syncthreads();
-            }
-            id_thr = s_prefix64;
-        }
-        if (tid == 0) { s_base_lt = 0; s_base_eq = 0; }
-        __syncthreads();
-        // deterministic ordered collection
-        for (int j = 0; j < a.P; ++j) {
-            const int seg = a.pair_seg[q * a.P + j];
-            if (seg < 0) continue;
-            const int64_t r0 = a.seg_row0[seg];
-            const int n = seg_rows[seg];
-            for (int base = 0; base < n; base += blockDim.x) {
-                const int r = base + tid;
-                uint32_t dk = KEY_MAX;
-                bool lt = false, eq = false;
-                if (r < n) {
-                    dk = dist_key(r0 + r);
-                    lt = dk < T;
-                    eq = (dk == T) && (id_key(r0 + r) <= id_thr);
-                }
-                // block exclusive scan of (lt, eq) packed
-                int v = (lt ? 1 : 0) | (eq ? (1 << 16) : 0);
-                s_scan[tid] = v;
-                __syncthreads();
-                for (int o = 1; o < 256; o <<= 1) {
-                    int t = (tid >= o) ? s_scan[tid - o] : 0;
-                    __syncthreads();
-                    s_scan[tid] += t;
-                    __syncthreads();
-                }
-                const int incl = s_scan[tid];
-                const int excl = incl - v;
-                const int blt = s_base_lt, beq = s_base_eq;
-                int slot = -1;
-                if (lt) slot = blt + (excl & 0xffff);
-                else if (eq) {
-                    const int e = beq + (excl >> 16);
-                    if (e < (int)take_eq) slot = (int)n_less + e;
-                }
-                if (slot >= 0 && slot < kp) {
-                    const int64_t row = r0 + r;
-                    rkey[slot] = ((uint64_t)dk << 32) | (uint32_t)slot;
-                    rid[slot] = a.ids ? a.ids[row] : row;
-                    rrow[slot] = (uint32_t)row;
-                }
-                __syncthreads();
-                if (tid == 255) {
-                    s_base_lt = blt + (incl & 0xffff);
-                    s_base_eq = beq + (incl >> 16);
-                }
-                __syncthreads();
-            }
-        }
-    }
-    for (int i = kk + tid; i < kp; i += blockDim.x) rkey[i] = COMP_MAX;
-    const int64_t* ridc = rid;
-    block_bitonic_sort(rkey, kp, [ridc](uint64_t x, uint64_t y) {
-        const uint32_t dx = (uint32_t)(x >> 32), dy = (uint32_t)(y >> 32);
-        if (dx != dy) return dx < dy;
-        if (x == COMP_MAX || y == COMP_MAX) return x < y;
-        return ridc[(uint32_t)x] < ridc[(uint32_t)y];
-    });
-    for (int i = tid; i < a.k; i += blockDim.x) {
-        int64_t id = -1, row = -1;
-        float dist = inf_pad;
-        if (i < kk) {
-            const uint64_t rk = rkey[i];
-            const uint32_t slot = (uint32_t)rk;
-            const float v = key2f((uint32_t)(rk >> 32));
-            dist = kIP ? -v : (a.rank_squared ? __fsqrt_rn(v) : v);
-            id = rid[slot];
-            row = rrow[slot];
-        }
-        a.out_ids[q * a.k + i] = id;
-        a.out_dist[q * a.k + i] = dist;
-        if (a.out_rows) a.out_rows[q * a.k + i] = row;
-    }
-}
 
 // ------------------------------------------------------------------------------------------------
 // host side
@@ -1506,6 +1091,30 @@ struct ProfileRecord {
 };
 static ProfileRecord* g_prof = nullptr;
 static int g_prof_cap = 0, g_prof_n = 0;
+
+// Fork/join partner of the caller's stream (threshold seeds run beside the grouping kernels): one per device, created
+// on first use under a lock -- an index on a second GPU of the same process gets its own.
+struct SideStream {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+};
+static constexpr int QK_MAX_DEVICES = 64;
+static SideStream g_side[QK_MAX_DEVICES];
+static std::mutex g_side_mutex;
+static int side_stream_for_current_device(SideStream** out) {
+    int dev = 0;
+    QK_CUDA(cudaGetDevice(&dev));
+    QK_REQUIRE(dev >= 0 && dev < QK_MAX_DEVICES, "device ordinal %d out of range", dev);
+    std::lock_guard<std::mutex> lock(g_side_mutex);
+    SideStream& ss = g_side[dev];
+    if (!ss.stream) {
+        QK_CUDA(cudaStreamCreateWithFlags(&ss.stream, cudaStreamNonBlocking));
+        QK_CUDA(cudaEventCreateWithFlags(&ss.fork, cudaEventDisableTiming));
+        QK_CUDA(cudaEventCreateWithFlags(&ss.join, cudaEventDisableTiming));
+    }
+    *out = &ss;
+    return QK_OK;
+}
 
 // Tensor map of the row arena for the scan kernel's TMA loads: [num_rows x pitch] f32, box = 64 rows x 32
 // floats (128 B), 128-byte swizzle, out-of-bounds elements read as zero.
@@ -1540,29 +1149,60 @@ static int make_row_tensor_map(const qk_store_t* st, int box_rows, CUtensorMap* 
     return QK_OK;
 }
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per kernel and size instead of before every launch
+static int ensure_smem_impl(const void* kern, size_t bytes) {
+    static std::mutex m;
+    static const void* fn[256];
+    static int fdev[256];
+    static size_t granted[256];
+    static int n = 0;
+    int dev = 0;
+    QK_CUDA(cudaGetDevice(&dev));  // the attribute is per function AND per device
+    std::lock_guard<std::mutex> lock(m);
+    int i = 0;
+    while (i < n && (fn[i] != kern || fdev[i] != dev)) ++i;
+    if (i == n) {
+        if (n == 256) {
+            QK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+            return QK_OK;
+        }
+        fn[n] = kern;
+        fdev[n] = dev;
+        granted[n] = 0;  // static + dynamic shared memory together may pass 48 KB: always opt in
+        ++n;
+        // these kernels live on shared memory, not L1: ask for the largest carve-out so that occupancy is not capped
+        // by the default split
+        QK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+    }
+    if (bytes > granted[i]) {
+        QK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        granted[i] = bytes;
+    }
+    return QK_OK;
+}
+template <typename K>
+static int ensure_smem(K kern, size_t bytes) { return ensure_smem_impl((const void*)kern, bytes); }
+
 static int launch_scan(const ScanArgs& sa, const CUtensorMap& vmap, int metric, size_t smem, bool mma, cudaStream_t stream) {
     const int grid = sm_count();
+    int rc;
     if (mma) {
         const size_t msmem = scan_mma_smem_bytes();
         if (metric == QK_METRIC_INNER_PRODUCT) {
-            auto kern = scan_mma_kernel<true>;
-            QK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem));
-            kern<<<grid, MMA_THREADS, msmem, stream>>>(sa, vmap);
+            if ((rc = ensure_smem(scan_mma_kernel<true>, msmem))) return rc;
+            scan_mma_kernel<true><<<grid, MMA_THREADS, msmem, stream>>>(sa, vmap);
         } else {
-            auto kern = scan_mma_kernel<false>;
-            QK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem));
-            kern<<<grid, MMA_THREADS, msmem, stream>>>(sa, vmap);
+            if ((rc = ensure_smem(scan_mma_kernel<false>, msmem))) return rc;
+            scan_mma_kernel<false><<<grid, MMA_THREADS, msmem, stream>>>(sa, vmap);
         }
     } else if (metric == QK_METRIC_INNER_PRODUCT) {
-        auto kern = scan_kernel<true>;
-        QK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, SCAN_THREADS, smem, stream>>>(sa, vmap);
+        if ((rc = ensure_smem(scan_kernel<true>, smem))) return rc;
+        scan_kernel<true><<<grid, SCAN_THREADS, smem, stream>>>(sa, vmap);
     } else {
-        auto kern = scan_kernel<false>;
-        QK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, SCAN_THREADS, smem, stream>>>(sa, vmap);
+        if ((rc = ensure_smem(scan_kernel<false>, smem))) return rc;
+        scan_kernel<false><<<grid, SCAN_THREADS, smem, stream>>>(sa, vmap);
     }
-    QK_CUDA(cudaGetLastError());
+    QK_LAUNCHED();
     return QK_OK;
 }
 
@@ -1581,21 +1221,26 @@ extern "C" int qk_scan_partitions(const qk_store_t* st, const float* queries, in
                                   const int32_t* probe_lists, int nprobe, int metric, int k, int64_t* out_ids,
                                   float* out_dist, int64_t* out_rows, void* workspace, size_t workspace_bytes,
                                   int32_t* stats, void* stream_v) {
+    ScanExtras ex;
     return qk::scan_partitions_impl(st, queries, Q, q_pitch, probe_lists, nprobe, metric, k, out_ids, out_dist, out_rows,
-                                    workspace, workspace_bytes, stats, stream_v, 0);
+                                    workspace, workspace_bytes, stats, stream_v, ex);
 }
 
 int qk::scan_partitions_impl(const qk_store_t* st, const float* queries, int64_t Q, int64_t q_pitch,
                              const int32_t* probe_lists, int nprobe, int metric, int k, int64_t* out_ids,
                              float* out_dist, int64_t* out_rows, void* workspace, size_t workspace_bytes,
-                             int32_t* stats, void* stream_v, int rank_squared) {
+                             int32_t* stats, void* stream_v, const ScanExtras& ex) {
     cudaStream_t stream = (cudaStream_t)stream_v;
-    QK_REQUIRE(st && queries && probe_lists && out_ids && out_dist, "null argument");
+    QK_REQUIRE(st && queries && out_ids && out_dist, "null argument");
     QK_REQUIRE(metric == QK_METRIC_L2 || metric == QK_METRIC_INNER_PRODUCT, "metric %d not supported", metric);
     QK_REQUIRE(Q > 0 && nprobe > 0, "empty query batch");
     QK_REQUIRE(st->num_segments > 0 && st->num_lists > 0, "store has no segments");
+    // flat mode: a single-list store scanned without a probe table -- every query scans the whole list
+    const bool flat = (probe_lists == nullptr && ex.probe_ids == nullptr);
+    QK_REQUIRE(!flat || (st->num_lists == 1 && nprobe == 1), "a probe table is required unless the store has one list");
+    QK_REQUIRE(probe_lists || flat || (ex.id_to_slot && ex.table_size > 0), "probe ids need an id -> slot table");
     ScanPlan p;
-    int rc = make_plan(st, Q, nprobe, k, &p);
+    int rc = make_plan(st, Q, nprobe, k, &p, /*allow_dense=*/flat);  // the dense key matrix is indexed by (query, row of THE list)
     if (rc) return rc;
     QK_REQUIRE(q_pitch >= p.dp && q_pitch % 4 == 0, "query pitch %lld must be a multiple of 4 and >= %d",
                (long long)q_pitch, p.dp);
@@ -1619,47 +1264,47 @@ int qk::scan_partitions_impl(const qk_store_t* st, const float* queries, int64_t
     uint64_t* qbuf = (uint64_t*)(ws + p.off_qbuf);
     const int S = st->num_segments;
     const int64_t QP = Q * p.P;
+    const bool ip = metric == QK_METRIC_INNER_PRODUCT;
+    const bool use_mma = (g_scan_variant == 0) && p.dp <= 128;
 
     // seg_count, seg_fill, flags, qcount, ctrl are contiguous: one memset; candidate slots start as +inf
     QK_CUDA(cudaMemsetAsync(ws + p.off_seg_count, 0, p.off_seg_start - p.off_seg_count, stream));
     if (!p.dense) QK_CUDA(cudaMemsetAsync(qbuf, 0xff, (size_t)Q * p.qcap * 8, stream));
-    const bool single = (p.P == nprobe);
-    if (single) {
-        int64_t n = Q * nprobe;
-        expand_pairs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(probe_lists, Q, nprobe, p.P, st->list_seg0,
-                                                                              st->list_nseg, st->num_lists, pair_seg,
-                                                                              seg_count, gthr, true);
-    } else if (nprobe == 1) {
-        int64_t n = Q * p.P;
-        expand_pairs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(probe_lists, Q, nprobe, p.P, st->list_seg0,
-                                                                              st->list_nseg, st->num_lists, pair_seg,
-                                                                              seg_count, gthr, false);
+    if (flat) {
+        if (!p.dense) QK_CUDA(cudaMemsetAsync(gthr, 0xff, (size_t)Q * 4, stream));  // KEY_MAX: no threshold yet
     } else {
-        expand_pairs_kernel<<<(unsigned)((Q + 127) / 128), 128, 0, stream>>>(probe_lists, Q, nprobe, p.P, st->list_seg0,
-                                                                              st->list_nseg, st->num_lists, pair_seg,
-                                                                              seg_count, gthr, false);
+        ProbeSource ps;
+        ps.slots = probe_lists; ps.ids = ex.probe_ids; ps.id_to_slot = ex.id_to_slot; ps.table_size = ex.table_size;
+        ps.shard_rank = ex.shard_rank; ps.shard_world = ex.shard_world;
+        const bool single = (p.P == nprobe);
+        if (single) {
+            int64_t n = Q * nprobe;
+            expand_pairs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(ps, Q, nprobe, p.P, st->list_seg0, st->list_nseg,
+                                                                                  st->num_lists, pair_seg, seg_count, gthr, true);
+        } else if (nprobe == 1) {
+            int64_t n = Q * p.P;
+            expand_pairs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(ps, Q, nprobe, p.P, st->list_seg0, st->list_nseg,
+                                                                                  st->num_lists, pair_seg, seg_count, gthr, false);
+        } else {
+            expand_pairs_kernel<<<(unsigned)((Q + 127) / 128), 128, 0, stream>>>(ps, Q, nprobe, p.P, st->list_seg0, st->list_nseg,
+                                                                                  st->num_lists, pair_seg, seg_count, gthr, false);
+        }
+        QK_LAUNCHED();
     }
-    QK_CUDA(cudaGetLastError());
     // The seeds only need the pair table; the grouping kernels (prefix, scatter) only the histogram: run them side by
     // side (fork / join through a second stream -- inside a CUDA-graph capture this becomes two parallel branches).
-    bool forked = false;
+    SideStream* side = nullptr;
     cudaStream_t seed_stream = stream;
-    if (p.sample) {
-        if (!g_side_stream) {
-            QK_CUDA(cudaStreamCreateWithFlags(&g_side_stream, cudaStreamNonBlocking));
-            QK_CUDA(cudaEventCreateWithFlags(&g_ev_fork, cudaEventDisableTiming));
-            QK_CUDA(cudaEventCreateWithFlags(&g_ev_join, cudaEventDisableTiming));
-        }
-        QK_CUDA(cudaEventRecord(g_ev_fork, stream));
-        QK_CUDA(cudaStreamWaitEvent(g_side_stream, g_ev_fork, 0));
-        seed_stream = g_side_stream;
-        forked = true;
+    const bool forked = p.sample && !flat;  // flat mode has no grouping kernels to overlap with
+    if (forked) {
+        if ((rc = side_stream_for_current_device(&side))) return rc;
+        QK_CUDA(cudaEventRecord(side->fork, stream));
+        QK_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0));
+        seed_stream = side->stream;
     }
     if (p.sample) {
         const int sample = p.sample;
-        const bool mma_path = (g_scan_variant == 0) && p.dp <= 128;
-        const float rel_margin = 4.f * (float)(st->d + 8) * 5.9604645e-08f + (mma_path ? 4.f * 7.62939453125e-06f : 0.f);
-        const bool ip = metric == QK_METRIC_INNER_PRODUCT;
+        const float rel_margin = 4.f * (float)(st->d + 8) * 5.9604645e-08f + (use_mma ? 4.f * 7.62939453125e-06f : 0.f);
         if (p.flat_seed) {
             // the single list's first rows (its segments are consecutive in the arena); host-known geometry
             if (st->flat_rows > 0) {
@@ -1672,43 +1317,53 @@ int qk::scan_partitions_impl(const qk_store_t* st, const float* queries, int64_t
                 else
                     seed_scores_flat_kernel<false><<<grid, 256, 0, seed_stream>>>(st->vectors, st->pitch, st->row_norms, st->d, queries,
                                                                              q_pitch, Q, st->flat_row0, (int)st->flat_rows, sample, skeys);
-                QK_CUDA(cudaGetLastError());
+                QK_LAUNCHED();
                 seed_select_flat_kernel<<<(unsigned)((Q + 7) / 8), 256, 0, seed_stream>>>(skeys, sample, have, queries, q_pitch, st->d, Q,
-                                                                                     p.kc, st->max_row_norm, rel_margin, gthr);
-                QK_CUDA(cudaGetLastError());
+                                                                                     p.kc, st->max_row_norm, ex.max_row_norm_dev,
+                                                                                     rel_margin, gthr);
+                QK_LAUNCHED();
             }
-        } else {
-            const size_t ssm = (size_t)2 * (p.dp + sample) * sizeof(float);
-            const unsigned grid = (unsigned)((Q + 1) / 2);
+        } else if (!flat) {
+            const size_t ssm = seed_smem_bytes(p.dp, sample);
+            const unsigned grid = (unsigned)Q;
+            if ((rc = ip ? ensure_smem(seed_thresholds_kernel<true>, ssm) : ensure_smem(seed_thresholds_kernel<false>, ssm))) return rc;
             if (ip)
                 seed_thresholds_kernel<true><<<grid, 256, ssm, seed_stream>>>(st->vectors, st->pitch, st->row_norms, st->d, p.dp,
                                                                          queries, q_pitch, Q, pair_seg, p.P, st->seg_row0,
-                                                                         st->seg_rows, p.kc, sample, st->max_row_norm,
-                                                                         rel_margin, gthr);
+                                                                         st->seg_rows, p.kc, sample, seed_chunk_rows(p.dp, sample),
+                                                                         st->max_row_norm, rel_margin, gthr);
             else
                 seed_thresholds_kernel<false><<<grid, 256, ssm, seed_stream>>>(st->vectors, st->pitch, st->row_norms, st->d, p.dp,
                                                                           queries, q_pitch, Q, pair_seg, p.P, st->seg_row0,
-                                                                          st->seg_rows, p.kc, sample, st->max_row_norm,
-                                                                          rel_margin, gthr);
-            QK_CUDA(cudaGetLastError());
+                                                                          st->seg_rows, p.kc, sample, seed_chunk_rows(p.dp, sample),
+                                                                          st->max_row_norm, rel_margin, gthr);
+            QK_LAUNCHED();
         }
     }
-    if (forked) QK_CUDA(cudaEventRecord(g_ev_join, g_side_stream));
-    prefix_segments_kernel<<<1, 1024, 0, stream>>>(seg_count, S, p.gq, seg_start, item_start, ctrl);
-    QK_CUDA(cudaGetLastError());
-    {
+    if (forked) QK_CUDA(cudaEventRecord(side->join, side->stream));
+    ScanArgs sa;
+    memset(&sa, 0, sizeof(sa));
+    if (!flat) {
+        prefix_segments_kernel<<<1, 1024, 0, stream>>>(seg_count, S, p.gq, seg_start, item_start, ctrl);
+        QK_LAUNCHED();
         int64_t n = QP > S ? QP : S;
         scatter_pairs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(pair_seg, QP, S, seg_start, seg_fill,
                                                                                seg_pairs, item_start, st->seg_row0,
                                                                                st->seg_rows, p.gq, items);
-        QK_CUDA(cudaGetLastError());
+        QK_LAUNCHED();
+    } else {
+        sa.flat = 1;
+        sa.flat_nchunks = (int)((Q + p.gq - 1) / p.gq);
+        const int64_t n_items = (int64_t)S * sa.flat_nchunks;
+        QK_REQUIRE(n_items < ((int64_t)1 << 31), "too many work items; split the query batch");
+        sa.flat_items = (int)n_items;
     }
-    ScanArgs sa;
     sa.norms = st->row_norms; sa.dp = p.dp;
     sa.queries = queries; sa.q_pitch = q_pitch;
     sa.seg_pairs = seg_pairs; sa.items = items; sa.ctrl = ctrl;
     sa.gthr = gthr; sa.qcount = qcount; sa.qbuf = qbuf;
     sa.P = p.P; sa.kc = p.kc; sa.gq = p.gq; sa.nq = p.nq; sa.qcap = p.qcap;
+    sa.Q = Q; sa.seg_row0 = st->seg_row0; sa.seg_rows = st->seg_rows;
     {
         static int dbg = -1;
         if (dbg < 0) { const char* e = getenv("QK_SCAN_DBG"); dbg = e ? atoi(e) : 0; }
@@ -1717,14 +1372,12 @@ int qk::scan_partitions_impl(const qk_store_t* st, const float* queries, int64_t
         sa.dense_row0 = st->flat_row0;
         sa.dense_rows = (int)st->flat_rows;
     }
-    if (forked) QK_CUDA(cudaStreamWaitEvent(stream, g_ev_join, 0));
+    if (forked) QK_CUDA(cudaStreamWaitEvent(stream, side->join, 0));
     CUtensorMap vmap;
     // d <= 128: tensor-core filter (tcgen05, 3xTF32 split); otherwise the FP32-pipe kernel. QK_SCAN_PATH=ffma
     // forces the latter (tests cross-check the two).
-    const bool use_mma = (g_scan_variant == 0) && p.dp <= 128;
     rc = make_row_tensor_map(st, use_mma ? MMA_TM : SCAN_TV, &vmap);
     if (rc) return rc;
-    sa.norms = st->row_norms;
     ProfileRecord* rec = nullptr;
     if (g_prof && g_prof_n < g_prof_cap) {
         rec = &g_prof[g_prof_n++];
@@ -1734,57 +1387,123 @@ int qk::scan_partitions_impl(const qk_store_t* st, const float* queries, int64_t
     rc = launch_scan(sa, vmap, metric, p.smem, use_mma, stream);
     if (rc) return rc;
     if (rec) QK_CUDA(cudaEventRecord(rec->stop, stream));
-    if (p.dense) {
-        const size_t dsm = (size_t)st->flat_rows * sizeof(uint32_t);
-        if (dsm > 48 * 1024)
-            QK_CUDA(cudaFuncSetAttribute(dense_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm));
-        dense_select_kernel<<<(unsigned)Q, 256, dsm, stream>>>(sa.dense, (int)st->flat_rows, st->flat_row0, p.kc, p.qcap, gthr,
-                                                               qcount, qbuf);
-        QK_CUDA(cudaGetLastError());
-    }
 
     MergeArgs ma;
+    memset(&ma, 0, sizeof(ma));
     ma.vecs = st->vectors; ma.pitch = st->pitch; ma.ids = st->ids; ma.d = st->d;
-    ma.seg_row0 = st->seg_row0; ma.queries = queries; ma.q_pitch = q_pitch;
-    ma.pair_seg = pair_seg; ma.gthr = gthr; ma.qbuf = qbuf; ma.qcount = qcount; ma.qcap = p.qcap;
+    ma.seg_row0 = st->seg_row0; ma.seg_rows = st->seg_rows; ma.queries = queries; ma.q_pitch = q_pitch;
+    ma.pair_seg = pair_seg; ma.flat_nseg = flat ? S : 0;
+    ma.gthr = gthr; ma.qbuf = qbuf; ma.qcount = qcount; ma.qcap = p.qcap;
     ma.flags = flags; ma.ctrl = ctrl; ma.P = p.P; ma.kc = p.kc; ma.k = k;
     ma.max_row_norm = st->max_row_norm;
+    ma.max_row_norm_dev = ex.max_row_norm_dev;
     // 3xTF32 dot products: measured ~2^-20 of sum|q_i v_i| (scripts/umma_probe.cu); bounded here by 2^-17 |q||v|
     ma.filter_gam = use_mma ? 7.62939453125e-06 : 0.0;
     ma.out_ids = out_ids; ma.out_dist = out_dist; ma.out_rows = out_rows;
     ma.force_rescan = g_force_rescan;
-    ma.seg_rows = st->seg_rows;
-    ma.rank_squared = rank_squared;
-    {
-        int kcp = 1;
-        while (kcp < p.kc) kcp <<= 1;
-        // the sort buffer never needs more than the candidate buffer holds; small buffers let more CTAs share an SM
+    ma.rank_squared = ex.rank_squared;
+    const int kcp = next_pow2(p.kc);
+    if (p.dense) {
+        ma.dense = sa.dense; ma.dense_rows = (int)st->flat_rows; ma.dense_row0 = st->flat_row0;
+        const size_t dsm = (size_t)((st->flat_rows + 1) & ~(int64_t)1) * 4 + refine_tail_bytes(st->d, kcp);
+        if (ip) {
+            if ((rc = ensure_smem(dense_refine_kernel<true>, dsm))) return rc;
+            dense_refine_kernel<true><<<(unsigned)Q, MERGE_THREADS, dsm, stream>>>(ma);
+        } else {
+            if ((rc = ensure_smem(dense_refine_kernel<false>, dsm))) return rc;
+            dense_refine_kernel<false><<<(unsigned)Q, MERGE_THREADS, dsm, stream>>>(ma);
+        }
+    } else {
+        // the gather buffer never needs more than the candidate buffer holds; small buffers let more CTAs share an SM
         int sort_cap = MERGE_SORT_CAP;
         while (sort_cap / 2 >= p.qcap && sort_cap > 256) sort_cap >>= 1;
+        if (sort_cap < kcp) sort_cap = kcp;
         ma.sort_cap = sort_cap;
-        size_t msmem = (size_t)sort_cap * 8 + (size_t)((st->d + 3) & ~3) * 4 + (size_t)kcp * (8 + 8 + 4) + 16;
-        if (metric == QK_METRIC_INNER_PRODUCT) {
-            QK_CUDA(cudaFuncSetAttribute(merge_refine_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem));
+        const size_t msmem = (size_t)sort_cap * 8 + refine_tail_bytes(st->d, kcp);
+        if (ip) {
+            if ((rc = ensure_smem(merge_refine_kernel<true>, msmem))) return rc;
             merge_refine_kernel<true><<<(unsigned)Q, MERGE_THREADS, msmem, stream>>>(ma);
         } else {
-            QK_CUDA(cudaFuncSetAttribute(merge_refine_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem));
+            if ((rc = ensure_smem(merge_refine_kernel<false>, msmem))) return rc;
             merge_refine_kernel<false><<<(unsigned)Q, MERGE_THREADS, msmem, stream>>>(ma);
         }
-        QK_CUDA(cudaGetLastError());
-        int kp = 1;
-        while (kp < k) kp <<= 1;
-        size_t rsmem = (size_t)((st->d + 3) & ~3) * 4 + 32 + (size_t)kp * (8 + 8 + 4);
-        if (metric == QK_METRIC_INNER_PRODUCT) {
-            QK_CUDA(cudaFuncSetAttribute(exact_rescan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem));
-            exact_rescan_kernel<true><<<(unsigned)Q, 256, rsmem, stream>>>(ma, st->seg_rows);
-        } else {
-            QK_CUDA(cudaFuncSetAttribute(exact_rescan_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem));
-            exact_rescan_kernel<false><<<(unsigned)Q, 256, rsmem, stream>>>(ma, st->seg_rows);
-        }
-        QK_CUDA(cudaGetLastError());
     }
+    QK_LAUNCHED();
     if (stats) QK_CUDA(cudaMemcpyAsync(stats, ctrl + 2, 4 * sizeof(int32_t), cudaMemcpyDeviceToDevice, stream));
     return QK_OK;
+}
+
+// ---- two-level fixed-nprobe search in one call ------------------------------------------------------
+namespace {
+struct IvfLayout {
+    size_t off_pids, off_pdist, off_scan, coarse_bytes, part_bytes, total;
+    int np;  // partitions probed per query = min(nprobe, number of centroids)
+};
+int ivf_layout(const qk_store_t* parent, const qk_store_t* store, int64_t Q, int nprobe, int k, IvfLayout* L) {
+    QK_REQUIRE(parent && store && Q > 0 && nprobe > 0, "bad argument");
+    QK_REQUIRE(parent->num_lists == 1 && parent->flat_rows > 0, "the parent must be a flat (single-list) store");
+    L->np = (int)(nprobe < parent->flat_rows ? nprobe : parent->flat_rows);
+    L->coarse_bytes = qk_scan_workspace_bytes(parent, Q, 1, L->np);
+    L->part_bytes = store->num_segments > 0 ? qk_scan_workspace_bytes(store, Q, L->np, k) : 256;
+    if (L->coarse_bytes == 0 || L->part_bytes == 0) return QK_ERR_INVALID_ARGUMENT;
+    size_t o = 0;
+    L->off_pids = o;  o = align_up(o + (size_t)Q * L->np * 8, 256);
+    L->off_pdist = o; o = align_up(o + (size_t)Q * L->np * 4, 256);
+    L->off_scan = o;  o += L->coarse_bytes > L->part_bytes ? L->coarse_bytes : L->part_bytes;
+    L->total = o;
+    return QK_OK;
+}
+__global__ void fill_empty_result_kernel(int64_t n, int64_t* ids, float* dist, float pad) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { ids[i] = -1; dist[i] = pad; }
+}
+}  // namespace
+
+extern "C" size_t qk_search_ivf_workspace_bytes(const qk_store_t* parent, const qk_store_t* store, int64_t num_queries,
+                                                int nprobe, int k) {
+    IvfLayout L;
+    if (ivf_layout(parent, store, num_queries, nprobe, k, &L) != QK_OK) return 0;
+    return L.total;
+}
+
+extern "C" int qk_search_ivf(const qk_store_t* parent, const qk_store_t* store, const int32_t* id_to_slot,
+                             int64_t table_size, const float* queries, int64_t Q, int64_t q_pitch, int nprobe,
+                             int metric, int k, int shard_rank, int shard_world, int64_t* out_ids, float* out_dist,
+                             int64_t* out_probe_ids, void* workspace, size_t workspace_bytes, int32_t* stats,
+                             void* stream_v) {
+    cudaStream_t stream = (cudaStream_t)stream_v;
+    IvfLayout L;
+    int rc = ivf_layout(parent, store, Q, nprobe, k, &L);
+    if (rc) return rc;
+    QK_REQUIRE(id_to_slot && table_size > 0 && queries && out_ids && out_dist, "null argument");
+    if (!workspace || workspace_bytes < L.total) {
+        set_error("workspace too small: need %zu bytes, have %zu", L.total, workspace_bytes);
+        return QK_ERR_WORKSPACE;
+    }
+    char* ws = (char*)workspace;
+    int64_t* p_ids = out_probe_ids ? out_probe_ids : (int64_t*)(ws + L.off_pids);
+    float* p_dist = (float*)(ws + L.off_pdist);
+    // 1. coarse centroid scan (query_coordinator.cpp:644): top-np centroids per query, nearest first; flat mode
+    ScanExtras cx;
+    rc = scan_partitions_impl(parent, queries, Q, q_pitch, nullptr, 1, metric, L.np, p_ids, p_dist, nullptr, ws + L.off_scan,
+                              L.coarse_bytes, nullptr, stream, cx);
+    if (rc) return rc;
+    if (store->num_segments == 0) {  // every list is empty: padded results (query_coordinator.cpp:589-601)
+        const int64_t n = Q * k;
+        fill_empty_result_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(
+            n, out_ids, out_dist, metric == QK_METRIC_INNER_PRODUCT ? -INFINITY : INFINITY);
+        QK_LAUNCHED();
+        return QK_OK;
+    }
+    // 2. partition scan of the probed lists; the id -> slot map (and the shard filter) run inside the pair expansion
+    ScanExtras px;
+    px.probe_ids = p_ids;
+    px.id_to_slot = id_to_slot;
+    px.table_size = table_size;
+    px.shard_rank = shard_rank;
+    px.shard_world = shard_world < 1 ? 1 : shard_world;
+    return scan_partitions_impl(store, queries, Q, q_pitch, nullptr, L.np, metric, k, out_ids, out_dist, nullptr,
+                                ws + L.off_scan, L.part_bytes, stats, stream, px);
 }
 
 // ---- per-launch timing of the filter kernel ------------------------------------------------------

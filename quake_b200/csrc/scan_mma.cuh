@@ -16,17 +16,20 @@
 // MMAs per K-step instead of three (the single issuing thread is the scarce resource, not the tensor pipe).
 //
 // Roles (16 warps, one persistent CTA per SM):
-//   warp 0      producer: work items (atomic counter, metadata pipelined), TMA tensor loads of the row tiles
-//               (box 128 rows x 32 floats, ring of 8)
-//   warp 1      MMA issuer (one lane): 2 MMAs per K-step, tcgen05.commit onto the pipeline mbarriers
+//   warp 0      producer: work items (atomic counter, metadata pipelined; or the arithmetic grid of a flat-mode scan),
+//               TMA tensor loads of the row tiles (box 128 rows x 32 floats, ring of 8)
+//   warps 1, 15 MMA issuers (alternate tiles, one elected lane each): per row box the a_hi products
+//               a_hi . [b_hi | b_lo] (N = 2 npad, A from shared memory) as soon as the TMA data has landed, then
+//               a_lo . b_hi (N = npad, A from tensor memory) once the split warps delivered a_lo; tcgen05.commit onto
+//               the pipeline mbarriers. npad = the item's query slots padded to 16 or 32
 //   warps 2-5   split: a_lo = a - trunc(a) -> tensor memory; gather of the item's query chunk (prefetched one item
 //               ahead) into the swizzled K-major B tiles, b_hi and b_lo
 //   warps 6-13  epilogue + selection, two groups of four taking alternate tiles: tcgen05.ld of the
-//               accumulators (thread = row, 32 queries in registers), score vs the query's threshold in the
+//               accumulators (thread = row, npad query scores in registers), score vs the query's threshold in the
 //               float domain (one FFMA + one compare per score), thread-level append of the rare survivors to the
 //               per-query candidate buffers (one global atomic per survivor, issued in batches of four)
-//   warps 14-15 threshold refresh, off the critical path: when a query's fill passes a multiple of 64 the
-//               appending thread posts (query, fill) in its warp's mailbox; a refresh warp re-derives the
+//   warp 14     threshold refresh, off the critical path: when a query's fill passes a multiple of 64 the
+//               appending thread posts (query, fill) in its warp's mailbox; the refresh warp re-derives the
 //               kc-th smallest key appended so far (radix select over the buffer) and publishes it with atomicMin
 #pragma once
 
@@ -210,7 +213,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) scan_mma_kernel(const ScanArgs
         // index -> item -> query ids -> thresholds is consumed one iteration after it was issued, so none of them
         // is waited for. The descriptor of item n+1 is published BEFORE the row tiles of item n are issued, so
         // the split warps can prefetch its query chunk (B operand) while item n streams.
-        const int n_items = a.ctrl[1];
+        const int n_items = a.flat ? a.flat_items : a.ctrl[1];
         auto fetch_index = [&]() {  // lane 0 holds the result; broadcast where it is consumed
             int it = 0;
             if (lane == 0) it = atomicAdd(&a.ctrl[0], 1);
@@ -219,11 +222,22 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) scan_mma_kernel(const ScanArgs
         auto fetch_item = [&](int it) {
             WorkItem w;
             w.seg = -1; w.g_begin = 0; w.g_cnt = 0; w.nrows = 0; w.row0 = 0; w.pad_ = 0;
-            if (it < n_items) w = a.items[it];
+            if (it < n_items) {
+                if (a.flat) {  // the grid (segment x query chunk), chunk fastest: concurrent CTAs share the segment's rows
+                    flat_item(a, it, w.seg, w.g_begin, w.g_cnt);
+                    w.nrows = a.seg_rows[w.seg];
+                    w.row0 = a.seg_row0[w.seg];
+                } else {
+                    w = a.items[it];
+                }
+            }
             return w;
         };
         // query index of this lane's slot (the pair index is query * P + slot)
-        auto fetch_query = [&](const WorkItem& w) { return (w.seg >= 0 && lane < w.g_cnt) ? a.seg_pairs[w.g_begin + lane] / a.P : -1; };
+        auto fetch_query = [&](const WorkItem& w) {
+            if (w.seg < 0 || lane >= w.g_cnt) return -1;
+            return a.flat ? w.g_begin + lane : a.seg_pairs[w.g_begin + lane] / a.P;
+        };
         auto fetch_gthr = [&](int q) { return q >= 0 ? __ldcg(a.gthr + q) : KEY_MAX; };
         // descriptor of item n; false when n is past the last item (the sentinel is published instead)
         auto issue_desc_b = [&](uint32_t n, const WorkItem& m, int q, uint32_t gthr) {
@@ -287,8 +301,6 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) scan_mma_kernel(const ScanArgs
         // row boxes and the accumulator of a tile are released by the issuer that consumed them, the B slot of an item
         // by both (count 2).
         const int mi = warp == 1 ? 0 : 1;
-        constexpr uint32_t IDESC64 = umma_idesc_tf32(MMA_TM, 2 * MMA_NQ);  // a_hi . [b_hi | b_lo]
-        constexpr uint32_t IDESC32 = umma_idesc_tf32(MMA_TM, MMA_NQ);      // a_lo . b_hi
         uint32_t T = 0, U = 0;
         for (uint32_t n = 0;; ++n) {
             const int ib = n % NB, id = n % ND;
@@ -297,6 +309,10 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) scan_mma_kernel(const ScanArgs
             if (d.seg < 0) break;
             __syncwarp();
             if (lane == 0) mbar_arrive(i_empty + id);  // only the descriptor header was needed
+            // query slots padded to 16 or 32: b_hi in rows [0, npad) of every B box, b_lo in rows [npad, 2 npad)
+            const int npad = (d.g_cnt <= 16 && !QK_DBG(a, 16)) ? 16 : 32;
+            const uint32_t idesc_hl = umma_idesc_tf32(MMA_TM, 2 * npad);  // a_hi . [b_hi | b_lo]
+            const uint32_t idesc_h = umma_idesc_tf32(MMA_TM, npad);       // a_lo . b_hi
             mbar_wait(b_ready + ib, (n / NB) & 1u);
             const uint32_t bs = smem_u32(Bs + (size_t)ib * 4 * MMA_BBOX_BYTES);
             const int ntiles = (d.nrows + TM - 1) / TM;
@@ -307,18 +323,32 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) scan_mma_kernel(const ScanArgs
                 const uint32_t tmem_d = tmem + MMA_TMEM_D + db * (2 * MMA_NQ);
                 for (int b = 0; b < nbox; ++b, ++U) {
                     const int st = U % NS;
-                    // the split warps waited for the TMA data of this box themselves: a_lo ready => a_hi ready
-                    mbar_wait(alo_full + st, (U / NS) & 1u);
-                    tc_fence_after();
                     const uint64_t da0 = umma_desc_sw128(smem_u32(As + (size_t)st * MMA_BOX_BYTES));
                     const uint64_t db0 = umma_desc_sw128(bs + b * MMA_BBOX_BYTES);
                     const uint32_t talo = tmem + MMA_TMEM_ALO + st * MMA_BOX;
                     const int ksteps = min(4, (dp - b * MMA_BOX + 7) >> 3);
+                    if (QK_DBG(a, 8)) {
+                        // the a_hi products only need the TMA data: they run while the split warps still derive a_lo
+                        mbar_wait(a_full + st, (U / NS) & 1u);
+                        tc_fence_after();
 #pragma unroll
-                    for (int kk = 0; kk < 4; ++kk) {
-                        if (kk < ksteps && !(a.dbg & 2)) {  // a K-step advances both start addresses by 32 B (2 descriptor units)
-                            umma_ss(tmem_d, da0 + 2 * kk, db0 + 2 * kk, IDESC64, (b | kk) ? 1u : 0u);
-                            umma_ts(tmem_d, talo + kk * 8, db0 + 2 * kk, IDESC32, 1u);
+                        for (int kk = 0; kk < 4; ++kk)  // a K-step advances both start addresses by 32 B (2 descriptor units)
+                            if (kk < ksteps) umma_ss(tmem_d, da0 + 2 * kk, db0 + 2 * kk, idesc_hl, (b | kk) ? 1u : 0u);
+                        mbar_wait(alo_full + st, (U / NS) & 1u);
+                        tc_fence_after();
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk)
+                            if (kk < ksteps) umma_ts(tmem_d, talo + kk * 8, db0 + 2 * kk, idesc_h, 1u);
+                    } else {
+                        // the split warps waited for the TMA data of this box themselves: a_lo ready => a_hi ready
+                        mbar_wait(alo_full + st, (U / NS) & 1u);
+                        tc_fence_after();
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk) {
+                            if (kk < ksteps && !(QK_DBG(a, 2))) {  // a K-step advances both start addresses by 32 B (2 descriptor units)
+                                umma_ss(tmem_d, da0 + 2 * kk, db0 + 2 * kk, idesc_hl, (b | kk) ? 1u : 0u);
+                                umma_ts(tmem_d, talo + kk * 8, db0 + 2 * kk, idesc_h, 1u);
+                            }
                         }
                     }
                     umma_commit(a_empty + st);  // the row box (and its a_lo columns) may be refilled
@@ -365,14 +395,17 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) scan_mma_kernel(const ScanArgs
             mbar_wait(b_empty + ib, ((n / NB) & 1u) ^ 1u);  // the MMAs of item n - NB have completed
             if (c_used) {
                 unsigned char* bs = Bs + (size_t)ib * 4 * MMA_BBOX_BYTES + (size_t)(lane >> 3) * MMA_BBOX_BYTES;
+                const int npad = (d.g_cnt <= 16 && !QK_DBG(a, 16)) ? 16 : 32;
+                // slots g_cnt .. npad-1 are read by the MMA too: whatever an earlier item left there is finite query
+                // data (or the zeros of the first fill below), and their scores are masked in the epilogue
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const int g = 4 * j + sw;
-                    if (g < d.g_cnt) {
+                    if (g < d.g_cnt || (n < (uint32_t)NB && g < npad)) {
                         unsigned char* hp = bs + g * 128 + (((lane & 7) ^ (g & 7)) << 4);
-                        const float4 x = bq[j];
+                        const float4 x = g < d.g_cnt ? bq[j] : make_float4(0.f, 0.f, 0.f, 0.f);
                         *reinterpret_cast<float4*>(hp) = x;
-                        *reinterpret_cast<float4*>(hp + MMA_NQ * 128) =
+                        *reinterpret_cast<float4*>(hp + npad * 128) =
                             make_float4(tf32_lo(x.x), tf32_lo(x.y), tf32_lo(x.z), tf32_lo(x.w));
                     }
                 }
@@ -390,7 +423,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) scan_mma_kernel(const ScanArgs
                     mbar_wait(a_full + st, (U / NS) & 1u);
                     const unsigned char* rowp = As + (size_t)st * MMA_BOX_BYTES + r * 128;
                     uint32_t v[32];
-                    if (!(a.dbg & 4))
+                    if (!(QK_DBG(a, 4)))
 #pragma unroll
                     for (int cc = 0; cc < 8; ++cc) {
                         const float4 x = *reinterpret_cast<const float4*>(rowp + ((cc ^ (r & 7)) << 4));
@@ -399,7 +432,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) scan_mma_kernel(const ScanArgs
                         v[4 * cc + 2] = __float_as_uint(tf32_lo(x.z));
                         v[4 * cc + 3] = __float_as_uint(tf32_lo(x.w));
                     }
-                    if (!(a.dbg & 4)) tmem_st32(tmem + MMA_TMEM_ALO + st * MMA_BOX + ((uint32_t)(q4 * 32) << 16), v);
+                    if (!(QK_DBG(a, 4))) tmem_st32(tmem + MMA_TMEM_ALO + st * MMA_BOX + ((uint32_t)(q4 * 32) << 16), v);
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) { mbar_arrive(alo_full + st); mbar_arrive(a_empty + st); }
@@ -419,6 +452,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) scan_mma_kernel(const ScanArgs
             const WorkItem d = descs[id].w;
             if (d.seg < 0) break;
             const int g_cnt = d.g_cnt;
+            const int npad = (g_cnt <= 16 && !QK_DBG(a, 16)) ? 16 : 32;
             const uint32_t gvalid = g_cnt >= 32 ? 0xffffffffu : ((1u << g_cnt) - 1u);
             const int* dq = descs[id].q;
             float* limf = descs[id].limf;
@@ -435,27 +469,34 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) scan_mma_kernel(const ScanArgs
                 const int db = T % MMA_NACC;  // group eg sees the buffers with db & 1 == eg
                 mbar_wait(d_full + db, (T / MMA_NACC) & 1u);
                 tc_fence_after();
-                uint32_t v[32];  // dot = (a_hi + a_lo) . b_hi [columns 0-31] + a_hi . b_lo [columns 32-63]
+                // dot = (a_hi + a_lo) . b_hi [columns 0 .. npad-1] + a_hi . b_lo [columns npad .. 2 npad - 1]
+                uint32_t v[32];
                 {
                     const uint32_t td = tmem + MMA_TMEM_D + db * (2 * MMA_NQ) + ((uint32_t)(q4 * 32) << 16);
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
-                        uint32_t x[16], y[16];
-                        tmem_ld16_nowait(td + h * 16, x);
-                        tmem_ld16_nowait(td + MMA_NQ + h * 16, y);
-                        tmem_ld_wait();
+                        if (h * 16 < npad) {  // warp-uniform
+                            uint32_t x[16], y[16];
+                            tmem_ld16_nowait(td + h * 16, x);
+                            tmem_ld16_nowait(td + npad + h * 16, y);
+                            tmem_ld_wait();
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) v[h * 16 + i] = __float_as_uint(__uint_as_float(x[i]) + __uint_as_float(y[i]));
+                            for (int i = 0; i < 16; ++i) v[h * 16 + i] = __float_as_uint(__uint_as_float(x[i]) + __uint_as_float(y[i]));
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) v[h * 16 + i] = 0u;
+                        }
                     }
                 }
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(d_empty + db);
-                if (a.dbg & 1) continue;
+                if (QK_DBG(a, 1)) continue;
                 // ---- scores of this thread's row against the 32 query slots; bit g of pm: the score passes
                 uint32_t pm = 0;
 #pragma unroll
                 for (int g4 = 0; g4 < 8; ++g4) {
+                    if (4 * g4 >= npad) break;  // warp-uniform: only the padded slot count is scored
                     const float4 L = reinterpret_cast<const float4*>(limf)[g4];
                     const float lim[4] = {L.x, L.y, L.z, L.w};
 #pragma unroll

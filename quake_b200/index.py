@@ -45,6 +45,12 @@ GRAPHS_ENABLED = os.environ.get("QK_GRAPH", "1") != "0"
 _MAX_PLANS = 8
 _GRAPH_MAX_Q = 16384  # larger batches run eagerly: their launches are long, and a plan pins its whole workspace
 _capturing = False
+GRAPH_LAUNCHES = 0  # kernels of ours launched through graph replays (qk_launch_count() only sees host-side launches)
+
+
+def launch_count() -> int:
+    """Kernels of this library launched so far: host-side launches + those inside replayed CUDA graphs."""
+    return int(_lib.load().qk_launch_count()) + GRAPH_LAUNCHES
 
 
 class _SearchPlan:
@@ -64,9 +70,12 @@ class _SearchPlan:
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
             self.graph = torch.cuda.CUDAGraph()
+            lib = _lib.load()
+            n0 = lib.qk_launch_count()
             # thread_local: other threads (e.g. the NCCL watchdog of a multi-rank job) may touch the CUDA runtime
             with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
                 self.ids, self.dist, self.p_ids = index._search_core(self.xq, sp)
+            self.launches = int(lib.qk_launch_count() - n0)  # kernels of ours one replay launches
         finally:
             _capturing = False
         # everything outside the graph's private pool whose address the graph baked in lives as long as the plan: the
@@ -80,15 +89,23 @@ class _SearchPlan:
         if xq.data_ptr() != self.xq.data_ptr():
             self.xq.copy_(xq, non_blocking=True)
         self.graph.replay()
+        global GRAPH_LAUNCHES
+        GRAPH_LAUNCHES += self.launches
         return self.ids, self.dist, self.p_ids
 
 
-def scan_partitions(store: PartitionStore, xq: torch.Tensor, probe_slots: torch.Tensor, k: int, metric: int,
+def scan_partitions(store: PartitionStore, xq: torch.Tensor, probe_slots: torch.Tensor | None, k: int, metric: int,
                     want_rows: bool = False):
-    """qk_scan_partitions over a device query batch xq [Q, pitch] and probe_slots [Q, nprobe] (int32).
+    """qk_scan_partitions over a device query batch xq [Q, pitch] and probe_slots [Q, nprobe] (int32), or None for a
+    single-list store (flat mode: every query scans the whole list, no probe table, no grouping kernels).
     Returns (ids [Q,k] int64, distances [Q,k] float32[, rows]) on the device."""
     lib = _lib.load()
-    Q, nprobe = int(probe_slots.shape[0]), int(probe_slots.shape[1])
+    if probe_slots is None:
+        if store.slot_pid.size != 1:
+            raise RuntimeError("quake_b200: flat-mode scan needs a single-list store")
+        Q, nprobe = int(xq.shape[0]), 1
+    else:
+        Q, nprobe = int(probe_slots.shape[0]), int(probe_slots.shape[1])
     st, _ = store.tables(store.segment_len(Q, nprobe))
     dev = xq.device
     out_ids = torch.empty((Q, k), dtype=torch.int64, device=dev)
@@ -100,7 +117,8 @@ def scan_partitions(store: PartitionStore, xq: torch.Tensor, probe_slots: torch.
         if want_rows:
             out_rows.fill_(-1)
         return (out_ids, out_dist, out_rows) if want_rows else (out_ids, out_dist)
-    probe_slots = probe_slots.to(torch.int32).contiguous()
+    if probe_slots is not None:
+        probe_slots = probe_slots.to(torch.int32).contiguous()
     # chunk the batch so that the workspace stays bounded
     chunk = Q
     while True:
@@ -119,7 +137,8 @@ def scan_partitions(store: PartitionStore, xq: torch.Tensor, probe_slots: torch.
         stats = LAST_SCAN_STATS = torch.zeros(4, dtype=torch.int32, device=dev)
     for b in range(0, Q, chunk):
         n = min(chunk, Q - b)
-        check(lib.qk_scan_partitions(C.byref(st), ptr(xq[b:]), n, xq.stride(0), ptr(probe_slots[b:]), nprobe, metric, k,
+        check(lib.qk_scan_partitions(C.byref(st), ptr(xq[b:]), n, xq.stride(0),
+                                     ptr(probe_slots[b:]) if probe_slots is not None else None, nprobe, metric, k,
                                      ptr(out_ids[b:]), ptr(out_dist[b:]), ptr(out_rows[b:]) if want_rows else None,
                                      ptr(ws), wsb, ptr(stats), _stream()))
     return (out_ids, out_dist, out_rows) if want_rows else (out_ids, out_dist)
@@ -239,6 +258,8 @@ class QuakeIndex:
     def _flat_probe(self, Q: int) -> torch.Tensor:
         """[Q, nlist] probe table of a flat index: every query scans every partition (query_coordinator.cpp:624-626).
         One tensor per batch size for the current store version; captured plans keep their own reference."""
+        if self.store.slot_pid.size == 1:
+            return None  # flat mode: the scan needs no probe table for a single-list store
         self.store.tables()
         ver = (self.store.uid, self.store.version)
         cache = self.__dict__.setdefault("_flat_probe_cache", {})
@@ -268,6 +289,8 @@ class QuakeIndex:
         if self.parent is None:
             ids, dist = scan_partitions(self.store, xq, self._flat_probe(Q), k, self.metric)
             return ids, dist, None
+        if self.parent.parent is None and self.parent.store.slot_pid.size == 1 and Q <= _GRAPH_MAX_Q:
+            return self._search_ivf(xq, k, int(sp.nprobe))
         psp = SearchParams()
         psp.batched_scan = True
         psp.k = min(int(sp.nprobe), self.nlist())
@@ -277,6 +300,31 @@ class QuakeIndex:
         check(_lib.load().qk_map_ids_to_slots(ptr(p_ids), p_ids.numel(), ptr(table), table.numel(), ptr(slots), _stream()))
         ids, dist = scan_partitions(self.store, xq, slots, k, self.metric)
         return ids, dist, p_ids
+
+    def _search_ivf(self, xq: torch.Tensor, k: int, nprobe: int, shard_rank: int = 0, shard_world: int = 1):
+        """qk_search_ivf: coarse scan of the flat parent -> slot map -> partition scan, one C call, one workspace."""
+        lib = _lib.load()
+        Q = int(xq.shape[0])
+        dev = xq.device
+        pstore = self.parent.store
+        np_ = max(1, min(int(nprobe), pstore.ntotal))
+        pst, _ = pstore.tables(pstore.segment_len(Q, 1))
+        st, table = self.store.tables(self.store.segment_len(Q, np_))
+        wsb = lib.qk_search_ivf_workspace_bytes(C.byref(pst), C.byref(st), Q, np_, k)
+        if wsb == 0:
+            check(1)
+        ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+        out_ids = torch.empty((Q, k), dtype=torch.int64, device=dev)
+        out_dist = torch.empty((Q, k), dtype=torch.float32, device=dev)
+        p_ids = torch.empty((Q, np_), dtype=torch.int64, device=dev)
+        stats = None
+        if os.environ.get("QK_SCAN_STATS") == "1":
+            global LAST_SCAN_STATS
+            stats = LAST_SCAN_STATS = torch.zeros(4, dtype=torch.int32, device=dev)
+        check(lib.qk_search_ivf(C.byref(pst), C.byref(st), ptr(table), table.numel(), ptr(xq), Q, xq.stride(0), np_,
+                                self.metric, k, shard_rank, shard_world, ptr(out_ids), ptr(out_dist), ptr(p_ids), ptr(ws),
+                                wsb, ptr(stats), _stream()))
+        return out_ids, out_dist, p_ids
 
     def _plan(self, Q: int, sp: SearchParams) -> "_SearchPlan":
         plans = self.__dict__.setdefault("_plans", {})

@@ -3,9 +3,15 @@
 One process per GPU (torch.distributed). Partition p lives on rank ``p % world`` -- the round-robin of the
 reference's own partition-to-worker distribution (/root/reference/src/cpp/src/partition_manager.cpp:599-602).
 The centroid (parent) index is replicated: every rank runs the coarse scan for all queries (redundant, cheap),
-scans the probed lists it owns, and the per-rank partial top-k lists are exchanged with ONE all-gather
-(Q * k * 12 bytes per rank) and merged on every rank (qk_merge_topk), exactly what the reference does per core
-with TopkBuffer::batch_add (src/cpp/src/query_coordinator.cpp:167-173). There is no other data-path collective.
+scans the probed lists it owns, and the per-rank partial top-k lists (Q * k * 12 bytes per rank) are exchanged and
+merged on every rank, exactly what the reference does per core with TopkBuffer::batch_add
+(src/cpp/src/query_coordinator.cpp:167-173). There is no other data-path collective.
+
+The exchange is ONE kernel per rank over NVLink peer memory (qk_exchange_merge_topk, csrc/exchange.cu): every rank
+pushes its partial into every peer's buffer with remote stores, signals with one flag per CTA, waits for the peers'
+pushes and merges -- no NCCL call on the query path (NCCL is used once, at set-up, to distribute the CUDA IPC handles
+of the buffers). The per-rank step (coarse scan -> owned-list scan -> exchange + merge) is captured in a CUDA graph
+per (batch size, k, nprobe). QK_EXCHANGE=nccl selects the plain path (two all-gathers + qk_merge_topk) instead.
 
 The result is bit-identical to the unsharded index: a query's answer is the top-k of the union of per-list
 top-k's, and the merge orders by (distance, id) like the single-GPU refine step.
@@ -13,6 +19,7 @@ top-k's, and the merge orders by (distance, id) like the single-GPU refine step.
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -68,6 +75,33 @@ def mask_foreign_probes(partition_ids: torch.Tensor, slots: torch.Tensor, rank: 
     return torch.where(mine & (partition_ids >= 0), slots, torch.full_like(slots, -1))
 
 
+class _ShardPlan:
+    """One captured per-rank step (coarse scan -> owned-list scan -> peer exchange + merge). Every rank captures and
+    replays in lockstep: the warm-up runs and every replay are collective exchanges."""
+
+    def __init__(self, sh: "ShardedQuakeIndex", xq: torch.Tensor, sp: SearchParams):
+        dev = xq.device
+        self.xq = torch.zeros_like(xq)
+        self.xq.copy_(xq)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                sh._step(self.xq, sp)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
+            self.ids, self.dist = sh._step(self.xq, sp)
+        self.keep = (sh.local.store.tables_snapshot(), sh.local.parent.store.tables_snapshot())
+
+    def run(self, xq: torch.Tensor):
+        if xq.data_ptr() != self.xq.data_ptr():
+            self.xq.copy_(xq, non_blocking=True)
+        self.graph.replay()
+        return self.ids, self.dist
+
+
 class ShardedQuakeIndex:
     """A two-level QuakeIndex whose lists are sharded over the ranks of `group`.
 
@@ -83,6 +117,9 @@ class ShardedQuakeIndex:
         self.local = QuakeIndex()  # parent replicated; store holds the owned lists only
         self.metric = 1
         self._ntotal = 0
+        self._peer = {}    # (Q, k) -> (local buffer ptr, ctypes array of world peer pointers)
+        self._plans = {}   # (Q, k, nprobe, store versions) -> captured per-rank step
+        self._peer_failed = None
 
     # ------------------------------------------------------------------ construction
     def shard_from(self, full) -> None:
@@ -195,16 +232,113 @@ class ShardedQuakeIndex:
         # the number of partitions of the whole index = the number of centroids the (flat) parent holds
         return self.local.parent.ntotal() if self.local.parent is not None else 0
 
-    def search_device(self, xq: torch.Tensor, sp: SearchParams):
-        """xq [Q, pitch] on this rank's device (the same queries on every rank) -> merged (ids, distances)."""
+    # ------------------------------------------------------------------ exchange over NVLink peer memory
+    def _use_peer_exchange(self) -> bool:
+        return (self.world > 1 and dist.is_initialized() and self._peer_failed is None
+                and os.environ.get("QK_EXCHANGE", "peer") != "nccl")
+
+    def exchange_kind(self) -> str:
+        if self.world <= 1:
+            return "none (one rank)"
+        if self._use_peer_exchange():
+            return "one kernel per rank over NVLink peer memory (remote stores + flags + merge); no NCCL call"
+        why = f" ({self._peer_failed})" if self._peer_failed else ""
+        return "NCCL all_gather x2 + qk_merge_topk" + why
+
+    def _peer_buffers(self, Q: int, k: int):
+        """Collective, once per (Q, k): allocate this rank's peer buffer, all-gather the CUDA IPC handles, open the
+        peers' buffers. Returns the ctypes array qk_exchange_merge_topk takes."""
+        key = (int(Q), int(k))
+        if key in self._peer:
+            return self._peer[key][1]
+        lib = _lib.load()
+        dev = self.local.store.device
+        nbytes = lib.qk_peer_buffer_bytes(Q, k, self.world)
+        local = C.c_void_p()
+        handle = (C.c_ubyte * 64)()
+        rc = lib.qk_peer_alloc(nbytes, C.byref(local), handle)
+        ok = torch.tensor([1 if rc == 0 else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
+        if int(ok.item()) == 0:
+            raise _lib.QuakeB200Error("peer buffer allocation failed: " + lib.qk_last_error().decode())
+        mine = torch.tensor(list(handle), dtype=torch.uint8, device=dev)
+        allh = torch.empty((self.world, 64), dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(allh, mine, group=self.group)
+        allh = allh.cpu().numpy()
+        ptrs = (C.c_void_p * self.world)()
+        opened = 1
+        for r in range(self.world):
+            if r == self.rank:
+                ptrs[r] = local.value
+                continue
+            h = (C.c_ubyte * 64)(*allh[r].tolist())
+            p = C.c_void_p()
+            if lib.qk_peer_open(h, C.byref(p)) != 0:
+                opened = 0
+                break
+            ptrs[r] = p.value
+        ok = torch.tensor([opened], dtype=torch.int32, device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
+        if int(ok.item()) == 0:
+            raise _lib.QuakeB200Error("peer buffer could not be opened on every rank: " + lib.qk_last_error().decode())
+        self._peer[key] = (local, ptrs)
+        return ptrs
+
+    def exchange_and_merge(self, ids: torch.Tensor, distances: torch.Tensor, k: int):
+        """Partial [Q, k] results of this rank -> merged result (the same on every rank). Collective."""
+        if self.world <= 1:
+            return ids, distances
+        if self._use_peer_exchange():
+            try:
+                ptrs = self._peer_buffers(int(ids.shape[0]), k)
+            except _lib.QuakeB200Error as e:  # no peer access on this box: every rank takes the NCCL path from now on
+                self._peer_failed = str(e)
+                ptrs = None
+            if ptrs is not None:
+                lib = _lib.load()
+                ids, distances = ids.contiguous(), distances.contiguous()
+                out_ids = torch.empty_like(ids)
+                out_dist = torch.empty_like(distances)
+                check(lib.qk_exchange_merge_topk(ptr(ids), ptr(distances), int(ids.shape[0]), k, self.metric, self.rank,
+                                                 self.world, ptrs, ptr(out_ids), ptr(out_dist), _stream()))
+                return out_ids, out_dist
+        return gather_and_merge(ids, distances, k, self.metric, self.group)
+
+    def _step(self, xq: torch.Tensor, sp: SearchParams):
         ids, dd = self.search_partial(xq, sp)
-        return gather_and_merge(ids, dd, max(int(sp.k), 1), self.metric, self.group)
+        return self.exchange_and_merge(ids, dd, max(int(sp.k), 1))
+
+    def search_device(self, xq: torch.Tensor, sp: SearchParams):
+        """xq [Q, pitch] on this rank's device (the same queries on every rank) -> merged (ids, distances).
+        The per-rank step is replayed from a CUDA graph when the exchange runs on peer memory (an NCCL collective
+        inside a captured graph is avoided on purpose)."""
+        from . import index as _qi
+        Q = int(xq.shape[0])
+        if not (_qi.GRAPHS_ENABLED and self._use_peer_exchange() and Q <= _qi._GRAPH_MAX_Q):
+            return self._step(xq, sp)
+        st = self.local.store
+        st.tables()
+        self.local.parent.store.tables()
+        key = (Q, int(sp.k), int(sp.nprobe), st.uid, st.version, self.local.parent.store.uid, self.local.parent.store.version)
+        plan = self._plans.get(key)
+        if plan is None:
+            self._peer_buffers(Q, max(int(sp.k), 1))  # collective set-up stays outside the capture
+            if not self._use_peer_exchange():
+                return self._step(xq, sp)
+            for kk in [kk for kk in self._plans if kk[3:] != key[3:]]:
+                del self._plans[kk]
+            plan = self._plans[key] = _ShardPlan(self, xq, sp)
+        return plan.run(xq)
 
     def search_partial(self, xq: torch.Tensor, sp: SearchParams):
         """This rank's partial top-k: coarse scan for all queries, partition scan of the probed lists it owns."""
         from .index import scan_partitions
         idx = self.local
         k = max(int(sp.k), 1)
+        if idx.parent.parent is None and idx.parent.store.slot_pid.size == 1 and idx.store.slot_pid.size > 0:
+            # one C call: coarse scan -> id map + ownership filter inside the pair expansion -> scan of the owned lists
+            ids, dd, _ = idx._search_ivf(xq, k, int(sp.nprobe), self.rank, self.world)
+            return ids, dd
         psp = SearchParams()
         psp.batched_scan = True
         psp.k = min(int(sp.nprobe), self.nlist())
