@@ -244,6 +244,14 @@ def run_reference_arm(args):
 
 
 # ------------------------------------------------------------------------------------------------ this repo (GPU)
+def log(msg):
+    """Progress on stderr (rank-tagged): a hung multi-rank run shows where it stopped."""
+    print(f"[bench rank {os.environ.get('RANK', '0')} +{time.perf_counter() - _T0:.1f}s] {msg}", file=sys.stderr, flush=True)
+
+
+_T0 = time.perf_counter()
+
+
 def median(v):
     v = sorted(v)
     return v[len(v) // 2]
@@ -291,6 +299,13 @@ def run_b200(args):
 
     W = dict(WORKLOAD, N=args.n, nlist=args.nlist, nprobe=args.nprobe, Q=args.q)
     W["name"] = workload_name(W)
+    if os.environ.get("QK_BENCH_ONLY_SHARDED") == "1" and world > 1:  # debugging aid: just the sharded section
+        out = sharded_section(qb, world, rank, dev, args)
+        if rank == 0:
+            print(json.dumps({"sharded": out}), flush=True)
+        dist.barrier()
+        dist.destroy_process_group()
+        return 0
     x, xq_h = make_data(W["N"], W["d"], W["Q"], rank)
     ids = torch.arange(W["N"], dtype=torch.int64)
     bp = qb.IndexBuildParams()
@@ -325,6 +340,7 @@ def run_b200(args):
         except Exception as e:
             ref, ref_why = None, repr(e)
 
+    log(f"index built in {build_s:.2f}s")
     parity = {}
     if rank == 0:
         full = idx.search(xq_h, sp)
@@ -356,6 +372,7 @@ def run_b200(args):
 
     # ---- eager phases (no CUDA graph): selection statistics of one partition scan, then the per-launch timing of the
     #      filter kernel with the library's own CUDA-event pair around it (qk_profile_*)
+    log("parity done; eager kernel timing")
     _qi.GRAPHS_ENABLED = False
     os.environ["QK_SCAN_STATS"] = "1"
     idx._search_device(xq_d, sp)
@@ -392,6 +409,7 @@ def run_b200(args):
     # ---- device-resident timing (value): the step as the library runs it (CUDA-graph replay). The K-step region is
     #      repeated R times back to back (>= MIN_TIMED_MS of GPU work in total) and the median repeat is reported: one
     #      6 ms region is at the mercy of a single host hiccup (e.g. the clock sampler's nvidia-smi poll).
+    log("device-resident timing")
     for _ in range(max(args.warmup, 3)):
         idx._search_device(xq_d, sp)
     sampler = ClockSampler(local_rank)
@@ -450,10 +468,15 @@ def run_b200(args):
     extra = {}
     if not args.quick:
         if rank == 0:
+            log("latency section")
             extra["latency"] = latency_section(qb, quake_ref, idx, ref, W, dev)
+            log("nprobe sweep")
             extra["nprobe_sweep"] = nprobe_sweep(qb, idx, xq_d, xq_h, x, W, dev)
+            log("build section")
             extra["build"] = build_section(qb, x, W, dev, binfo, build_s)
         if world > 1:
+            del x
+            log("waiting for the sharded section")
             barrier()
             extra["sharded"] = sharded_section(qb, world, rank, dev, args)
 
@@ -655,10 +678,12 @@ def sharded_section(qb, world, rank, dev, args):
     bp.nlist, bp.metric, bp.niter = nlist, "l2", 3
     sh = ShardedQuakeIndex()
     torch.cuda.synchronize(); dist.barrier()
+    log(f"sharded: distributed build of {n_total} x {d}, nlist {nlist}")
     t0 = time.perf_counter()
     sh.build(xl, idl, bp)
     torch.cuda.synchronize(); dist.barrier()
     build_s = time.perf_counter() - t0
+    log(f"sharded: built in {build_s:.1f}s; searching")
     del xl
     g2 = torch.Generator().manual_seed(4321)
     q = torch.randn(Q, d, generator=g2)
@@ -676,6 +701,7 @@ def sharded_section(qb, world, rank, dev, args):
     e1.record()
     torch.cuda.synchronize(); dist.barrier()
     total_ms = e0.elapsed_time(e1) / reps
+    log(f"sharded: {total_ms:.3f} ms per batch; timing the pieces")
     # the pieces: local partial search alone, exchange + merge alone
     e0.record()
     for _ in range(reps):
@@ -699,6 +725,7 @@ def sharded_section(qb, world, rank, dev, args):
     lo, hi = chk.clone(), chk.clone()
     dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
     ranks_agree = bool(torch.equal(lo, hi))
+    log("sharded: equals_unsharded check")
     # equals_unsharded on a small replicated index
     torch.manual_seed(1234)
     xs = torch.randn(60000, d)

@@ -201,9 +201,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(done)
-            : "r"(a), "r"(parity), "r"(1000000u)  // up to 1 ms per attempt
+            : "r"(a), "r"(parity), "r"(20000u)  // parked for at most 20 us per attempt
             : "memory");
-        if (!done && ++spins == 4000u) {
+        if (!done && ++spins == 400000u) {  // seconds: a pipeline protocol error, not a slow neighbour
             printf("quake_b200: mbarrier wait timed out: block %d warp %d lane %d barrier@%u parity %u\n", blockIdx.x,
                    threadIdx.x >> 5, threadIdx.x & 31, a & 0xffffu, parity);
             __trap();

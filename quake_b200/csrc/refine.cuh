@@ -103,11 +103,12 @@ __device__ __forceinline__ int probed_slots(const MergeArgs& a) { return a.flat_
 // Filter keys of one query share their leading bits (scores of similar magnitude), so a plain MSB-first radix pass
 // would pile every key into one or two histogram bins (serialised shared-memory atomics: most of the old 16 us
 // dense_select). Two scans of the data instead of six:
-//   1. histogram of the TOP 8 bits of v = key - kmin over the range [kmin, kmax] the caller measured while it staged
-//      the data (the keys spread over all 256 bins); per-warp histograms, summed; the bin b* holding rank kc
-//   2. one scan: entries below b* go straight to `out`, entries in b* to a small boundary list
-//   3. the boundary list (n / 256-ish entries) is ranked by counting; the `need` smallest complete the selection
-// Returns kc, or -1 when the boundary list overflows SELECT_BOUNDARY_CAP (masses of equal keys: exact re-scan).
+//   1. histogram passes, 8 bits of v = key - kmin at a time from the top of the range [kmin, kmax] the caller measured
+//      while it staged the data, per-warp histograms summed, narrowing to the bin that holds rank kc -- until that
+//      boundary bin has at most SELECT_BOUNDARY_CAP entries (typically one or two passes)
+//   2. one scan: entries below the boundary bin go straight to `out`, the bin's entries to a small list
+//   3. the boundary list is ranked by counting; its `need` smallest complete the selection
+// Returns kc.
 // `whist` = (MERGE_THREADS / 32) x 256 words, `sc` = 4 words, `blist` = SELECT_BOUNDARY_CAP entries.
 // ------------------------------------------------------------------------------------------------
 static constexpr int SELECT_BOUNDARY_CAP = 512;
@@ -117,64 +118,88 @@ __device__ int block_select_smallest(EntryAt entry_at, int n, int kc, uint32_t k
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int NW = MERGE_THREADS / 32;
     const uint32_t range = kmax - kmin;
-    const int hi = 32 - __clz(range);  // significant bits of v = key - kmin (0: all keys equal)
-    const int sh = hi > 8 ? hi - 8 : 0;
-    for (int i = tid; i < NW * 256; i += MERGE_THREADS) whist[i] = 0;
+    // The current bin is [lo, lo + 2^hi) in v = key - kmin space and holds rank kc; `below` entries lie under it.
+    // Order-preserving float keys are logarithmic in the score (sign and exponent on top), so one 8-bit pass may leave
+    // a whole binade -- hundreds of keys -- in the boundary bin: refine it 8 bits at a time until it is small.
+    int hi = 32 - __clz(range);  // significant bits of v (0: all keys equal)
+    uint32_t lo = 0;
+    int below = 0, nb = n;
+    while (hi > 0 && nb > SELECT_BOUNDARY_CAP) {
+        const int w = hi < 8 ? hi : 8, sh = hi - w;
+        for (int i = tid; i < NW * 256; i += MERGE_THREADS) whist[i] = 0;
+        __syncthreads();
+        for (int i = tid; i < n; i += MERGE_THREADS) {
+            const uint32_t v = (uint32_t)(entry_at(i) >> 32) - kmin;
+            const bool in_bin = hi >= 32 || (v >> hi) == (lo >> hi);
+            if (in_bin) atomicAdd(&whist[warp * 256 + ((v >> sh) & ((1u << w) - 1u))], 1u);
+        }
+        __syncthreads();
+        if (tid < 256) {
+            unsigned t = 0;
+#pragma unroll
+            for (int ww = 0; ww < NW; ++ww) t += whist[ww * 256 + tid];
+            whist[tid] = t;  // column tid is only touched by this thread
+        }
+        __syncthreads();
+        if (tid < 32) {  // lane l owns bins 8l .. 8l+7
+            uint32_t h[8], sum = 0;
+#pragma unroll
+            for (int b = 0; b < 8; ++b) { h[b] = whist[lane * 8 + b]; sum += h[b]; }
+            uint32_t incl = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += y;
+            }
+            const uint32_t need = (uint32_t)(kc - below);
+            const unsigned owner = __ballot_sync(0xffffffffu, incl >= need);
+            const int ol = __ffs(owner) - 1;
+            if (lane == ol) {
+                uint32_t before = incl - sum;
+                int bin = 0;
+#pragma unroll
+                for (int b = 0; b < 8; ++b) {
+                    if (before + h[b] >= need) { bin = lane * 8 + b; break; }
+                    before += h[b];
+                }
+                sc[0] = (uint32_t)bin;
+                sc[1] = before;
+                sc[2] = h[bin & 7];
+            }
+        }
+        __syncthreads();
+        lo |= sc[0] << sh;
+        below += (int)sc[1];
+        nb = (int)sc[2];
+        hi = sh;
+        __syncthreads();  // sc is rewritten by the next pass
+    }
+    // one scan: entries under the boundary bin go straight to `out`, the boundary bin's to the list
     if (tid == 0) { sc[2] = 0u; sc[3] = 0u; }
     __syncthreads();
-    for (int i = tid; i < n; i += MERGE_THREADS) {
-        const uint32_t v = (uint32_t)(entry_at(i) >> 32) - kmin;
-        atomicAdd(&whist[warp * 256 + (v >> sh)], 1u);
-    }
-    __syncthreads();
-    if (tid < 256) {
-        unsigned t = 0;
-#pragma unroll
-        for (int ww = 0; ww < NW; ++ww) t += whist[ww * 256 + tid];
-        whist[tid] = t;  // column tid is only touched by this thread
-    }
-    __syncthreads();
-    if (tid < 32) {  // lane l owns bins 8l .. 8l+7
-        uint32_t h[8], sum = 0;
-#pragma unroll
-        for (int b = 0; b < 8; ++b) { h[b] = whist[lane * 8 + b]; sum += h[b]; }
-        uint32_t incl = sum;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += y;
-        }
-        const unsigned owner = __ballot_sync(0xffffffffu, incl >= (uint32_t)kc);
-        const int ol = __ffs(owner) - 1;
-        if (lane == ol) {
-            uint32_t before = incl - sum;
-            int bin = 0;
-#pragma unroll
-            for (int b = 0; b < 8; ++b) {
-                if (before + h[b] >= (uint32_t)kc) { bin = lane * 8 + b; break; }
-                before += h[b];
-            }
-            sc[0] = (uint32_t)bin;  // b*
-            sc[1] = before;         // entries in the bins below b*: all selected
-        }
-    }
-    __syncthreads();
-    const uint32_t bstar = sc[0];
-    const int before = (int)sc[1];
+    const int need = kc - below;  // 1 .. nb entries of the boundary bin complete the selection
+    const bool all_equal = nb > SELECT_BOUNDARY_CAP;  // hi == 0: one key value, any `need` of its entries will do
     for (int i = tid; i < n; i += MERGE_THREADS) {
         const uint64_t e = entry_at(i);
-        const uint32_t bin = ((uint32_t)(e >> 32) - kmin) >> sh;
-        if (bin < bstar) {
-            out[atomicAdd(&sc[2], 1u)] = e;
-        } else if (bin == bstar) {
+        const uint32_t v = (uint32_t)(e >> 32) - kmin;
+        const bool in_bin = hi >= 32 || (v >> hi) == (lo >> hi);
+        if (in_bin) {
             const unsigned pos = atomicAdd(&sc[3], 1u);
-            if (pos < (unsigned)SELECT_BOUNDARY_CAP) blist[pos] = e;
+            if (all_equal) {
+                if (pos < (unsigned)need) out[below + pos] = e;
+            } else if (pos < (unsigned)SELECT_BOUNDARY_CAP) {
+                blist[pos] = e;
+            }
+        } else if (v < lo) {
+            out[atomicAdd(&sc[2], 1u)] = e;
         }
     }
     __syncthreads();
-    const int nb = (int)sc[3];
-    if (nb > SELECT_BOUNDARY_CAP) return -1;
-    const int need = kc - before;  // 1 .. nb
+    if (all_equal) {
+        if (tid == 0) *t_out = kmin + lo;
+        __syncthreads();
+        return kc;
+    }
     for (int i = tid; i < nb; i += MERGE_THREADS) {
         const uint64_t e = blist[i];
         const uint32_t ke = (uint32_t)(e >> 32);
@@ -183,7 +208,7 @@ __device__ int block_select_smallest(EntryAt entry_at, int n, int kc, uint32_t k
             const uint32_t kj = (uint32_t)(blist[j] >> 32);
             rank += (kj < ke || (kj == ke && j < i)) ? 1 : 0;
         }
-        if (rank < need) out[before + rank] = e;
+        if (rank < need) out[below + rank] = e;
         if (rank == need - 1) *t_out = ke;
     }
     __syncthreads();

@@ -99,14 +99,24 @@ static_assert(256 + SCAN_MAX_NQ * sizeof(ItemDesc) <= SCAN_SMEM_HEADER, "header"
 // about kc * (1 + ln(rows / kc)) rows over a whole scan; the threshold is refreshed every SCAN_REFRESH_STEP-ish
 // appends and several pairs of one query can be in flight, hence the slack. Overflow is not an error: the query
 // is handed to the exact re-scan.
-static int candidate_buffer_cap(int kc) {
+static int candidate_buffer_cap(int kc, double rows_per_query) {
     // small k: thresholds converge within a few hundred appends. Large k needs many more rows before a useful
     // threshold exists (the kc-th best of what was seen so far) and floods the refresh warps meanwhile: give it room
     // (8 B per entry) rather than pay the exact re-scan.
     int c = kc <= 32 ? 2048 : 256 * kc;
-    if (c > 32768) c = 32768;
-    if (c < 32 * kc) c = 32 * kc;
+    // long scans: the appends of a query grow with the rows it scans (measured at k = 10: mean 534 / max ~1900 of
+    // 15.6k rows, mean 609 / max > 2048 now and then of 62k rows) and ONE overflowing query costs an exact re-scan of
+    // all of them (~1.4 ms for 62k rows): scale the buffer with the expected rows per query
+    if (rows_per_query > 16384.0) {
+        double f = rows_per_query / 16384.0;
+        if (f > 16.0) f = 16.0;
+        c = (int)(c * f) / 1024 * 1024;
+    }
+    static const int env_cap = getenv("QK_QCAP") ? atoi(getenv("QK_QCAP")) : 0;  // experiments
+    if (env_cap > 0) c = env_cap;
     if (c > 65536) c = 65536;
+    if (c < 32 * kc) c = 32 * kc;
+    if (c > 131072) c = 131072;
     return c;
 }
 
@@ -163,7 +173,10 @@ static int make_plan(const qk_store_t* st, int64_t Q, int nprobe, int k, ScanPla
     size_t max_items = QP / gq + (QP < S ? QP : S) + 1;
     p->off_items = o;      o = align_up(o + max_items * sizeof(WorkItem), 256);
     p->off_gthr = o;       o = align_up(o + (size_t)Q * 4, 256);
-    p->qcap = candidate_buffer_cap(p->kc);
+    {
+        const double mean_list = st->num_lists > 0 ? (double)st->num_rows / st->num_lists : 0.0;
+        p->qcap = candidate_buffer_cap(p->kc, st->num_lists == 1 ? 0.0 : mean_list * nprobe);  // single-list stores: one seed sample fits all rows
+    }
     if (st->max_segment_rows > 0) {
         // a query never appends more rows than it scans
         const int64_t bound = ((int64_t)p->P * st->max_segment_rows + 63) / 64 * 64;
