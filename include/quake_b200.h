@@ -62,7 +62,10 @@ typedef struct qk_store {
     int64_t        flat_row0;    /* single-list stores (num_lists == 1): first arena row of the list ...  */
     int64_t        flat_rows;    /* ... and its length (host-known copy; 0 otherwise)                     */
     int32_t        max_segment_rows; /* largest seg_rows entry (host-known; 0 = unknown)                   */
-    int32_t        reserved_;
+    int32_t        filter_terms; /* tensor-core filter precision for this store: 0 or 3 = 3xTF32 (error ~2^-20, bounded
+                                   * 2^-17), 2 = 2xTF32 (a_hi (b_hi + b_lo), bound 2^-10): faster, and still exact results
+                                   * -- the refine step's proof sends a query to the exact re-scan whenever the looser
+                                   * filter cannot separate its k-th neighbour from the rest                             */
 } qk_store_t;
 
 #define QK_SEGMENT_ROWS 4096

@@ -44,7 +44,7 @@ class QkStore(C.Structure):
         ("flat_row0", C.c_int64),
         ("flat_rows", C.c_int64),
         ("max_segment_rows", C.c_int32),
-        ("reserved_", C.c_int32),
+        ("filter_terms", C.c_int32),
     ]
 
 

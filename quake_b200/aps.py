@@ -82,7 +82,7 @@ def adaptive_scan(index, xq: torch.Tensor, cand_rows: torch.Tensor, slots: torch
         xa = xq.index_select(0, act64)
         xrep = xa.repeat_interleave(r_eff, dim=0)                       # pseudo-query (a, r) = a * r_eff + r
         probe = slots.index_select(0, act64)[:, p:p + r_eff].reshape(-1, 1).contiguous()
-        r_ids, r_dist = scan_partitions(store, xrep, probe, k, metric)
+        r_ids, r_dist = scan_partitions(store, xrep, probe, k, metric, filter_terms=3)  # no re-scan monitor on this path
         check(lib.qk_aps_advance(ptr(active), Qa, r_eff, p, m, k, d, metric, ptr(slots), ptr(r_ids), ptr(r_dist),
                                  ptr(boundary), ptr(table), float(sp.recall_target), float(sp.recompute_threshold),
                                  int(bool(sp.use_precomputed)), ptr(run_ids), ptr(run_dist), ptr(run_cnt), ptr(radius),

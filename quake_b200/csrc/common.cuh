@@ -201,9 +201,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(done)
-            : "r"(a), "r"(parity), "r"(20000u)  // parked for at most 20 us per attempt
+            : "r"(a), "r"(parity), "r"(1000000u)  // parked for up to 1 ms per attempt (a 20 us limit cost 14 us at C2:
+                                                   // the parked warps of a 16-warp CTA wake up and spin)
             : "memory");
-        if (!done && ++spins == 400000u) {  // seconds: a pipeline protocol error, not a slow neighbour
+        if (!done && ++spins == 8000u) {  // seconds: a pipeline protocol error, not a slow neighbour
             printf("quake_b200: mbarrier wait timed out: block %d warp %d lane %d barrier@%u parity %u\n", blockIdx.x,
                    threadIdx.x >> 5, threadIdx.x & 31, a & 0xffffu, parity);
             __trap();

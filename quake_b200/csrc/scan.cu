@@ -34,12 +34,18 @@ namespace qk {
 
 static int g_scan_variant = -1;  // 0: tensor-core filter for d <= 128 (default), 1: FP32-pipe filter everywhere
 static int g_force_rescan = 0;
+static int g_filter_terms_env = 0;  // QK_FILTER_TERMS: overrides the store's setting (experiments)
+// relative error bound of the tensor-core filter's dot products against |q||v|: 3xTF32 measured ~2^-20 of sum|q_i v_i|
+// (scripts/umma_probe.cu), bounded by 2^-17; 2xTF32 drops a_lo = a - tf32(a), |a_lo| < 2^-10 |a| element-wise
+static double filter_gamma(int terms) { return terms == 2 ? 9.765625e-04 + 7.62939453125e-06 : 7.62939453125e-06; }
 static void read_scan_env() {
     if (g_scan_variant >= 0) return;
     const char* e = getenv("QK_SCAN_PATH");
     g_scan_variant = (e && strcmp(e, "ffma") == 0) ? 1 : 0;
     const char* f = getenv("QK_FORCE_RESCAN");
     g_force_rescan = f ? atoi(f) : 0;
+    const char* t = getenv("QK_FILTER_TERMS");
+    g_filter_terms_env = t ? atoi(t) : 0;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -688,6 +694,7 @@ struct ScanArgs {
     int dense_rows;
     // flat mode (single-list store scanned without a probe table): the work items are the grid (segment x chunk of gq
     // consecutive queries), item it = seg * flat_nchunks + chunk, computed in the kernel -- no pair tables, no grouping
+    int terms;  // tensor-core filter: 3 = 3xTF32 (a_hi b_hi + a_lo b_hi + a_hi b_lo), 2 = 2xTF32 (no a_lo term)
     int flat;
     int flat_nchunks;
     int flat_items;
@@ -1279,6 +1286,9 @@ int qk::scan_partitions_impl(const qk_store_t* st, const float* queries, int64_t
     const int64_t QP = Q * p.P;
     const bool ip = metric == QK_METRIC_INNER_PRODUCT;
     const bool use_mma = (g_scan_variant == 0) && p.dp <= 128;
+    int terms = g_filter_terms_env ? g_filter_terms_env : st->filter_terms;
+    if (terms != 2) terms = 3;
+    const double fgam = use_mma ? filter_gamma(terms) : 0.0;
 
     // seg_count, seg_fill, flags, qcount, ctrl are contiguous: one memset; candidate slots start as +inf
     QK_CUDA(cudaMemsetAsync(ws + p.off_seg_count, 0, p.off_seg_start - p.off_seg_count, stream));
@@ -1317,7 +1327,7 @@ int qk::scan_partitions_impl(const qk_store_t* st, const float* queries, int64_t
     }
     if (p.sample) {
         const int sample = p.sample;
-        const float rel_margin = 4.f * (float)(st->d + 8) * 5.9604645e-08f + (use_mma ? 4.f * 7.62939453125e-06f : 0.f);
+        const float rel_margin = 4.f * (float)(st->d + 8) * 5.9604645e-08f + 4.f * (float)fgam;
         if (p.flat_seed) {
             // the single list's first rows (its segments are consecutive in the arena); host-known geometry
             if (st->flat_rows > 0) {
@@ -1377,6 +1387,7 @@ int qk::scan_partitions_impl(const qk_store_t* st, const float* queries, int64_t
     sa.gthr = gthr; sa.qcount = qcount; sa.qbuf = qbuf;
     sa.P = p.P; sa.kc = p.kc; sa.gq = p.gq; sa.nq = p.nq; sa.qcap = p.qcap;
     sa.Q = Q; sa.seg_row0 = st->seg_row0; sa.seg_rows = st->seg_rows;
+    sa.terms = terms;
     {
         static int dbg = -1;
         if (dbg < 0) { const char* e = getenv("QK_SCAN_DBG"); dbg = e ? atoi(e) : 0; }
@@ -1410,8 +1421,7 @@ int qk::scan_partitions_impl(const qk_store_t* st, const float* queries, int64_t
     ma.flags = flags; ma.ctrl = ctrl; ma.P = p.P; ma.kc = p.kc; ma.k = k;
     ma.max_row_norm = st->max_row_norm;
     ma.max_row_norm_dev = ex.max_row_norm_dev;
-    // 3xTF32 dot products: measured ~2^-20 of sum|q_i v_i| (scripts/umma_probe.cu); bounded here by 2^-17 |q||v|
-    ma.filter_gam = use_mma ? 7.62939453125e-06 : 0.0;
+    ma.filter_gam = fgam;
     ma.out_ids = out_ids; ma.out_dist = out_dist; ma.out_rows = out_rows;
     ma.force_rescan = g_force_rescan;
     ma.rank_squared = ex.rank_squared;

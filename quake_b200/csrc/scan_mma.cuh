@@ -163,7 +163,7 @@ __device__ __forceinline__ float key2lim(uint32_t t) { return t == KEY_MAX ? INF
 
 template <bool kIP>
 __global__ void __launch_bounds__(MMA_THREADS, 1) scan_mma_kernel(const ScanArgs a, const __grid_constant__ CUtensorMap vmap) {
-    constexpr int TM = MMA_TM, NS = MMA_STAGES, NB = MMA_NB, ND = MMA_ND;
+    constexpr int TM = MMA_TM, NB = MMA_NB, ND = MMA_ND;
     static_assert(MMA_STAGES <= 16 && 768 + MMA_ND * sizeof(MmaDesc) <= MMA_SMEM_HEADER, "descriptor ring");
     extern __shared__ __align__(16) unsigned char smem_dyn[];
     unsigned char* smem_raw = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
@@ -182,15 +182,22 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) scan_mma_kernel(const ScanArgs
     volatile unsigned long long* mbox = reinterpret_cast<volatile unsigned long long*>(smem_raw + 704);  // [8] refresh requests
     MmaDesc* descs = reinterpret_cast<MmaDesc*>(smem_raw + 768);    // [ND]
     unsigned char* As = smem_raw + MMA_SMEM_HEADER;                 // [NS][128 rows][128 B]
-    unsigned char* Bs = As + (size_t)NS * MMA_BOX_BYTES;            // [NB][4 boxes][hi: 32 rows | lo: 32 rows][128 B]
+    unsigned char* Bs = As + (size_t)MMA_STAGES * MMA_BOX_BYTES;    // [NB][4 boxes][hi: 32 rows | lo: 32 rows][128 B]
     uint32_t* hists = reinterpret_cast<uint32_t*>(Bs + (size_t)NB * 4 * MMA_BBOX_BYTES);  // [2 refresh warps][256]
     uint32_t* rscratch = hists + 2 * 256;                                                  // [2][MMA_REFRESH_CAP] keys
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int dp = a.dp, kc = a.kc;
     const int nbox = (dp + MMA_BOX - 1) / MMA_BOX;  // 1..4
+    // Ring slots in use: a multiple of two tiles' worth of boxes (8, 8, 6, 8 for 1..4 boxes per tile), so that each of
+    // the two MMA issuers (alternate tiles) meets every slot it uses in EVERY round. With 3 boxes per tile on 8 slots an
+    // issuer would skip rounds of a slot; its parity wait could then be satisfied by the completion of an older round
+    // (mbarrier waits only tell "the phase of this parity is over") -- seen as a pipeline deadlock at d = 96 in the
+    // 2-term mode, where nothing else orders the issuer behind the data.
+    const int NS = (MMA_STAGES / (2 * nbox)) * 2 * nbox;
     if (tid == 0) {
-        for (int s = 0; s < NS; ++s) { mbar_init(a_full + s, 1); mbar_init(a_empty + s, 5); mbar_init(alo_full + s, 4); }
+        // a row box is released by the MMA commit and -- when the a_lo term is computed (3 terms) -- by the 4 split warps
+        for (int s = 0; s < MMA_STAGES; ++s) { mbar_init(a_full + s, 1); mbar_init(a_empty + s, a.terms == 2 ? 1 : 5); mbar_init(alo_full + s, 4); }
         for (int s = 0; s < NB; ++s) { mbar_init(b_ready + s, 4); mbar_init(b_empty + s, 2); }
         for (int s = 0; s < ND; ++s) { mbar_init(i_full + s, 1); mbar_init(i_empty + s, 14); }
         for (int s = 0; s < MMA_NACC; ++s) { mbar_init(d_full + s, 1); mbar_init(d_empty + s, 4); }
@@ -327,7 +334,14 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) scan_mma_kernel(const ScanArgs
                     const uint64_t db0 = umma_desc_sw128(bs + b * MMA_BBOX_BYTES);
                     const uint32_t talo = tmem + MMA_TMEM_ALO + st * MMA_BOX;
                     const int ksteps = min(4, (dp - b * MMA_BOX + 7) >> 3);
-                    if (QK_DBG(a, 8)) {
+                    if (a.terms == 2) {
+                        // 2xTF32: a_hi . (b_hi + b_lo) only -- no a_lo term, nothing to wait for but the TMA data
+                        mbar_wait(a_full + st, (U / NS) & 1u);
+                        tc_fence_after();
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk)
+                            if (kk < ksteps) umma_ss(tmem_d, da0 + 2 * kk, db0 + 2 * kk, idesc_hl, (b | kk) ? 1u : 0u);
+                    } else if (QK_DBG(a, 8)) {
                         // the a_hi products only need the TMA data: they run while the split warps still derive a_lo
                         mbar_wait(a_full + st, (U / NS) & 1u);
                         tc_fence_after();
@@ -415,7 +429,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) scan_mma_kernel(const ScanArgs
             if (lane == 0) mbar_arrive(b_ready + ib);
             const int nrows = d.nrows;
             prefetch_b(n + 1, d);  // d now describes item n+1
-            const int ntiles = (nrows + TM - 1) / TM;
+            const int ntiles = a.terms == 2 ? 0 : (nrows + TM - 1) / TM;  // 2xTF32: no a_lo term, the boxes are not touched here
             const int r = q4 * 32 + lane;  // this thread's row of the tile == its tensor-memory lane
             for (int tile = 0; tile < ntiles; ++tile) {
                 for (int b = 0; b < nbox; ++b, ++U) {

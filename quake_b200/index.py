@@ -36,6 +36,13 @@ def _device() -> torch.device:
     return torch.device("cuda", torch.cuda.current_device())
 
 
+# Filter precision policy of the PARTITION scan of a two-level index ("auto" | "2" | "3", env QK_FILTER): the
+# tensor-core filter may drop the a_lo term (2xTF32: ~13 % faster scan kernel at C2). Results stay exact either way --
+# the refine step proves every answer and re-scans a query exactly when the looser filter cannot separate its k-th
+# neighbour -- but re-scans are slow, so "auto" starts at 2 terms and falls back to 3 for good as soon as a search
+# reports more than 1 % of its queries re-scanned (checked from the statistics of the previous calls, no extra sync).
+# Coarse scans, flat indexes and the k-means assign always run 3xTF32 (their top-k margins are much tighter).
+FILTER_POLICY = os.environ.get("QK_FILTER", "auto")
 LAST_SCAN_STATS = None  # set QK_SCAN_STATS=1: int32[4] device tensor of the last qk_scan_partitions call
 
 # Fixed-nprobe searches are replayed from a CUDA graph captured per (batch size, k, nprobe, index version): the
@@ -51,6 +58,35 @@ GRAPH_LAUNCHES = 0  # kernels of ours launched through graph replays (qk_launch_
 def launch_count() -> int:
     """Kernels of this library launched so far: host-side launches + those inside replayed CUDA graphs."""
     return int(_lib.load().qk_launch_count()) + GRAPH_LAUNCHES
+
+
+class _FilterMonitor:
+    """Asynchronous read-back of a search's scan statistics (16 bytes through pinned memory + an event; never waited
+    for): how many queries of an earlier batch fell into the exact re-scan."""
+
+    def __init__(self):
+        self.host = torch.zeros(4, dtype=torch.int32).pin_memory()
+        self.event = None
+        self.queries = 0
+        self.calls = 0
+
+    def submit(self, stats: torch.Tensor, queries: int) -> None:
+        self.calls += 1
+        if self.event is not None or stats is None:
+            return  # one read-back in flight at a time
+        if self.calls > 32 and (self.calls & 7):
+            return  # steady state: every 8th call
+        self.host.copy_(stats, non_blocking=True)
+        self.event = torch.cuda.Event()
+        self.event.record()
+        self.queries = queries
+
+    def poll(self):
+        """(queries re-scanned, queries) of a finished read-back, or None."""
+        if self.event is None or not self.event.query():
+            return None
+        self.event = None
+        return int(self.host[0]), self.queries
 
 
 class _SearchPlan:
@@ -76,6 +112,7 @@ class _SearchPlan:
             with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
                 self.ids, self.dist, self.p_ids = index._search_core(self.xq, sp)
             self.launches = int(lib.qk_launch_count() - n0)  # kernels of ours one replay launches
+            self.stats = index.__dict__.get("_last_stats")   # written by the replay (static buffer of the plan)
         finally:
             _capturing = False
         # everything outside the graph's private pool whose address the graph baked in lives as long as the plan: the
@@ -95,7 +132,7 @@ class _SearchPlan:
 
 
 def scan_partitions(store: PartitionStore, xq: torch.Tensor, probe_slots: torch.Tensor | None, k: int, metric: int,
-                    want_rows: bool = False):
+                    want_rows: bool = False, filter_terms: int | None = None):
     """qk_scan_partitions over a device query batch xq [Q, pitch] and probe_slots [Q, nprobe] (int32), or None for a
     single-list store (flat mode: every query scans the whole list, no probe table, no grouping kernels).
     Returns (ids [Q,k] int64, distances [Q,k] float32[, rows]) on the device."""
@@ -107,6 +144,11 @@ def scan_partitions(store: PartitionStore, xq: torch.Tensor, probe_slots: torch.
     else:
         Q, nprobe = int(probe_slots.shape[0]), int(probe_slots.shape[1])
     st, _ = store.tables(store.segment_len(Q, nprobe))
+    if filter_terms is not None and int(filter_terms) != st.filter_terms:
+        keep = st
+        st = _lib.QkStore.from_buffer_copy(st)  # same device tables, other filter precision (callers without a monitor)
+        st.filter_terms = int(filter_terms)
+        st._keepalive = keep
     dev = xq.device
     out_ids = torch.empty((Q, k), dtype=torch.int64, device=dev)
     out_dist = torch.empty((Q, k), dtype=torch.float32, device=dev)
@@ -194,6 +236,7 @@ class QuakeIndex:
             self.store.init_from_sorted(xd, idd, None, np.array([n], dtype=np.int64), np.array([0], dtype=np.int64))
         info.n_clusters = self.nlist()
         self.initialize_maintenance_policy(MaintenancePolicyParams())
+        self._apply_filter_policy()
         torch.cuda.synchronize()
         info.total_time_us = int((time.perf_counter() - t0) * 1e6)
         return info
@@ -275,11 +318,31 @@ class QuakeIndex:
             cache[Q] = slots[None, :].expand(Q, -1).contiguous()
         return cache[Q]
 
+    def _apply_filter_policy(self) -> None:
+        """Filter precision of the partition scan (see FILTER_POLICY): two-level indexes start at 2xTF32 unless told
+        otherwise; everything else stays at 3xTF32."""
+        if self.store is None:
+            return
+        two_level = self.parent is not None and self.current_level == 0
+        self.store.set_filter_terms(2 if (two_level and FILTER_POLICY in ("auto", "2")) else 3)
+
+    def _filter_feedback(self) -> None:
+        mon = self.__dict__.get("_monitor")
+        if mon is None or self.store.filter_terms != 2 or FILTER_POLICY != "auto":
+            return
+        got = mon.poll()
+        if got is not None and got[0] > max(2, got[1] // 100):
+            # the 2-term filter cannot separate this data's neighbours often enough: exact results either way, but every
+            # failed proof is an exhaustive re-scan. 3xTF32 from now on (plans are re-captured: the store version moves).
+            self.store.set_filter_terms(3)
+            self.filter_fallback = got
+
     def _reset_caches(self) -> None:
         """build() / load() install a new store: captured plans, probe tables and staging buffers of the old one go."""
         self.__dict__.pop("_plans", None)
         self.__dict__.pop("_flat_probe_cache", None)
         self.__dict__.pop("_host_stage", None)
+        self.__dict__.pop("_monitor", None)
 
     def _search_core(self, xq: torch.Tensor, sp: SearchParams):
         """Fixed-nprobe search, launches only (capturable in a CUDA graph): coarse scan -> slot map -> partition scan.
@@ -317,10 +380,13 @@ class QuakeIndex:
         out_ids = torch.empty((Q, k), dtype=torch.int64, device=dev)
         out_dist = torch.empty((Q, k), dtype=torch.float32, device=dev)
         p_ids = torch.empty((Q, np_), dtype=torch.int64, device=dev)
-        stats = None
+        # statistics of the partition scan {queries re-scanned exactly, max / total candidates}: the filter precision
+        # policy reads them back asynchronously (_FilterMonitor)
+        stats = torch.empty(4, dtype=torch.int32, device=dev)
+        self._last_stats = stats
         if os.environ.get("QK_SCAN_STATS") == "1":
             global LAST_SCAN_STATS
-            stats = LAST_SCAN_STATS = torch.zeros(4, dtype=torch.int32, device=dev)
+            LAST_SCAN_STATS = stats
         check(lib.qk_search_ivf(C.byref(pst), C.byref(st), ptr(table), table.numel(), ptr(xq), Q, xq.stride(0), np_,
                                 self.metric, k, shard_rank, shard_world, ptr(out_ids), ptr(out_dist), ptr(p_ids), ptr(ws),
                                 wsb, ptr(stats), _stream()))
@@ -386,14 +452,22 @@ class QuakeIndex:
         else:
             t1 = time.perf_counter()
             plan = None
+            monitored = self.current_level == 0 and self.parent is not None and not _capturing
+            if monitored:
+                self._filter_feedback()
             if GRAPHS_ENABLED and not _capturing and self.current_level == 0 and Q <= _GRAPH_MAX_Q:
                 plan = self._plan(Q, sp)
             if plan is not None:
                 ids, dist, p_ids = plan.run(xq)
                 if p_ids is not None:
                     p_ids = p_ids.clone()  # the hit window below outlives the plan's static buffer
+                stats = plan.stats
             else:
+                self._last_stats = None
                 ids, dist, p_ids = self._search_core(xq, sp)
+                stats = self._last_stats
+            if monitored and self.store.filter_terms == 2 and FILTER_POLICY == "auto":
+                self.__dict__.setdefault("_monitor", _FilterMonitor()).submit(stats, Q)
             parent_info.total_time_ns = int((time.perf_counter() - t1) * 1e9)
         if self.parent is not None:
             parent_info.n_queries = Q
@@ -616,6 +690,7 @@ class QuakeIndex:
         else:
             self.parent = None
         self.initialize_maintenance_policy(MaintenancePolicyParams())
+        self._apply_filter_policy()
 
     def _load_partitions(self, path: str, dev) -> None:
         with open(path, "rb") as f:

@@ -53,6 +53,9 @@ class PartitionStore:
         self.free_slots: list[int] = []
         self.curr_list_id = 0
         self.max_row_norm = 0.0
+        # tensor-core filter precision of scans over this store (qk_store_t.filter_terms): 3 = 3xTF32, 2 = 2xTF32.
+        # QuakeIndex sets 2 on the partition store of a two-level index (see index.py: filter precision policy).
+        self.filter_terms = 3
         self._dirty = True
         self.version = 0  # bumped by every mutation; search plans (CUDA graphs) are keyed by it
         self._cache = {}
@@ -389,6 +392,11 @@ class PartitionStore:
             seg_len //= 2
         return seg_len
 
+    def set_filter_terms(self, terms: int) -> None:
+        if int(terms) != self.filter_terms:
+            self.filter_terms = int(terms)
+            self._dirty = True  # the struct is rebuilt, captured plans are dropped (version bump)
+
     def tables_snapshot(self):
         """References to everything a kernel launch of the current version reads: keeps it alive for a captured graph."""
         return (self.vectors, self.ids, self.norms, dict(self._cache))
@@ -442,6 +450,7 @@ class PartitionStore:
         st.flat_row0 = int(self.list_row0[0]) if nslots == 1 else 0
         st.flat_rows = int(self.list_size[0]) if nslots == 1 else 0
         st.max_segment_rows = int(seg_rows.max()) if S else 0
+        st.filter_terms = int(self.filter_terms)
         st._keepalive = t  # the struct holds raw pointers into these tensors
         self._cache[key] = (st, t["id_to_slot"])
         return self._cache[key]
