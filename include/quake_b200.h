@@ -244,6 +244,30 @@ int qk_scatter_rows(const float* src, int64_t src_pitch, const int64_t* src_ids,
                     const int64_t* order, const int64_t* dst_rows, int64_t n, int d,
                     float* dst, int64_t dst_pitch, int64_t* dst_ids, void* stream);
 
+/* ---- device-resident bookkeeping of the dynamic partition store -------------------------------------
+ * id -> arena row hash table (open addressing, power-of-two capacity from qk_hash_capacity, keys/vals are device
+ * int64 arrays) and removal by id. Replaces the reference's per-list linear searches and the removal loop that walks
+ * every list (src/cpp/src/dynamic_inverted_list.cpp:137-149, 302-321; src/cpp/src/index_partition.cpp:79-98, 129-145;
+ * src/cpp/src/partition_manager.cpp:264-320).
+ * qk_store_remove: erase ids from the table; out_rows[i] = the row the id lived in (-1: absent, or a duplicate of an
+ * id already erased by this call), row_flags[row] = 1, *n_erased += rows flagged.
+ * qk_store_compact_lists: one CTA per list; lists with flagged rows are compacted with the reference's
+ * swap-with-last rule (the holes below the new size take, in ascending order, the surviving tail rows in descending
+ * order -- the state IndexPartition::remove leaves behind, dynamic_inverted_list.cpp:127-133), the table follows the
+ * moved ids, flags are cleared, new_size[list] = size after the removal. scratch_*: int32 arrays of arena length. */
+int64_t qk_hash_capacity(int64_t n);
+int qk_hash_clear(int64_t* keys, int64_t capacity, void* stream);
+int qk_hash_insert(int64_t* keys, int64_t* vals, int64_t capacity, const int64_t* ids, const int64_t* rows,
+                   int64_t n, int32_t* failed_flag, void* stream);
+int qk_hash_lookup(const int64_t* keys, const int64_t* vals, int64_t capacity, const int64_t* ids, int64_t n,
+                   int64_t* out_rows, void* stream);
+int qk_store_remove(int64_t* keys, const int64_t* vals, int64_t capacity, const int64_t* ids, int64_t n,
+                    int64_t* out_rows, uint8_t* row_flags, unsigned long long* n_erased, void* stream);
+int qk_store_compact_lists(float* vectors, int64_t pitch, int64_t* ids, float* norms,
+                           const int64_t* list_row0, const int64_t* list_size, int64_t num_lists,
+                           int64_t* new_size, uint8_t* row_flags, int32_t* scratch_holes, int32_t* scratch_surv,
+                           int64_t* hash_keys, int64_t* hash_vals, int64_t hash_capacity, void* stream);
+
 /* ---- host-side helpers (no GPU work): vendored-faiss control logic of Clustering::train ----------
  * First m entries of faiss::rand_perm(n, seed) (third_party/faiss/faiss/utils/random.cpp:153-163). */
 int qk_host_rand_perm_prefix(int64_t n, int64_t seed, int64_t m, int64_t* out);

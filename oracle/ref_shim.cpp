@@ -9,6 +9,9 @@
 //   kmeans                    src/clustering.cpp:13-97
 //   kmeans_refine_partitions  src/clustering.cpp:99-182
 //   compute_boundary_distances / compute_recall_profile   include/geometry.h:57-113, 345-407
+//   MaintenanceCostEstimator (split / delete deltas) + ListScanLatencyEstimator interpolation
+//                             src/maintenance_cost_estimator.cpp:131-251, 355-493 -- with a latency table supplied by
+//                             the test (the reference's own table is a CPU profile of the host it runs on)
 // Nothing here restates reference logic; it only marshals tensors.
 #include <torch/extension.h>
 #include <pybind11/pybind11.h>
@@ -19,6 +22,7 @@
 #include <clustering.h>
 #include <geometry.h>
 #include <index_partition.h>
+#include <maintenance_cost_estimator.h>
 
 namespace py = pybind11;
 
@@ -160,7 +164,38 @@ static std::vector<float> shim_recall_profile(std::vector<float> boundary, float
     return compute_recall_profile(boundary, radius, d, {}, use_precomputed, euclidean);
 }
 
+// The reference's cost model with its latency grid values replaced by `table` [n_values x k_values] (public member)
+struct ShimCostModel {
+    std::shared_ptr<MaintenanceCostEstimator> est;
+    ShimCostModel(int d, float alpha, int k, std::vector<std::vector<float>> table) {
+        est = std::make_shared<MaintenanceCostEstimator>(d, alpha, k);  // profiles the CPU once (discarded below)
+        auto lat = est->get_latency_estimator();
+        if (table.size() != lat->n_values_.size() || table[0].size() != lat->k_values_.size())
+            throw std::runtime_error("latency table shape does not match the reference's grid");
+        lat->scan_latency_model_ = table;
+    }
+    float latency(int n, int k) const { return est->get_latency_estimator()->estimate_scan_latency(n, k); }
+    float split_delta(int size, float hit_rate, int total) const { return est->compute_split_delta(size, hit_rate, total); }
+    float delete_delta(int size, float hit_rate, int total, float avg_rate, float avg_size) const {
+        return est->compute_delete_delta(size, hit_rate, total, avg_rate, avg_size);
+    }
+    float delete_delta_w_reassign(int size, float hit_rate, int total, std::vector<int64_t> counts,
+                                  std::vector<int64_t> sizes, std::vector<float> rates) const {
+        return est->compute_delete_delta_w_reassign(size, hit_rate, total, counts, sizes, rates);
+    }
+    std::vector<int> n_values() const { return est->get_latency_estimator()->n_values_; }
+    std::vector<int> k_values() const { return est->get_latency_estimator()->k_values_; }
+};
+
 PYBIND11_MODULE(_shim, m) {
+    py::class_<ShimCostModel>(m, "CostModel")
+        .def(py::init<int, float, int, std::vector<std::vector<float>>>())
+        .def("latency", &ShimCostModel::latency)
+        .def("split_delta", &ShimCostModel::split_delta)
+        .def("delete_delta", &ShimCostModel::delete_delta)
+        .def("delete_delta_w_reassign", &ShimCostModel::delete_delta_w_reassign)
+        .def("n_values", &ShimCostModel::n_values)
+        .def("k_values", &ShimCostModel::k_values);
     m.def("scan_list", &shim_scan_list, py::arg("query"), py::arg("list_vecs"), py::arg("list_ids"), py::arg("k"),
           py::arg("metric"));
     m.def("batched_scan_list", &shim_batched_scan_list, py::arg("queries"), py::arg("list_vecs"),

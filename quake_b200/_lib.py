@@ -97,6 +97,12 @@ PROTOTYPES = {
     "qk_gather_rows": (C.c_int, [vp, C.c_int64, vp, vp, C.c_int64, C.c_int, vp, C.c_int64, vp, vp]),
     "qk_scatter_rows": (C.c_int, [vp, C.c_int64, vp, vp, vp, C.c_int64, C.c_int, vp, C.c_int64, vp, vp]),
     "qk_normalize_rows": (C.c_int, [vp, C.c_int64, C.c_int64, C.c_int, vp]),
+    "qk_hash_capacity": (C.c_int64, [C.c_int64]),
+    "qk_hash_clear": (C.c_int, [vp, C.c_int64, vp]),
+    "qk_hash_insert": (C.c_int, [vp, vp, C.c_int64, vp, vp, C.c_int64, vp, vp]),
+    "qk_hash_lookup": (C.c_int, [vp, vp, C.c_int64, vp, C.c_int64, vp, vp]),
+    "qk_store_remove": (C.c_int, [vp, vp, C.c_int64, vp, C.c_int64, vp, vp, vp, vp]),
+    "qk_store_compact_lists": (C.c_int, [vp, C.c_int64, vp, vp, vp, vp, C.c_int64, vp, vp, vp, vp, vp, vp, C.c_int64, vp]),
     "qk_host_rand_perm_prefix": (C.c_int, [C.c_int64, C.c_int64, C.c_int64, c_i64p]),
     "qk_host_split_clusters": (C.c_int, [C.c_int64, C.c_int64, C.c_int64, c_f32p, c_f32p, C.c_int64, c_i64p]),
 }

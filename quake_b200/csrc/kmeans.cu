@@ -144,27 +144,62 @@ __global__ void __launch_bounds__(256) sort_lists_kernel(const int64_t* __restri
 
 // ------------------------------------------------------------------------------------------------
 // per-centroid sums in ascending point order (faiss compute_centroids order,
-// third_party/faiss/faiss/Clustering.cpp:123-192): one CTA per centroid, one thread per dimension.
+// third_party/faiss/faiss/Clustering.cpp:123-192): one WARP per centroid, lane l owns dimensions 4l .. 4l+3 of a
+// 128-wide dimension block (one 16-byte load per member row and lane, a warp reads 512 contiguous bytes of the row).
+// The member indices of 32 rows are fetched with one coalesced load and handed round with shuffles; eight row loads
+// are in flight per lane; every dimension still adds its members one by one in list order, so the sums are
+// bit-identical to the sequential loop of the reference. HBM-bound: N*d*4 + N*8 + K*d*4 bytes.
 // ------------------------------------------------------------------------------------------------
-__global__ void accumulate_kernel(const float* __restrict__ points, int64_t pitch, int d,
-                                  const int64_t* __restrict__ order, const int64_t* __restrict__ offsets,
-                                  int64_t K, float* __restrict__ sums, int64_t out_pitch) {
-    for (int64_t c = blockIdx.x; c < K; c += gridDim.x) {
+__global__ void __launch_bounds__(256) accumulate_kernel(const float* __restrict__ points, int64_t pitch, int d,
+                                                         const int64_t* __restrict__ order,
+                                                         const int64_t* __restrict__ offsets, int64_t K,
+                                                         float* __restrict__ sums, int64_t out_pitch) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const bool vec = (pitch % 4 == 0) && ((reinterpret_cast<uintptr_t>(points) & 15) == 0);
+    for (int64_t c = warp; c < K; c += nwarps) {
         const int64_t b = offsets[c], e = offsets[c + 1];
-        for (int j = threadIdx.x; j < d; j += blockDim.x) {
-            float s = 0.f;
-            int64_t i = b;
-            for (; i + 4 <= e; i += 4) {  // 4 independent loads in flight, sequential adds
-                const int64_t r0 = order[i], r1 = order[i + 1], r2 = order[i + 2], r3 = order[i + 3];
-                const float v0 = points[r0 * pitch + j], v1 = points[r1 * pitch + j];
-                const float v2 = points[r2 * pitch + j], v3 = points[r3 * pitch + j];
-                s = __fadd_rn(s, v0);
-                s = __fadd_rn(s, v1);
-                s = __fadd_rn(s, v2);
-                s = __fadd_rn(s, v3);
+        for (int j0 = 0; j0 < d; j0 += 128) {
+            const int j = j0 + 4 * lane;
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+            for (int64_t base = b; base < e; base += 32) {
+                const int m = (int)((e - base) < 32 ? (e - base) : 32);
+                const int64_t mine = lane < m ? order[base + lane] : 0;
+                for (int t0 = 0; t0 < m; t0 += 8) {
+                    float4 v[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int64_t r = __shfl_sync(0xffffffffu, mine, (t0 + u) & 31);
+                        v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (t0 + u < m && j < d) {
+                            const float* rp = points + r * pitch + j;
+                            if (vec && j + 3 < d) {
+                                v[u] = *reinterpret_cast<const float4*>(rp);
+                            } else {
+                                v[u].x = rp[0];
+                                if (j + 1 < d) v[u].y = rp[1];
+                                if (j + 2 < d) v[u].z = rp[2];
+                                if (j + 3 < d) v[u].w = rp[3];
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        if (t0 + u < m) {  // warp-uniform
+                            s0 = __fadd_rn(s0, v[u].x); s1 = __fadd_rn(s1, v[u].y);
+                            s2 = __fadd_rn(s2, v[u].z); s3 = __fadd_rn(s3, v[u].w);
+                        }
+                    }
+                }
             }
-            for (; i < e; ++i) s = __fadd_rn(s, points[order[i] * pitch + j]);
-            sums[c * out_pitch + j] = s;
+            if (j < d) {
+                float* o = sums + c * out_pitch + j;
+                o[0] = s0;
+                if (j + 1 < d) o[1] = s1;
+                if (j + 2 < d) o[2] = s2;
+                if (j + 3 < d) o[3] = s3;
+            }
         }
     }
 }
@@ -370,9 +405,9 @@ extern "C" int qk_kmeans_accumulate(const float* points, int64_t point_pitch, in
                                     void* stream_v) {
     cudaStream_t stream = (cudaStream_t)stream_v;
     QK_REQUIRE(points && order && offsets && out_sums && K > 0 && d > 0, "bad argument");
-    int threads = d < 32 ? 32 : (d > 256 ? 256 : (d + 31) / 32 * 32);
-    int grid = (int)(K < 65535 ? K : 65535);
-    accumulate_kernel<<<grid, threads, 0, stream>>>(points, point_pitch, d, order, offsets, K, out_sums, out_pitch);
+    const int64_t ctas = (K + 7) / 8;  // one warp per centroid, eight per CTA
+    int grid = (int)(ctas < 65535 ? ctas : 65535);
+    accumulate_kernel<<<grid, 256, 0, stream>>>(points, point_pitch, d, order, offsets, K, out_sums, out_pitch);
     QK_LAUNCHED();
     return QK_OK;
 }

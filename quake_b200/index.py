@@ -194,7 +194,7 @@ class QuakeIndex:
         self.metric = 1
         self.build_params: IndexBuildParams | None = None
         self.maintenance_policy_params: MaintenancePolicyParams | None = None
-        self._hits: list[np.ndarray] = []  # per-query probed partitions (hit window)
+        self.maintenance_policy = None  # maintenance.MaintenancePolicy (hit window + cost model), level 0 only
 
     # ------------------------------------------------------------------ build (quake_index.cpp:29-90)
     def build(self, x: torch.Tensor, ids: torch.Tensor, build_params: IndexBuildParams) -> BuildTimingInfo:
@@ -240,6 +240,30 @@ class QuakeIndex:
         torch.cuda.synchronize()
         info.total_time_us = int((time.perf_counter() - t0) * 1e6)
         return info
+
+    @classmethod
+    def from_partitions(cls, centroids: torch.Tensor, vectors: list, ids: list, metric: str = "l2") -> "QuakeIndex":
+        """A two-level index over GIVEN partitions: partition j holds vectors[j] / ids[j] and is represented by
+        centroids[j] (PartitionManager::init_partitions with a ready-made Clustering, partition_manager.cpp:33-121)."""
+        dev = _device()
+        self = cls()
+        self.metric = str_to_metric(metric)
+        self.build_params = IndexBuildParams()
+        self.build_params.metric = metric
+        self.build_params.nlist = len(vectors)
+        d = int(centroids.shape[1])
+        counts = np.array([int(v.shape[0]) for v in vectors], dtype=np.int64)
+        xd = clustering.pad_rows(torch.cat([v.reshape(-1, d) for v in vectors]), dev)
+        idd = torch.cat([i.reshape(-1) for i in ids]).to(device=dev, dtype=torch.int64)
+        self.store = PartitionStore(d, dev)
+        self.store.init_from_sorted(xd, idd, None, counts, np.arange(len(vectors), dtype=np.int64))
+        self.parent = cls(1)
+        pp = IndexBuildParams()
+        pp.metric = metric
+        self.parent.build(centroids, torch.arange(len(vectors), dtype=torch.int64), pp)
+        self.initialize_maintenance_policy(MaintenancePolicyParams())
+        self._apply_filter_policy()
+        return self
 
     # ------------------------------------------------------------------ search (query_coordinator.cpp:612-657)
     def _check_built(self, who: str):
@@ -449,6 +473,7 @@ class QuakeIndex:
             self.last_partitions_scanned = scanned  # per query, device int32 (the reference only reports it for workers)
             if tinfo is not None:
                 tinfo.partitions_scanned = int(scanned.sum().item())
+            aps_hits = (p_ids, scanned)
         else:
             t1 = time.perf_counter()
             plan = None
@@ -472,26 +497,25 @@ class QuakeIndex:
         if self.parent is not None:
             parent_info.n_queries = Q
             parent_info.n_clusters = self.parent.nlist()
-            if self.maintenance_policy_params is not None and self.current_level == 0:
-                self._record_hits(p_ids)
+            if self.maintenance_policy is not None and self.current_level == 0 and not _capturing:
+                if use_aps:
+                    self._record_hits(*aps_hits)
+                else:
+                    self._record_hits(p_ids)
         return ids, dist, parent_info
 
-    def _record_hits(self, p_ids: torch.Tensor) -> None:
-        """Keep the last `window_size` queries' probed partitions (the reference's HitCountTracker,
-        hit_count_tracker.cpp:43-66; docs/architecture/architecture.rst:21). Kept on the device and only
-        materialised by maintenance()."""
-        w = int(self.maintenance_policy_params.window_size)
-        self._hits.append(p_ids[-w:].detach())
-        total = sum(int(h.shape[0]) for h in self._hits)
-        while len(self._hits) > 1 and total - int(self._hits[0].shape[0]) >= w:
-            total -= int(self._hits.pop(0).shape[0])
+    def _record_hits(self, p_ids: torch.Tensor, scanned: torch.Tensor | None = None) -> None:
+        """Feed the maintenance policy's hit window (the reference's HitCountTracker, hit_count_tracker.cpp:43-66;
+        docs/architecture/architecture.rst:21) with the partitions this batch probed. Stays on the device; only
+        maintenance() materialises it."""
+        if self.maintenance_policy is not None and p_ids is not None:
+            self.maintenance_policy.record_query_hits(p_ids, scanned)
 
     # ------------------------------------------------------------------ accessors
     def get_ids(self) -> torch.Tensor:
         if self.store is None:
             raise RuntimeError("[QuakeIndex::get_ids()] No partition manager. Index not built?")
-        out = [self.store.get_list(int(p))[1] for p in self.store.partition_ids()]
-        return torch.cat(out).cpu() if out else torch.empty((0,), dtype=torch.int64)
+        return self.store.all_ids().cpu()  # one gather on the device, one copy
 
     def get(self, ids: torch.Tensor) -> torch.Tensor:
         if self.store is None:
@@ -587,8 +611,73 @@ class QuakeIndex:
 
     # ------------------------------------------------------------------ maintenance
     def initialize_maintenance_policy(self, maintenance_policy_params: MaintenancePolicyParams) -> None:
+        """QuakeIndex::initialize_maintenance_policy (quake_index.cpp:148-155)."""
+        from .maintenance import MaintenancePolicy
         self.maintenance_policy_params = maintenance_policy_params
-        self._hits = []
+        self.maintenance_policy = None
+        if self.store is not None and self.parent is not None and self.current_level == 0:
+            self.maintenance_policy = MaintenancePolicy(self, maintenance_policy_params)
+
+    # ------------------------------------------------------------------ partition surgery (partition_manager.cpp:393-554)
+    def select_partitions(self, partition_ids: torch.Tensor):
+        """(centroids [P, d], [vectors_p], [ids_p]) copies of the given partitions (PartitionManager::select_partitions)."""
+        pids = [int(p) for p in partition_ids.tolist()]
+        cents = self.parent.get(torch.tensor(pids, dtype=torch.int64).to(self.store.device)) if pids else None
+        vecs, ids = [], []
+        for p in pids:
+            v, i = self.store.get_list(p, padded=True)
+            vecs.append(v.clone())
+            ids.append(i.clone())
+        return cents, vecs, ids
+
+    def split_partitions(self, partition_ids: torch.Tensor):
+        """PartitionManager::split_partitions (:393-445): every partition is cut in two by k-means (K = 2, the build
+        defaults) over its own vectors. Returns (centroids [2P, d], [vectors], [ids]) of the halves, in order."""
+        d = self.store.d
+        cents_out, vecs_out, ids_out = [], [], []
+        for p in [int(x) for x in partition_ids.tolist()]:
+            v, i = self.store.get_list(p, padded=True)
+            if int(v.shape[0]) < 4:
+                raise RuntimeError("Partition must have at least 4 vectors to split.")
+            x = v.clone()  # kmeans normalises its input in place for the inner-product metric
+            c, counts, offsets, order = clustering.kmeans(x, d, 2, self.metric, 5)
+            offs = offsets.cpu().tolist()
+            for j in range(2):
+                sel = order[offs[j]:offs[j + 1]]
+                cents_out.append(c[j, :d])
+                vecs_out.append(x.index_select(0, sel))
+                ids_out.append(i.index_select(0, sel))
+        return torch.stack(cents_out), vecs_out, ids_out
+
+    def add_partitions(self, clustering_triple) -> torch.Tensor:
+        """PartitionManager::add_partitions (:490-520): new partition ids curr_list_id .., lists filled, centroids
+        added to the parent. Returns the new ids."""
+        cents, vecs, ids = clustering_triple
+        n = len(vecs)
+        st = self.store
+        first = int(st.curr_list_id)
+        new_pids = torch.arange(first, first + n, dtype=torch.int64)
+        for j in range(n):
+            cnt = int(vecs[j].shape[0])
+            st.add_list(first + j, capacity=(cnt + max(16, cnt // 8) + 3) // 4 * 4)
+            st.set_list(first + j, vecs[j][:, : st.d], ids[j])
+        self.parent.add(cents[:, : st.d].contiguous(), new_pids)
+        return new_pids
+
+    def delete_partitions(self, partition_ids: torch.Tensor, reassign: bool = False) -> None:
+        """PartitionManager::delete_partitions (:522-554): the centroids leave the parent, the lists leave the store;
+        with `reassign` their vectors are added back (each to its nearest remaining partition)."""
+        if self.parent is None:
+            raise RuntimeError("Index is not partitioned")
+        _, vecs, ids = self.select_partitions(partition_ids)
+        self.parent.remove(partition_ids)
+        for p in partition_ids.tolist():
+            self.store.remove_list(int(p))
+        self.store.maybe_compact()
+        if reassign:
+            keep = [(v, i) for v, i in zip(vecs, ids) if int(v.shape[0]) > 0]
+            if keep:
+                self.add(torch.cat([v[:, : self.store.d] for v, _ in keep]), torch.cat([i for _, i in keep]))
 
     def refine_partitions(self, partition_ids: torch.Tensor | None = None, iterations: int = 0) -> None:
         """PartitionManager::refine_partitions (partition_manager.cpp:447-488): Lloyd refit restricted to
@@ -612,31 +701,15 @@ class QuakeIndex:
         self.parent.modify(pid_t, new_c[:, :d])
 
     def maintenance(self) -> MaintenanceTimingInfo:
-        """QuakeIndex::maintenance (quake_index.cpp:157-163). Like the reference, nothing happens until the
-        hit window is full (maintenance_policies.cpp:36-41). Once it is, the partitions probed in the
-        window are refit with the k-means refit kernel path (refine_partitions with
-        `refinement_iterations`), which is the hot-path part of the reference's maintenance; the
-        cost-model split/delete policy is host control logic outside this build's scope."""
+        """QuakeIndex::maintenance (quake_index.cpp:157-163) -> MaintenancePolicy::perform_maintenance
+        (maintenance_policies.cpp:33-172): nothing happens until the hit window is full; then hit rates feed the cost
+        model (with the scan latency measured on this GPU), partitions are deleted / split accordingly and the
+        neighbourhood of the new partitions is refit (quake_b200/maintenance.py)."""
         if self.maintenance_policy_params is None:
             raise RuntimeError("[QuakeIndex::maintenance()] No maintenance policy set.")
-        info = MaintenanceTimingInfo()
-        p = self.maintenance_policy_params
-        recorded = sum(int(h.shape[0]) for h in self._hits)
-        if self.parent is None or recorded < int(p.window_size):
-            print(f"Window not full yet. {recorded} queries recorded and {p.window_size} queries required.")
-            return info
-        t0 = time.perf_counter()
-        hit = torch.unique(torch.cat([h.reshape(-1) for h in self._hits]))
-        hit = hit[hit >= 0].cpu()
-        live = set(int(x) for x in self.store.partition_ids())
-        hit = torch.tensor([int(x) for x in hit.tolist() if int(x) in live], dtype=torch.int64)
-        if hit.numel():
-            self.refine_partitions(hit, int(p.refinement_iterations))
-        torch.cuda.synchronize()
-        info.split_refine_time_us = int((time.perf_counter() - t0) * 1e6)
-        info.total_time_us = info.split_refine_time_us
-        self._hits = []
-        return info
+        if self.maintenance_policy is None:
+            return MaintenanceTimingInfo()  # flat index: nothing to maintain
+        return self.maintenance_policy.perform_maintenance()
 
     # ------------------------------------------------------------------ save / load (quake_index.cpp:170-267)
     def save(self, dir_path: str) -> None:
@@ -659,14 +732,19 @@ class QuakeIndex:
         sizes = np.array([st.size_of(int(p)) for p in pids], dtype=np.uint64)
         chunk = sizes * np.uint64(code_size + 8)
         offsets = np.concatenate([[0], np.cumsum(chunk)]).astype(np.uint64)
+        # one gather of the live rows on the device, one copy each for vectors and ids
+        rows = st.rows_of(pids) if len(pids) else torch.zeros(0, dtype=torch.int64, device=st.device)
+        vec_h = st.vectors.index_select(0, rows)[:, : st.d].contiguous().cpu().numpy()
+        ids_h = st.ids.index_select(0, rows).cpu().numpy()
+        starts = np.concatenate([[0], np.cumsum(sizes.astype(np.int64))])
         with open(path, "wb") as f:
             f.write(struct.pack("<IIQQQ", SERIALIZATION_MAGIC, SERIALIZATION_VERSION, len(pids), code_size, len(pids)))
             f.write(offsets.tobytes())
             f.write(pids.astype(np.uint64).tobytes())
-            for p in pids:
-                v, i = st.get_list(int(p))
-                f.write(v.contiguous().cpu().numpy().tobytes())
-                f.write(i.contiguous().cpu().numpy().tobytes())
+            for j in range(len(pids)):
+                a, b = int(starts[j]), int(starts[j + 1])
+                f.write(vec_h[a:b].tobytes())
+                f.write(ids_h[a:b].tobytes())
 
     def load(self, dir_path: str, n_workers: int = 0) -> None:
         if not os.path.isdir(dir_path):

@@ -8,8 +8,10 @@ which the first ``size`` are live. Appends fill the slack; a list that outgrows 
 to the end of the arena with doubled capacity (the reference doubles per-list mallocs); removal is the
 reference's swap-with-last. Lists are cut into scan segments of <= QK_SEGMENT_ROWS rows.
 
-All bookkeeping (list table, id -> slot map) lives on the host, as it does in the reference; only the
-vector/id payload and the small lookup tables the kernels read live on the device.
+The list table (row0 / size / capacity per list) is mirrored on the host for planning, as in the reference; the
+payload, the lookup tables the kernels read AND the id -> row index live on the device: a hash table (csrc/store.cu)
+answers get / remove by id in O(1) per id where the reference walks every list, and a removal is two kernels (erase +
+per-list compaction that replays the reference's swap-with-last rule) with one small read-back of the new sizes.
 """
 from __future__ import annotations
 
@@ -59,6 +61,12 @@ class PartitionStore:
         self._dirty = True
         self.version = 0  # bumped by every mutation; search plans (CUDA graphs) are keyed by it
         self._cache = {}
+        # id -> arena row hash table on the device (built lazily; kept incrementally by append / remove, rebuilt after
+        # anything that moves whole lists)
+        self._hkeys = None
+        self._hvals = None
+        self._hash_valid = False
+        self._hash_fill = 0  # live entries + tombstones
 
     # ------------------------------------------------------------------ basic queries
     @property
@@ -127,6 +135,7 @@ class PartitionStore:
         self.slot_pid[s] = -1
         self.free_slots.append(s)
         self._dirty = True
+        self._invalidate_hash()
 
     def _grow_list(self, s: int, need: int) -> None:
         """Move list `s` to the end of the arena with capacity >= need (doubling)."""
@@ -142,6 +151,7 @@ class PartitionStore:
         self.list_cap[s] = new_cap
         self.rows_used += new_cap
         self._dirty = True
+        self._invalidate_hash()  # rows moved
 
     # ------------------------------------------------------------------ bulk build
     def init_from_sorted(self, src: torch.Tensor, src_ids: torch.Tensor, order: torch.Tensor | None,
@@ -175,6 +185,7 @@ class PartitionStore:
             check(lib.qk_scatter_rows(ptr(src), src.stride(0), ptr(src_ids), ptr(order), ptr(dst_rows), n, self.d,
                                       ptr(self.vectors), self.pitch, ptr(self.ids), _stream()))
         self._dirty = True
+        self._invalidate_hash()
         self.refresh_max_norm()
 
     def refresh_max_norm(self) -> None:
@@ -228,6 +239,7 @@ class PartitionStore:
         xn = torch.empty(n, dtype=torch.float32, device=self.device)
         check(lib.qk_row_sqnorms(ptr(x), n, x.stride(0), self.d, ptr(xn), _stream()))
         self.norms[dst_rows] = xn[order_d]
+        self._hash_add(x_ids.to(torch.int64)[order_d], dst_rows)
         self.list_size = self.list_size + counts
         out = torch.tensor([self.max_row_norm], dtype=torch.float32, device=self.device)
         check(lib.qk_max_row_norm(ptr(x), n, x.stride(0), self.d, ptr(out), _stream()))
@@ -244,57 +256,108 @@ class PartitionStore:
         starts = torch.cumsum(sz, 0) - sz
         return torch.arange(n, dtype=torch.int64, device=self.device) + torch.repeat_interleave(r0 - starts, sz)
 
+    # ------------------------------------------------------------------ id -> row index (device hash table)
+    def _invalidate_hash(self) -> None:
+        self._hash_valid = False
+
+    def _ensure_hash(self) -> None:
+        """(Re)build the id -> row table from the live rows: one kernel over ntotal ids."""
+        if self._hash_valid:
+            return
+        lib = _lib.load()
+        rows = self.live_rows()
+        n = int(rows.numel())
+        cap = int(lib.qk_hash_capacity(max(n, 1) * 2))  # room for as many inserts again before the next rebuild
+        if self._hkeys is None or int(self._hkeys.numel()) != cap:
+            self._hkeys = torch.empty(cap, dtype=torch.int64, device=self.device)
+            self._hvals = torch.empty(cap, dtype=torch.int64, device=self.device)
+        check(lib.qk_hash_clear(ptr(self._hkeys), cap, _stream()))
+        if n:
+            failed = torch.zeros(1, dtype=torch.int32, device=self.device)
+            live_ids = self.ids[rows]
+            check(lib.qk_hash_insert(ptr(self._hkeys), ptr(self._hvals), cap, ptr(live_ids), ptr(rows), n, ptr(failed), _stream()))
+        self._hash_fill = n
+        self._hash_valid = True
+
+    def _hash_add(self, ids: torch.Tensor, rows: torch.Tensor) -> None:
+        """Keep a valid table in step with an append / a moved list (insert or overwrite)."""
+        if not self._hash_valid:
+            return
+        n = int(ids.numel())
+        if self._hash_fill + n > int(self._hkeys.numel()) * 6 // 10:
+            self._hash_valid = False  # too full: rebuilt (larger) on the next lookup
+            return
+        failed = torch.zeros(1, dtype=torch.int32, device=self.device)
+        check(_lib.load().qk_hash_insert(ptr(self._hkeys), ptr(self._hvals), int(self._hkeys.numel()), ptr(ids.contiguous()),
+                                         ptr(rows.contiguous()), n, ptr(failed), _stream()))
+        self._hash_fill += n
+
     def find_rows(self, ids: torch.Tensor) -> torch.Tensor:
         """Arena row of each id (-1 if absent). The reference searches every list linearly
-        (dynamic_inverted_list.cpp:302-321, index_partition.cpp:129-145)."""
-        rows = self.live_rows()
-        ids = ids.to(self.device)
-        if rows.numel() == 0:
-            return torch.full_like(ids, -1)
-        live_ids = self.ids[rows]
-        sorted_ids, perm = torch.sort(live_ids)
-        pos = torch.searchsorted(sorted_ids, ids).clamp(max=sorted_ids.numel() - 1)
-        hit = sorted_ids[pos] == ids
-        return torch.where(hit, rows[perm[pos]], torch.full_like(ids, -1))
+        (dynamic_inverted_list.cpp:302-321, index_partition.cpp:129-145); here one hash probe per id."""
+        ids = ids.to(device=self.device, dtype=torch.int64).contiguous()
+        out = torch.empty_like(ids)
+        if ids.numel() == 0:
+            return out
+        self._ensure_hash()
+        check(_lib.load().qk_hash_lookup(ptr(self._hkeys), ptr(self._hvals), int(self._hkeys.numel()), ptr(ids),
+                                         int(ids.numel()), ptr(out), _stream()))
+        return out
+
+    def device_list_table(self):
+        """(row0 [nslots], size [nslots]) int64 device copies of the host list table (cached per version)."""
+        self.tables()
+        if "list_table" not in self._cache:
+            self._cache["list_table"] = (torch.from_numpy(self.list_row0.astype(np.int64)).to(self.device),
+                                         torch.from_numpy(self.list_size.astype(np.int64)).to(self.device))
+        return self._cache["list_table"]
+
+    def device_sizes_by_pid(self) -> torch.Tensor:
+        """int64 [curr_list_id] device tensor: size of partition id p (0 for ids that are not live)."""
+        self.tables()
+        if "sizes_by_pid" not in self._cache:
+            t = np.zeros(max(self.curr_list_id, 1), dtype=np.int64)
+            for pid, s in self.pid_slot.items():
+                t[pid] = self.list_size[s]
+            self._cache["sizes_by_pid"] = torch.from_numpy(t).to(self.device)
+        return self._cache["sizes_by_pid"]
 
     def remove_ids(self, ids: torch.Tensor) -> int:
         """DynamicInvertedLists::remove_vectors (dynamic_inverted_list.cpp:137-149): every list drops its
-        members found in `ids`, filling each hole with the list's current last element."""
-        rows = self.find_rows(ids)
-        rows = rows[rows >= 0]
-        if rows.numel() == 0:
+        members found in `ids`, filling each hole with the list's current last element. Two kernels (erase from the
+        id table + flag the rows; per-list compaction) and one read-back of the new list sizes; duplicate and absent
+        ids are ignored like the reference's std::set lookup (partition_manager.cpp:306-310)."""
+        lib = _lib.load()
+        ids = ids.to(device=self.device, dtype=torch.int64).contiguous()
+        n = int(ids.numel())
+        nslots = self.slot_pid.size
+        if n == 0 or nslots == 0 or self.rows_used == 0:
             return 0
-        rows_h = np.unique(rows.cpu().numpy())  # sorted; the reference collects the ids in a std::set (partition_manager.cpp:306-310)
-        order = np.argsort(self.list_row0, kind="stable")
-        starts = self.list_row0[order]
-        li = order[np.searchsorted(starts, rows_h, side="right") - 1]
-        src_l, dst_l = [], []
-        # group by list and replay the reference's swap-with-last loop on positions only
-        cuts = np.nonzero(np.diff(li))[0] + 1
-        for grp_rows, s in zip(np.split(rows_h, cuts), li[np.concatenate([[0], cuts])]):
-            s = int(s)
-            r0, n = int(self.list_row0[s]), int(self.list_size[s])
-            pos = (grp_rows - r0).tolist()
-            removed = set(pos)
-            tail = n - 1
-            for p in pos:
-                if p > tail:
-                    break
-                while tail > p and tail in removed:
-                    tail -= 1
-                if tail > p:
-                    src_l.append(r0 + tail)
-                    dst_l.append(r0 + p)
-                tail -= 1
-            self.list_size[s] = n - len(pos)
-        if src_l:
-            src = torch.tensor(src_l, dtype=torch.int64, device=self.device)
-            dst = torch.tensor(dst_l, dtype=torch.int64, device=self.device)
-            self.vectors[dst] = self.vectors[src]
-            self.ids[dst] = self.ids[src]
-            self.norms[dst] = self.norms[src]
+        self._ensure_hash()
+        rows_cap = int(self.vectors.shape[0])
+        flags = torch.zeros(rows_cap, dtype=torch.uint8, device=self.device)
+        n_erased = torch.zeros(1, dtype=torch.int64, device=self.device)
+        check(lib.qk_store_remove(ptr(self._hkeys), ptr(self._hvals), int(self._hkeys.numel()), ptr(ids), n, None, ptr(flags),
+                                  ptr(n_erased), _stream()))
+        row0_d, size_d = self.device_list_table()
+        new_size = torch.empty(nslots, dtype=torch.int64, device=self.device)
+        scratch = torch.empty((2, rows_cap), dtype=torch.int32, device=self.device)
+        check(lib.qk_store_compact_lists(ptr(self.vectors), self.pitch, ptr(self.ids), ptr(self.norms), ptr(row0_d), ptr(size_d),
+                                         nslots, ptr(new_size), ptr(flags), ptr(scratch[0]), ptr(scratch[1]), ptr(self._hkeys),
+                                         ptr(self._hvals), int(self._hkeys.numel()), _stream()))
+        sizes = new_size.cpu().numpy()  # the one synchronisation of a removal
+        live = self.slot_pid >= 0
+        removed = int((self.list_size[live] - sizes[live]).sum())
+        self.list_size = np.where(live, sizes, self.list_size).astype(np.int64)
         self._dirty = True
-        return int(rows_h.size)
+        return removed
+
+    def all_ids(self) -> torch.Tensor:
+        """Ids of all live vectors, partition by partition in ascending partition id (device; one gather)."""
+        pids = self.partition_ids()
+        if pids.size == 0:
+            return torch.zeros(0, dtype=torch.int64, device=self.device)
+        return self.ids[self.rows_of(pids)]
 
     def get_list(self, pid: int, padded: bool = False):
         s = self.pid_slot[int(pid)]
@@ -321,6 +384,7 @@ class PartitionStore:
             self.max_row_norm = float(out.item())
         self.list_size[s] = n
         self._dirty = True
+        self._invalidate_hash()
 
     def rows_of(self, pids) -> torch.Tensor:
         """Arena rows of the members of the given partitions, partition by partition (device int64)."""
@@ -356,21 +420,32 @@ class PartitionStore:
             self.norms[dst] = xn
         self.list_size[slots] = counts
         self._dirty = True
+        self._invalidate_hash()
+
+    def dead_rows(self) -> int:
+        """Arena rows that belong to no live list (lists that moved or were removed leave their old runs behind)."""
+        live = self.slot_pid >= 0
+        return int(self.rows_used - self.list_cap[live].sum()) if self.slot_pid.size else 0
+
+    def maybe_compact(self) -> bool:
+        """Rewrite the arena once more than half of it is dead space."""
+        if self.rows_used > 4096 and 2 * self.dead_rows() > self.rows_used:
+            self.compact()
+            return True
+        return False
 
     def compact(self) -> None:
         """Rewrite the arena without dead space (lists keep their content order)."""
         pids = self.partition_ids()
         slots = np.array([self.pid_slot[int(p)] for p in pids], dtype=np.int64)
         counts = self.list_size[slots]
-        rows = []
-        for s in slots:
-            r0, n = int(self.list_row0[s]), int(self.list_size[s])
-            rows.append(torch.arange(r0, r0 + n, dtype=torch.int64, device=self.device))
-        order = torch.cat(rows) if rows else torch.zeros(0, dtype=torch.int64, device=self.device)
+        order = self.rows_of(pids) if len(pids) else torch.zeros(0, dtype=torch.int64, device=self.device)
         old_v, old_i = self.vectors, self.ids
-        norm = self.max_row_norm
+        norm, next_id, terms = self.max_row_norm, self.curr_list_id, self.filter_terms
         self.init_from_sorted(old_v, old_i, order, counts, pids)
         self.max_row_norm = max(norm, self.max_row_norm)
+        self.curr_list_id = max(next_id, self.curr_list_id)  # partition ids are never reused
+        self.filter_terms = terms
 
     # ------------------------------------------------------------------ device tables for the kernels
     def segment_len(self, num_queries: int, nprobe: int) -> int:

@@ -78,3 +78,28 @@ def test_host_helpers_rand_perm():
     got = clustering.rand_perm_prefix(n, seed, 300)
     assert got.tolist() == perm[:300].tolist()
     assert sorted(clustering.rand_perm_prefix(50, 7, 50).tolist()) == list(range(50))
+
+
+def test_host_split_clusters_rule():
+    """qk_host_split_clusters on a hand-made case: one empty cluster takes a perturbed copy of the roulette's pick and
+    half of its weight (Clustering.cpp:218-247)."""
+    import ctypes as C
+    import numpy as np
+    from quake_b200 import _lib
+    lib = _lib.load()
+    d, k, n = 4, 3, 100
+    hassign = np.array([60.0, 0.0, 40.0], dtype=np.float32)
+    cents = np.array([[1, 2, 3, 4], [9, 9, 9, 9], [5, 6, 7, 8]], dtype=np.float32)
+    nsplit = C.c_int64(0)
+    rc = lib.qk_host_split_clusters(d, k, n, hassign.ctypes.data_as(C.POINTER(C.c_float)),
+                                    cents.ctypes.data_as(C.POINTER(C.c_float)), d, C.byref(nsplit))
+    assert rc == 0 and nsplit.value == 1
+    # std::mt19937(1234): the first draw decides whether cluster 0 (p = 59/97) is taken; whichever cluster cj was taken,
+    # the new centroid is cj * (1 +- 1/1024) on alternating dimensions and the weights are halved
+    eps = 1.0 / 1024
+    picked = 0 if abs(hassign[0] - 30.0) < 1e-6 else 2
+    src = np.array([[1, 2, 3, 4], [9, 9, 9, 9], [5, 6, 7, 8]], dtype=np.float32)[picked]
+    sign = np.array([1, -1, 1, -1], dtype=np.float32)
+    assert np.allclose(cents[1], src * (1 + sign * eps), rtol=1e-6)
+    assert np.allclose(cents[picked], src * (1 - sign * eps), rtol=1e-6)
+    assert hassign[1] == [60.0, 0, 40.0][picked] / 2 and hassign[picked] == [60.0, 0, 40.0][picked] / 2
