@@ -92,8 +92,10 @@ int qk_device_check(int* sm_count, int* cc_major, int* cc_minor);
  *              every query scans the whole list, query_coordinator.cpp:624-626); the work items are then generated
  *              inside the scan kernel and no grouping kernels run.
  * out_rows   : optional [Q x k] int64 arena row of each result (-1 where padded).
- * stats      : optional device int32[4]: {queries that took the exact re-scan path, largest number of
- *              candidates any query appended, total candidates appended (low, high 32 bits)}.
+ * stats      : optional device int32[8]: {queries that took the exact re-scan path, largest number of
+ *              candidates any query appended, total candidates appended (low, high 32 bits), queries whose proof
+ *              would have failed under the 2xTF32 filter's error bound (3xTF32 scans of multi-list stores only;
+ *              see qk_store_t.filter_terms), 3 reserved}.
  */
 size_t qk_scan_workspace_bytes(const qk_store_t* store, int64_t num_queries, int nprobe, int k);
 int qk_scan_partitions(const qk_store_t* store,
@@ -187,12 +189,29 @@ int qk_exchange_merge_topk(const int64_t* ids, const float* distances, int64_t n
  * run_ids/run_distances [Q x k] (padded -1 / +-inf), run_count, radius (initialise to +-1e6,
  * query_coordinator.cpp:524-527), have_probs, probs [Q x m], done, scanned (partitions scanned so far).
  * still_active: device int32, number of listed queries that need another round. k <= 1024. */
+/* qk_aps_thresholds: per listed query, the filter-key threshold under which every row that can still enter its
+ * running top-k must fall (k-th distance so far, widened by the filter's error bound; +inf while fewer than k
+ * results are held). qk_scan_collect: the partition scan with those thresholds given and FIXED -- every row under
+ * them is kept, refined in the reference's exact arithmetic and handed out grouped by the probe rank of its list,
+ * each group best first and cut at k: out_ids / out_distances [Q x nprobe x k], out_cnt [Q x nprobe] entries per
+ * group, out_overflow [Q] = 1 when a query's candidate buffer overflowed (its groups are then unusable). One call
+ * replaces R pseudo-queries with a full top-k each (the per-list results serial_scan merges one by one,
+ * query_coordinator.cpp:537-580). Lists must be single-segment (<= QK_SEGMENT_ROWS rows); workspace as for
+ * qk_scan_partitions. */
+int qk_aps_thresholds(const int32_t* active, int64_t num_active, const float* queries, int64_t query_pitch, int d,
+                      const float* run_distances, const int32_t* run_count, int k, int metric,
+                      float max_row_norm, int filter_terms, uint32_t* out_keys, void* stream);
+int qk_scan_collect(const qk_store_t* store, const float* queries, int64_t num_queries, int64_t query_pitch,
+                    const int32_t* probe_lists, int nprobe, int metric, int k, const uint32_t* threshold_keys,
+                    int64_t* out_ids, float* out_distances, int32_t* out_cnt, int32_t* out_overflow,
+                    void* workspace, size_t workspace_bytes, void* stream);
 int qk_host_beta_table(int d, double* table);
 int qk_aps_boundary_distances(const float* queries, int64_t num_queries, int64_t query_pitch, int d,
                               const float* centroids, int64_t centroid_pitch, const int64_t* cand_rows, int m,
                               int metric, float* out_boundary, void* stream);
 int qk_aps_advance(const int32_t* active, int64_t num_active, int R, int p0, int m, int k, int d, int metric,
                    const int32_t* slots, const int64_t* round_ids, const float* round_distances,
+                   const int32_t* round_cnt /* optional [num_active x R]: entries per list; else lists are padded with id -1 */,
                    const float* boundary, const double* beta_table, float recall_target,
                    float recompute_threshold, int use_precomputed, int64_t* run_ids, float* run_distances,
                    int32_t* run_count, float* radius, int32_t* have_probs, float* probs, int32_t* done,

@@ -81,9 +81,14 @@ PROTOTYPES = {
     "qk_exchange_merge_topk": (C.c_int, [vp, vp, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(vp), vp, vp, vp]),
     "qk_host_beta_table": (C.c_int, [C.c_int, C.POINTER(C.c_double)]),
     "qk_aps_boundary_distances": (C.c_int, [vp, C.c_int64, C.c_int64, C.c_int, vp, C.c_int64, vp, C.c_int, C.c_int, vp, vp]),
+    "qk_aps_thresholds": (C.c_int, [vp, C.c_int64, vp, C.c_int64, C.c_int, vp, vp, C.c_int, C.c_int, C.c_float, C.c_int, vp, vp]),
+    "qk_scan_collect": (
+        C.c_int,
+        [C.POINTER(QkStore), vp, C.c_int64, C.c_int64, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, C.c_size_t, vp],
+    ),
     "qk_aps_advance": (
         C.c_int,
-        [vp, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, C.c_float, C.c_float,
+        [vp, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, C.c_float, C.c_float,
          C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp],
     ),
     "qk_kmeans_assign_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int64, C.c_int]),

@@ -7,6 +7,7 @@ Host-side mirror of the APS part of QueryCoordinator::serial_scan
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -14,11 +15,13 @@ import torch
 from . import _lib
 from ._lib import check, ptr
 
-_FIRST_ROUND = 4   # probe ranks scanned in the first round
+_FIRST_ROUND = 2   # probe ranks scanned in the first round (pseudo-queries with a full top-k each)
 _MAX_ROUND = 128   # ... doubling every round while most queries are still active
 _MAX_PSEUDO = 1 << 17  # pseudo-queries (query, rank) per scan call
 
 _beta_tables: dict = {}
+_TRACE = os.environ.get("QK_APS_TRACE") == "1"
+_trace_t = [0.0]
 
 
 def _stream():
@@ -73,22 +76,70 @@ def adaptive_scan(index, xq: torch.Tensor, cand_rows: torch.Tensor, slots: torch
     scanned = torch.zeros(Q, dtype=torch.int32, device=dev)
     still = torch.zeros(1, dtype=torch.int32, device=dev)
 
+    # Rounds of R probe ranks. While some active query holds fewer than k results (no finite k-th distance yet) a round
+    # scans every (query, rank) as its own pseudo-query with a full top-k (the first round, normally). After that a
+    # round is ONE scan per active query in collect mode: the query's current k-th distance -- a valid bound for
+    # everything that can still enter its top-k -- is turned into a fixed filter threshold, all rows under it are
+    # refined exactly and grouped by rank, and the advance kernel replays the reference's list-by-list loop on them.
+    # A list of 610 rows then costs a handful of exact distances instead of a 100-deep top-k of its own.
     active = torch.arange(Q, dtype=torch.int32, device=dev)
+    if _TRACE:
+        import time as _t
+        torch.cuda.synchronize()
+        _trace_t[0] = _t.perf_counter()
     p, R = 0, _FIRST_ROUND
+    collect_ok = os.environ.get("QK_APS_COLLECT", "1") != "0" and store.list_size.size > 0 and \
+        int(store.list_size.max()) <= _lib.QK_SEGMENT_ROWS
+    first = True
     while p < m and active.numel() > 0:
         Qa = int(active.numel())
-        r_eff = min(R, m - p, max(1, _MAX_PSEUDO // Qa))
         act64 = active.to(torch.int64)
         xa = xq.index_select(0, act64)
-        xrep = xa.repeat_interleave(r_eff, dim=0)                       # pseudo-query (a, r) = a * r_eff + r
-        probe = slots.index_select(0, act64)[:, p:p + r_eff].reshape(-1, 1).contiguous()
-        r_ids, r_dist = scan_partitions(store, xrep, probe, k, metric, filter_terms=3)  # no re-scan monitor on this path
-        check(lib.qk_aps_advance(ptr(active), Qa, r_eff, p, m, k, d, metric, ptr(slots), ptr(r_ids), ptr(r_dist),
-                                 ptr(boundary), ptr(table), float(sp.recall_target), float(sp.recompute_threshold),
-                                 int(bool(sp.use_precomputed)), ptr(run_ids), ptr(run_dist), ptr(run_cnt), ptr(radius),
-                                 ptr(have), ptr(probs), ptr(done), ptr(scanned), ptr(still), _stream()))
+        use_collect = collect_ok and not first and int(run_cnt.index_select(0, act64).min().item()) >= k
+        done_round = False
+        if use_collect:
+            r_eff = min(R, m - p)
+            probe = slots.index_select(0, act64)[:, p:p + r_eff].contiguous()
+            st, _ = store.tables(_lib.QK_SEGMENT_ROWS)  # whole lists: one segment each (pair slot == probe rank)
+            st3 = _lib.QkStore.from_buffer_copy(st)
+            st3.filter_terms = 3  # no re-scan monitor on this path: the tight filter
+            thr = torch.empty(Qa, dtype=torch.int32, device=dev)
+            check(lib.qk_aps_thresholds(ptr(active), Qa, ptr(xq), xq.stride(0), d, ptr(run_dist), ptr(run_cnt), k, metric,
+                                        float(store.max_row_norm), 3, ptr(thr), _stream()))
+            wsb = lib.qk_scan_workspace_bytes(C.byref(st3), Qa, r_eff, k)
+            ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+            r_ids = torch.empty((Qa, r_eff, k), dtype=torch.int64, device=dev)
+            r_dist = torch.empty((Qa, r_eff, k), dtype=torch.float32, device=dev)
+            r_cnt = torch.empty((Qa, r_eff), dtype=torch.int32, device=dev)
+            ovf = torch.empty(Qa, dtype=torch.int32, device=dev)
+            check(lib.qk_scan_collect(C.byref(st3), ptr(xa), Qa, xa.stride(0), ptr(probe), r_eff, metric, k, ptr(thr),
+                                      ptr(r_ids), ptr(r_dist), ptr(r_cnt), ptr(ovf), ptr(ws), wsb, _stream()))
+            if int(ovf.max().item()) == 0:  # (one host read; an overflow sends the round down the pseudo-query path)
+                check(lib.qk_aps_advance(ptr(active), Qa, r_eff, p, m, k, d, metric, ptr(slots), ptr(r_ids), ptr(r_dist),
+                                         ptr(r_cnt), ptr(boundary), ptr(table), float(sp.recall_target),
+                                         float(sp.recompute_threshold), int(bool(sp.use_precomputed)), ptr(run_ids),
+                                         ptr(run_dist), ptr(run_cnt), ptr(radius), ptr(have), ptr(probs), ptr(done),
+                                         ptr(scanned), ptr(still), _stream()))
+                done_round = True
+        if not done_round:
+            r_eff = min(R if not first else _FIRST_ROUND, m - p, max(1, _MAX_PSEUDO // Qa))
+            xrep = xa.repeat_interleave(r_eff, dim=0)                       # pseudo-query (a, r) = a * r_eff + r
+            probe = slots.index_select(0, act64)[:, p:p + r_eff].reshape(-1, 1).contiguous()
+            r_ids, r_dist = scan_partitions(store, xrep, probe, k, metric, filter_terms=3)
+            check(lib.qk_aps_advance(ptr(active), Qa, r_eff, p, m, k, d, metric, ptr(slots), ptr(r_ids), ptr(r_dist), None,
+                                     ptr(boundary), ptr(table), float(sp.recall_target), float(sp.recompute_threshold),
+                                     int(bool(sp.use_precomputed)), ptr(run_ids), ptr(run_dist), ptr(run_cnt), ptr(radius),
+                                     ptr(have), ptr(probs), ptr(done), ptr(scanned), ptr(still), _stream()))
+        first = False
         p += r_eff
         n_still = int(still.item())   # one host read per round: how many queries go on
+        if _TRACE:
+            import time as _t
+            torch.cuda.synchronize()
+            now = _t.perf_counter()
+            print(f"[aps] ranks {p - r_eff}..{p - 1} {'collect' if done_round else 'pseudo'} active {Qa} -> {n_still} "
+                  f"({(now - _trace_t[0]) * 1e3:.2f} ms)", flush=True)
+            _trace_t[0] = now
         if n_still == 0:
             break
         # every round streams the probed lists again: while most queries are still going, bigger rounds cost less than

@@ -156,6 +156,7 @@ struct ApsArgs {
     const int32_t* slots;       // [Q x m] list slot of every candidate (-1: skip, query_coordinator.cpp:540)
     const int64_t* round_ids;   // [num_active x R x k]
     const float* round_dist;
+    const int32_t* round_cnt;   // optional [num_active x R]: valid entries of every list (else: padded with id -1)
     const float* boundary;      // [Q x m]
     const double* table;        // device [APS_TABLE] or null
     float recall_target, recompute_threshold;
@@ -211,14 +212,23 @@ __global__ void __launch_bounds__(APS_THREADS) aps_advance_kernel(const ApsArgs 
         const float* rdv = a.round_dist + ((size_t)slot_a * a.R + r) * k;
         if (tid == 0) s_cnt = 0;
         __syncthreads();
-        int local = 0;
-        for (int i = tid; i < k; i += blockDim.x) {
-            const int64_t id = rid[i];
-            idB[i] = id;
-            kB[i] = f2key(a.ip ? -rdv[i] : rdv[i]);
-            if (id >= 0) ++local;
+        if (a.round_cnt) {
+            const int c = a.round_cnt[(size_t)slot_a * a.R + r];
+            for (int i = tid; i < c; i += blockDim.x) {
+                idB[i] = rid[i];
+                kB[i] = f2key(a.ip ? -rdv[i] : rdv[i]);
+            }
+            if (tid == 0) s_cnt = c;
+        } else {
+            int local = 0;
+            for (int i = tid; i < k; i += blockDim.x) {
+                const int64_t id = rid[i];
+                idB[i] = id;
+                kB[i] = f2key(a.ip ? -rdv[i] : rdv[i]);
+                if (id >= 0) ++local;
+            }
+            if (local) atomicAdd(&s_cnt, local);
         }
-        if (local) atomicAdd(&s_cnt, local);
         __syncthreads();
         const int cntB = s_cnt;  // valid entries are a prefix (best first, padding last)
         // ---- merge by rank: position of x in the union = own index + number of smaller elements of the other list
@@ -316,9 +326,63 @@ __global__ void __launch_bounds__(APS_THREADS) aps_advance_kernel(const ApsArgs 
     }
 }
 
+// Per active query: the filter-key threshold below which EVERY row whose exact distance can still enter the running
+// top-k must fall (collect mode of the scan). With r = the current k-th distance (the reference's
+// TopkBuffer::get_kth_distance, +-inf while fewer than k results are held) and s the filter score:
+//   l2: exact d^2 >= (|q|^2 (1 - g) + s - e1)(1 - e2)   =>   d <= r implies s <= r^2 / (1 - e2) - |q|^2 (1 - g) + e1
+//   ip: |s + <q,v>| <= err                               =>   <q,v> >= r implies s <= -r + err
+// (the same error terms as the refine step's proof, csrc/refine.cuh), rounded up generously.
+__global__ void aps_thresholds_kernel(const int32_t* __restrict__ active, int64_t num_active, const float* __restrict__ queries,
+                                      int64_t q_pitch, int d, const float* __restrict__ run_dist, const int32_t* __restrict__ run_cnt,
+                                      int k, int ip, float max_row_norm, double filter_gam, uint32_t* __restrict__ out_keys) {
+    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (w >= num_active) return;
+    const int64_t q = active[w];
+    double qn = 0.0;
+    for (int i = lane; i < d; i += 32) {
+        const double x = queries[q * q_pitch + i];
+        qn += x * x;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) qn += __shfl_xor_sync(0xffffffffu, qn, o);
+    if (lane) return;
+    uint32_t key = f2key(INFINITY);  // everything with a valid score
+    if (run_cnt[q] >= k) {
+        const double r = (double)run_dist[q * k + k - 1];
+        const double eps = 5.960464477539063e-08, U = (double)max_row_norm, qnorm = sqrt(qn);
+        const double gam = (d + 8) * eps, e2 = (d / 8 + 12) * eps;
+        double t;
+        if (!ip) {
+            const double base = r * r / (1.0 - e2) - qn * (1.0 - gam) + gam * U * U + 2.0 * (gam + filter_gam) * qnorm * U;
+            t = base + 16.0 * eps * (fabs(base) + r * r + qn);
+        } else {
+            const double err = (gam + filter_gam + e2) * qnorm * U;
+            t = -r + err + 16.0 * eps * (fabs(r) + qnorm * U);
+        }
+        float tf = __double2float_ru(t);
+        tf = nextafterf(tf, INFINITY);
+        if (tf == tf) key = f2key(tf);
+    }
+    out_keys[w] = key;
+}
+
 }  // namespace qk
 
 using namespace qk;
+
+extern "C" int qk_aps_thresholds(const int32_t* active, int64_t num_active, const float* queries, int64_t q_pitch, int d,
+                                 const float* run_distances, const int32_t* run_count, int k, int metric,
+                                 float max_row_norm, int filter_terms, uint32_t* out_keys, void* stream_v) {
+    cudaStream_t stream = (cudaStream_t)stream_v;
+    QK_REQUIRE(active && queries && run_distances && run_count && out_keys && num_active > 0 && k > 0, "bad argument");
+    const double fg = filter_terms == 2 ? 9.765625e-04 + 7.62939453125e-06 : 7.62939453125e-06;
+    aps_thresholds_kernel<<<(unsigned)((num_active * 32 + 255) / 256), 256, 0, stream>>>(
+        active, num_active, queries, q_pitch, d, run_distances, run_count, k, metric == QK_METRIC_INNER_PRODUCT ? 1 : 0,
+        max_row_norm, fg, out_keys);
+    QK_LAUNCHED();
+    return QK_OK;
+}
 
 extern "C" int qk_host_beta_table(int d, double* table) {
     QK_REQUIRE(d > 0 && table, "qk_host_beta_table: bad argument");
@@ -343,7 +407,7 @@ extern "C" int qk_aps_boundary_distances(const float* queries, int64_t Q, int64_
 }
 
 extern "C" int qk_aps_advance(const int32_t* active, int64_t num_active, int R, int p0, int m, int k, int d, int metric,
-                              const int32_t* slots, const int64_t* round_ids, const float* round_distances,
+                              const int32_t* slots, const int64_t* round_ids, const float* round_distances, const int32_t* round_cnt,
                               const float* boundary, const double* beta_table, float recall_target,
                               float recompute_threshold, int use_precomputed, int64_t* run_ids, float* run_distances,
                               int32_t* run_count, float* radius, int32_t* have_probs, float* probs, int32_t* done,
@@ -355,7 +419,8 @@ extern "C" int qk_aps_advance(const int32_t* active, int64_t num_active, int R, 
     QK_REQUIRE(num_active > 0 && R > 0 && m >= 2 && k >= 1 && k <= 1024, "qk_aps_advance: bad sizes (k <= 1024, m >= 2)");
     ApsArgs a;
     a.active = active; a.R = R; a.p0 = p0; a.m = m; a.k = k; a.d = d; a.ip = metric == QK_METRIC_INNER_PRODUCT;
-    a.slots = slots; a.round_ids = round_ids; a.round_dist = round_distances; a.boundary = boundary; a.table = beta_table;
+    a.slots = slots; a.round_ids = round_ids; a.round_dist = round_distances; a.round_cnt = round_cnt; a.boundary = boundary;
+    a.table = beta_table;
     a.recall_target = recall_target; a.recompute_threshold = recompute_threshold; a.use_precomputed = use_precomputed;
     a.run_ids = run_ids; a.run_dist = run_distances; a.run_cnt = run_count; a.radius = radius; a.have_probs = have_probs;
     a.probs = probs; a.done = done; a.scanned = scanned; a.still_active = still_active;

@@ -51,6 +51,14 @@ struct ScanExtras {
     const int32_t* id_to_slot = nullptr;     // ... mapped through this dense table
     int64_t table_size = 0;
     int shard_rank = 0, shard_world = 1;     // shard_world > 1: scan only the partitions with id % world == rank
+    // collect mode (APS rounds, qk_scan_collect): the per-query filter thresholds are GIVEN (device keys, [Q]) and
+    // stay fixed -- every row at or below them is kept -- and instead of a top-k the survivors are refined exactly and
+    // handed out grouped by the probe rank of their list
+    const uint32_t* preset_thresholds = nullptr;
+    int64_t* collect_ids = nullptr;          // [Q x nprobe x k]
+    float* collect_dist = nullptr;           // [Q x nprobe x k]
+    int32_t* collect_cnt = nullptr;          // [Q x nprobe] entries per (query, rank), <= k, best first
+    int32_t* collect_overflow = nullptr;     // [Q] 1 = the candidate buffer overflowed: this query's lists are unusable
 };
 // probe_lists == NULL and probe_ids == NULL: flat mode -- the store has ONE list and every query scans it.
 int scan_partitions_impl(const qk_store_t* st, const float* queries, int64_t Q, int64_t q_pitch,

@@ -67,6 +67,8 @@ struct MergeArgs {
     float max_row_norm;
     const float* max_row_norm_dev;  // optional: the bound lives on the device (k-means assign); overrides max_row_norm
     double filter_gam;  // extra relative error bound of the filter's dot products (tensor-core path), vs |q||v|
+    double probe_gam;   // > 0: also evaluate the proof with THIS filter bound and count the queries that would fail it
+                        // (ctrl[6]): how the host decides whether the cheaper 2xTF32 filter would do for this data
     int64_t* out_ids;
     float* out_dist;
     int64_t* out_rows;
@@ -497,10 +499,21 @@ __device__ void refine_and_emit(const MergeArgs& a, int64_t q, const uint64_t* c
                     const double lb = (qn * (1.0 - gam) + (double)a_score - e1) * (1.0 - e2);
                     const float lbf = __double2float_rd(lb);
                     ok = a.rank_squared ? (lb > (double)rk) : (lbf > 0.f && __fsqrt_rn(lbf) > rk);
+                    if (a.probe_gam > 0.0) {
+                        const double e1p = gam * U * U + 2.0 * (gam + a.probe_gam) * qnorm * U + 4.0 * eps * fabs((double)a_score);
+                        const double lbp = (qn * (1.0 - gam) + (double)a_score - e1p) * (1.0 - e2);
+                        const float lbpf = __double2float_rd(lbp);
+                        const bool okp = a.rank_squared ? (lbp > (double)rk) : (lbpf > 0.f && __fsqrt_rn(lbpf) > rk);
+                        if (!okp) atomicAdd(&a.ctrl[6], 1);
+                    }
                 } else {
                     // scores are -<q,v>: any rejected v has ip <= -a_score + err; need that below the k-th exact ip
                     const double err = (gam + a.filter_gam + e2) * qnorm * U + 4.0 * eps * fabs((double)a_score);
                     ok = (-(double)a_score + err) < -(double)rk;
+                    if (a.probe_gam > 0.0) {
+                        const double errp = (gam + a.probe_gam + e2) * qnorm * U + 4.0 * eps * fabs((double)a_score);
+                        if (!((-(double)a_score + errp) < -(double)rk)) atomicAdd(&a.ctrl[6], 1);
+                    }
                 }
                 *s_flag = ok ? 0 : -1;
             }
@@ -607,10 +620,11 @@ __global__ void __launch_bounds__(MERGE_THREADS, 5) merge_refine_kernel(const Me
     }
     overflow = __syncthreads_or(overflow);
     const int ns = s_n;
-    if (ns < a.kc && !overflow) {
-        // Fewer survivors than candidates wanted is only legitimate when the query probed fewer than kc rows
-        // altogether (every threshold is an upper bound on the kc-th best key). Anything else means a threshold
-        // was too tight (or rows scored NaN): leave the query to the exact re-scan.
+    if (ns < a.k && !overflow) {
+        // Fewer survivors than results wanted is only legitimate when the query probed fewer than k rows altogether.
+        // Anything else (rows that scored NaN, a threshold that somehow got too tight) goes to the exact re-scan.
+        // Between k and kc survivors is fine: all of them are refined and the proof below decides -- thresholds that
+        // follow the running minimum (top-1 mode) legitimately leave only a handful.
         int total = 0;
         const int nslots = probed_slots(a);
         for (int j = tid; j < nslots; j += blockDim.x) {
@@ -625,7 +639,7 @@ __global__ void __launch_bounds__(MERGE_THREADS, 5) merge_refine_kernel(const Me
     const uint64_t* cand = sbuf;
     int m = ns;
     uint32_t a_key = gthr;  // every row that is not a survivor has a filter key above the final threshold
-    bool have_rejects = ns >= a.kc && gthr != KEY_MAX;
+    bool have_rejects = gthr != KEY_MAX;  // KEY_MAX: no threshold ever existed, every valid row is a survivor
     if (!rescan && ns > kcp) {
         // more survivors than the refine holds: keep the kc best by filter key
         const uint64_t* sb = sbuf;
@@ -704,6 +718,106 @@ __global__ void __launch_bounds__(MERGE_THREADS, 5) dense_refine_kernel(const Me
         atomicAdd(reinterpret_cast<unsigned long long*>(a.ctrl + 4), (unsigned long long)m);
     }
     refine_and_emit<kIP>(a, q, cbuf, m, s_T, /*have_rejects=*/rows > m, rescan, s, s_qn, rs, &s_flag);
+}
+
+// ------------------------------------------------------------------------------------------------
+// collect mode (APS rounds): ALL survivors of a scan with given, fixed thresholds are refined exactly and handed out
+// grouped by the probe rank of the list they came from, each group best first (distance, then id) and cut at k -- the
+// per-(query, partition) result lists the sequential APS loop consumes (query_coordinator.cpp:537-580), without a
+// pseudo-query per partition.
+// ------------------------------------------------------------------------------------------------
+static constexpr int COLLECT_CAP = 4096;
+struct CollectArgs {
+    const float* vecs;
+    int64_t pitch;
+    const int64_t* ids;
+    int d;
+    const int64_t* seg_row0;
+    const int32_t* seg_rows;
+    const float* queries;
+    int64_t q_pitch;
+    const int32_t* pair_seg;  // [Q x R] (single-segment lists: pair slot == probe rank)
+    int R, k;
+    const uint64_t* qbuf;
+    const int32_t* qcount;
+    int qcap, cap, np;        // cap = candidates handled per query (<= COLLECT_CAP), np = next power of two
+    int64_t* out_ids;         // [Q x R x k]
+    float* out_dist;
+    int32_t* out_cnt;         // [Q x R]
+    int32_t* overflow;        // [Q]
+};
+
+template <bool kIP>
+__global__ void __launch_bounds__(MERGE_THREADS) collect_refine_kernel(const CollectArgs a) {
+    extern __shared__ __align__(16) unsigned char csm[];
+    uint64_t* comp = reinterpret_cast<uint64_t*>(csm);                 // [np] rank << 44 | distance key << 12 | slot
+    int64_t* cid = reinterpret_cast<int64_t*>(comp + a.np);            // [cap]
+    float* qs = reinterpret_cast<float*>(cid + a.cap);                 // [d padded]
+    long long* srow0 = reinterpret_cast<long long*>(qs + ((a.d + 3) & ~3) + 2);
+    srow0 = reinterpret_cast<long long*>((reinterpret_cast<uintptr_t>(srow0) + 7) & ~(uintptr_t)7);  // [R]
+    int* srows = reinterpret_cast<int*>(srow0 + a.R);                  // [R]
+    int* first = srows + a.R;                                          // [R] first sorted position of every rank
+    const int64_t q = blockIdx.x;
+    const int tid = threadIdx.x;
+    const int appended = a.qcount[q];
+    for (int j = tid; j < a.R; j += MERGE_THREADS) a.out_cnt[q * a.R + j] = 0;
+    if (appended > a.cap) {
+        if (tid == 0) a.overflow[q] = 1;
+        return;
+    }
+    if (tid == 0) a.overflow[q] = 0;
+    const int n = appended;
+    for (int i = tid; i < a.d; i += MERGE_THREADS) qs[i] = a.queries[q * a.q_pitch + i];
+    for (int j = tid; j < a.R; j += MERGE_THREADS) {
+        const int seg = a.pair_seg[q * a.R + j];
+        srow0[j] = seg >= 0 ? a.seg_row0[seg] : -1;
+        srows[j] = seg >= 0 ? a.seg_rows[seg] : 0;
+        first[j] = n;
+    }
+    __syncthreads();
+    const uint64_t* cand = a.qbuf + (size_t)q * a.qcap;
+    for (int base = 0; base < a.np; base += MERGE_THREADS / 8) {
+        const int i = base + (tid >> 3), j8 = tid & 7;
+        if (i < n) {  // uniform inside every 8-lane group
+            const uint32_t row = (uint32_t)cand[i];
+            const float dist = ref_pair_distance_g8<kIP>(qs, a.vecs + (int64_t)row * a.pitch, a.d, j8);
+            if (j8 == 0) {
+                int rank = 0;
+                for (int j = 0; j < a.R; ++j)
+                    if (srow0[j] >= 0 && (long long)row >= srow0[j] && (long long)row < srow0[j] + srows[j]) { rank = j; break; }
+                const uint32_t dk = f2key(kIP ? -dist : __fsqrt_rn(dist));
+                comp[i] = ((uint64_t)rank << 44) | ((uint64_t)dk << 12) | (uint64_t)i;
+                cid[i] = a.ids ? a.ids[row] : (int64_t)row;
+            }
+        } else if (i < a.np && j8 == 0) {
+            comp[i] = COMP_MAX;
+        }
+    }
+    // (rank, distance key) order; ties between equal keys of one rank by id
+    const int64_t* cidc = cid;
+    block_bitonic_sort(comp, a.np, [cidc](uint64_t x, uint64_t y) {
+        const uint64_t hx = x >> 12, hy = y >> 12;
+        if (hx != hy) return hx < hy;
+        if (x == COMP_MAX || y == COMP_MAX) return x < y;
+        return cidc[x & 0xfffu] < cidc[y & 0xfffu];
+    });
+    for (int i = tid; i < n; i += MERGE_THREADS) {
+        const int r = (int)(comp[i] >> 44);
+        if (i == 0 || (int)(comp[i - 1] >> 44) != r) first[r] = i;
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += MERGE_THREADS) {
+        const uint64_t c = comp[i];
+        const int r = (int)(c >> 44);
+        const int idx = i - first[r];
+        if (idx < a.k) {
+            const float v = key2f((uint32_t)(c >> 12));
+            const size_t o = ((size_t)q * a.R + r) * a.k + idx;
+            a.out_ids[o] = cid[c & 0xfffu];
+            a.out_dist[o] = kIP ? -v : v;
+        }
+        if (i + 1 == n || (int)(comp[i + 1] >> 44) != r) a.out_cnt[q * a.R + r] = idx + 1 < a.k ? idx + 1 : a.k;
+    }
 }
 
 }  // namespace qk

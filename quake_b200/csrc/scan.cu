@@ -60,7 +60,7 @@ struct ScanPlan {
     size_t smem;  // dynamic shared memory of scan_kernel
     // workspace offsets (bytes)
     size_t off_pair_seg, off_seg_count, off_seg_fill, off_seg_start, off_item_start, off_seg_pairs, off_items,
-        off_ctrl, off_gthr, off_flags, off_qcount, off_qbuf, total;
+        off_ctrl, off_gthr, off_qdelta, off_flags, off_qcount, off_qbuf, total;
     int qcap;     // entries of the per-query candidate buffer
     int sample;   // rows sampled per query for the threshold seed (0: no seeding)
     int flat_seed;  // every query samples the same rows (single-list store): seed scores as one small GEMM
@@ -179,6 +179,7 @@ static int make_plan(const qk_store_t* st, int64_t Q, int nprobe, int k, ScanPla
     size_t max_items = QP / gq + (QP < S ? QP : S) + 1;
     p->off_items = o;      o = align_up(o + max_items * sizeof(WorkItem), 256);
     p->off_gthr = o;       o = align_up(o + (size_t)Q * 4, 256);
+    p->off_qdelta = o;     o = align_up(o + (size_t)Q * 4, 256);
     {
         const double mean_list = st->num_lists > 0 ? (double)st->num_rows / st->num_lists : 0.0;
         p->qcap = candidate_buffer_cap(p->kc, st->num_lists == 1 ? 0.0 : mean_list * nprobe);  // single-list stores: one seed sample fits all rows
@@ -243,14 +244,14 @@ __device__ __forceinline__ int probe_slot(const ProbeSource& ps, int64_t i) {
 __global__ void expand_pairs_kernel(const ProbeSource probe, int64_t Q, int nprobe, int P,
                                     const int32_t* __restrict__ list_seg0, const int32_t* __restrict__ list_nseg,
                                     int num_lists, int32_t* __restrict__ pair_seg, int32_t* __restrict__ seg_count,
-                                    uint32_t* __restrict__ gthr, bool single_segment_lists) {
+                                    uint32_t* __restrict__ gthr, bool single_segment_lists, bool reset_thresholds) {
     if (single_segment_lists) {
         // one thread per (query, probe)
         int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
         if (i >= Q * nprobe) return;
         int64_t q = i / nprobe;
         int j = (int)(i - q * nprobe);
-        if (j == 0) gthr[q] = KEY_MAX;
+        if (j == 0 && reset_thresholds) gthr[q] = KEY_MAX;
         int l = probe_slot(probe, i);
         int seg = -1;
         if (l >= 0 && l < num_lists && list_nseg[l] > 0) seg = list_seg0[l];
@@ -262,7 +263,7 @@ __global__ void expand_pairs_kernel(const ProbeSource probe, int64_t Q, int npro
         if (i >= Q * P) return;
         int64_t q = i / P;
         int s2 = (int)(i - q * P);
-        if (s2 == 0) gthr[q] = KEY_MAX;
+        if (s2 == 0 && reset_thresholds) gthr[q] = KEY_MAX;
         int l = probe_slot(probe, q);
         int seg = -1;
         if (l >= 0 && l < num_lists && s2 < list_nseg[l]) seg = list_seg0[l] + s2;
@@ -272,7 +273,7 @@ __global__ void expand_pairs_kernel(const ProbeSource probe, int64_t Q, int npro
         // one thread per query, sequential over its probes
         int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
         if (q >= Q) return;
-        gthr[q] = KEY_MAX;
+        if (reset_thresholds) gthr[q] = KEY_MAX;
         int pos = 0;
         for (int j = 0; j < nprobe; ++j) {
             int l = probe_slot(probe, q * nprobe + j);
@@ -673,6 +674,30 @@ __global__ void __launch_bounds__(256) seed_select_flat_kernel(const uint32_t* _
     }
 }
 
+// Top-1 mode margins: delta[q] = 3 x the filter/refine error bound of query q (the proof of refine.cuh needs the
+// rejected rows' scores to exceed the best one by more than 2 x that bound), rounded up.
+__global__ void top1_delta_kernel(const float* __restrict__ queries, int64_t q_pitch, int d, int64_t Q, float max_row_norm,
+                                  const float* __restrict__ max_row_norm_dev, double filter_gam, int ip,
+                                  float* __restrict__ qdelta) {
+    const int64_t q = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (q >= Q) return;
+    double qn = 0.0;
+    for (int i = lane; i < d; i += 32) {
+        const double x = queries[q * q_pitch + i];
+        qn += x * x;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) qn += __shfl_xor_sync(0xffffffffu, qn, o);
+    if (lane) return;
+    const double U = (double)(max_row_norm_dev ? *max_row_norm_dev : max_row_norm), qnorm = sqrt(qn);
+    const double eps = 5.960464477539063e-08, gam = (d + 8) * eps, e2 = (d / 8 + 12) * eps;
+    double e;
+    if (!ip) e = gam * U * U + 2.0 * (gam + filter_gam) * qnorm * U + (8.0 * eps + e2) * (qnorm + U) * (qnorm + U);
+    else e = (gam + filter_gam + e2) * qnorm * U + 8.0 * eps * qnorm * U;
+    qdelta[q] = __double2float_ru(3.0 * e) * 1.0001f + 1e-30f;
+}
+
 // ------------------------------------------------------------------------------------------------
 // 4. the scan (filter) kernel
 // ------------------------------------------------------------------------------------------------
@@ -694,6 +719,9 @@ struct ScanArgs {
     int dense_rows;
     // flat mode (single-list store scanned without a probe table): the work items are the grid (segment x chunk of gq
     // consecutive queries), item it = seg * flat_nchunks + chunk, computed in the kernel -- no pair tables, no grouping
+    int fixed_thr;  // collect mode: thresholds are given and never refreshed
+    int top1;       // k = 1: thresholds follow the running minimum + qdelta[query] (no seeds, no kc-th refresh needed)
+    const float* qdelta;  // [Q] top-1 margins
     int terms;  // tensor-core filter: 3 = 3xTF32 (a_hi b_hi + a_lo b_hi + a_hi b_lo), 2 = 2xTF32 (no a_lo term)
     int flat;
     int flat_nchunks;
@@ -950,7 +978,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) scan_kernel(const ScanArgs a,
                         if (slot < qcap) qb[slot] = ((uint64_t)pd.k1[j] << 32) | (pd.arow0 + 32 + lane);
                     }
                     const int e = b + c0 + c1;
-                    if (b / step != e / step && e >= kc) cross |= 1u << j;
+                    if (b / step != e / step && e >= kc && !a.fixed_thr) cross |= 1u << j;
                 }
                 // refresh the thresholds of the queries that crossed. The entries this warp just stored are
                 // read back by other lanes: order them first.
@@ -989,7 +1017,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) scan_kernel(const ScanArgs a,
                     const uint32_t k0 = kbase[g * KP + lane], k1 = kbase[g * KP + 32 + lane];
                     unsigned m0 = __ballot_sync(0xffffffffu, k0 <= lim);
                     unsigned m1 = __ballot_sync(0xffffffffu, k1 <= lim);
-                    if (kc <= 48 && __popc(m0) + __popc(m1) > kc + 8) {
+                    if (kc <= 48 && !a.fixed_thr && __popc(m0) + __popc(m1) > kc + 8) {
                         // a loose (stale or missing) threshold: this tile alone bounds the kc-th best key
                         const uint32_t* kq = kbase + g * KP;
                         const uint32_t t = radix_select([kq](int i) { return kq[i]; }, TV, kc, hist, lane);
@@ -1251,7 +1279,9 @@ int qk::scan_partitions_impl(const qk_store_t* st, const float* queries, int64_t
                              float* out_dist, int64_t* out_rows, void* workspace, size_t workspace_bytes,
                              int32_t* stats, void* stream_v, const ScanExtras& ex) {
     cudaStream_t stream = (cudaStream_t)stream_v;
-    QK_REQUIRE(st && queries && out_ids && out_dist, "null argument");
+    const bool collect = ex.preset_thresholds != nullptr;
+    QK_REQUIRE(st && queries && (collect || (out_ids && out_dist)), "null argument");
+    QK_REQUIRE(!collect || (ex.collect_ids && ex.collect_dist && ex.collect_cnt && ex.collect_overflow), "collect outputs");
     QK_REQUIRE(metric == QK_METRIC_L2 || metric == QK_METRIC_INNER_PRODUCT, "metric %d not supported", metric);
     QK_REQUIRE(Q > 0 && nprobe > 0, "empty query batch");
     QK_REQUIRE(st->num_segments > 0 && st->num_lists > 0, "store has no segments");
@@ -1262,6 +1292,14 @@ int qk::scan_partitions_impl(const qk_store_t* st, const float* queries, int64_t
     ScanPlan p;
     int rc = make_plan(st, Q, nprobe, k, &p, /*allow_dense=*/flat);  // the dense key matrix is indexed by (query, row of THE list)
     if (rc) return rc;
+    // top-1 mode: k = 1 on the tensor-core path -- thresholds follow the running minimum, no seeds
+    const bool top1 = (k == 1) && (g_scan_variant == 0) && p.dp <= 128 && !collect && !p.dense && getenv("QK_NO_TOP1") == nullptr;
+    if (top1) p.sample = 0;
+    if (collect) {
+        QK_REQUIRE(!flat && p.P == nprobe, "collect mode needs single-segment lists and a probe table");
+        if (p.P != nprobe) return QK_ERR_UNSUPPORTED;
+        p.sample = 0;  // thresholds are given
+    }
     QK_REQUIRE(q_pitch >= p.dp && q_pitch % 4 == 0, "query pitch %lld must be a multiple of 4 and >= %d",
                (long long)q_pitch, p.dp);
     QK_REQUIRE(((uintptr_t)queries % 16 == 0) && ((uintptr_t)st->vectors % 16 == 0), "vectors must be 16-byte aligned");
@@ -1303,16 +1341,17 @@ int qk::scan_partitions_impl(const qk_store_t* st, const float* queries, int64_t
         if (single) {
             int64_t n = Q * nprobe;
             expand_pairs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(ps, Q, nprobe, p.P, st->list_seg0, st->list_nseg,
-                                                                                  st->num_lists, pair_seg, seg_count, gthr, true);
+                                                                                  st->num_lists, pair_seg, seg_count, gthr, true, !collect);
         } else if (nprobe == 1) {
             int64_t n = Q * p.P;
             expand_pairs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(ps, Q, nprobe, p.P, st->list_seg0, st->list_nseg,
-                                                                                  st->num_lists, pair_seg, seg_count, gthr, false);
+                                                                                  st->num_lists, pair_seg, seg_count, gthr, false, !collect);
         } else {
             expand_pairs_kernel<<<(unsigned)((Q + 127) / 128), 128, 0, stream>>>(ps, Q, nprobe, p.P, st->list_seg0, st->list_nseg,
-                                                                                  st->num_lists, pair_seg, seg_count, gthr, false);
+                                                                                  st->num_lists, pair_seg, seg_count, gthr, false, !collect);
         }
         QK_LAUNCHED();
+        if (collect) QK_CUDA(cudaMemcpyAsync(gthr, ex.preset_thresholds, (size_t)Q * 4, cudaMemcpyDeviceToDevice, stream));
     }
     // The seeds only need the pair table; the grouping kernels (prefix, scatter) only the histogram: run them side by
     // side (fork / join through a second stream -- inside a CUDA-graph capture this becomes two parallel branches).
@@ -1388,6 +1427,15 @@ int qk::scan_partitions_impl(const qk_store_t* st, const float* queries, int64_t
     sa.P = p.P; sa.kc = p.kc; sa.gq = p.gq; sa.nq = p.nq; sa.qcap = p.qcap;
     sa.Q = Q; sa.seg_row0 = st->seg_row0; sa.seg_rows = st->seg_rows;
     sa.terms = terms;
+    sa.fixed_thr = collect ? 1 : 0;
+    sa.top1 = top1 ? 1 : 0;
+    sa.qdelta = (const float*)(ws + p.off_qdelta);
+    if (top1) {
+        top1_delta_kernel<<<(unsigned)((Q * 32 + 255) / 256), 256, 0, stream>>>(queries, q_pitch, st->d, Q, st->max_row_norm,
+                                                                               ex.max_row_norm_dev, fgam, ip ? 1 : 0,
+                                                                               (float*)(ws + p.off_qdelta));
+        QK_LAUNCHED();
+    }
     {
         static int dbg = -1;
         if (dbg < 0) { const char* e = getenv("QK_SCAN_DBG"); dbg = e ? atoi(e) : 0; }
@@ -1412,6 +1460,28 @@ int qk::scan_partitions_impl(const qk_store_t* st, const float* queries, int64_t
     if (rc) return rc;
     if (rec) QK_CUDA(cudaEventRecord(rec->stop, stream));
 
+    if (collect) {
+        CollectArgs ca;
+        memset(&ca, 0, sizeof(ca));
+        ca.vecs = st->vectors; ca.pitch = st->pitch; ca.ids = st->ids; ca.d = st->d;
+        ca.seg_row0 = st->seg_row0; ca.seg_rows = st->seg_rows; ca.queries = queries; ca.q_pitch = q_pitch;
+        ca.pair_seg = pair_seg; ca.R = nprobe; ca.k = k; ca.qbuf = qbuf; ca.qcount = qcount; ca.qcap = p.qcap;
+        ca.out_ids = ex.collect_ids; ca.out_dist = ex.collect_dist; ca.out_cnt = ex.collect_cnt; ca.overflow = ex.collect_overflow;
+        int cap = p.qcap < COLLECT_CAP ? p.qcap : COLLECT_CAP;
+        int np = 1;
+        while (np < cap) np <<= 1;
+        ca.cap = cap; ca.np = np;
+        const size_t csm = (size_t)np * 8 + (size_t)cap * 8 + (size_t)((st->d + 3) & ~3) * 4 + (size_t)nprobe * 16 + 64;
+        if (ip) {
+            if ((rc = ensure_smem(collect_refine_kernel<true>, csm))) return rc;
+            collect_refine_kernel<true><<<(unsigned)Q, MERGE_THREADS, csm, stream>>>(ca);
+        } else {
+            if ((rc = ensure_smem(collect_refine_kernel<false>, csm))) return rc;
+            collect_refine_kernel<false><<<(unsigned)Q, MERGE_THREADS, csm, stream>>>(ca);
+        }
+        QK_LAUNCHED();
+        return QK_OK;
+    }
     MergeArgs ma;
     memset(&ma, 0, sizeof(ma));
     ma.vecs = st->vectors; ma.pitch = st->pitch; ma.ids = st->ids; ma.d = st->d;
@@ -1422,6 +1492,9 @@ int qk::scan_partitions_impl(const qk_store_t* st, const float* queries, int64_t
     ma.max_row_norm = st->max_row_norm;
     ma.max_row_norm_dev = ex.max_row_norm_dev;
     ma.filter_gam = fgam;
+    // a 3-term scan also reports how many of its queries the 2-term filter's looser bound would have sent to the
+    // exact re-scan (stats[4]): the host's filter precision policy starts safe and relaxes on this evidence
+    ma.probe_gam = (use_mma && terms == 3 && !flat) ? filter_gamma(2) : 0.0;
     ma.out_ids = out_ids; ma.out_dist = out_dist; ma.out_rows = out_rows;
     ma.force_rescan = g_force_rescan;
     ma.rank_squared = ex.rank_squared;
@@ -1452,8 +1525,24 @@ int qk::scan_partitions_impl(const qk_store_t* st, const float* queries, int64_t
         }
     }
     QK_LAUNCHED();
-    if (stats) QK_CUDA(cudaMemcpyAsync(stats, ctrl + 2, 4 * sizeof(int32_t), cudaMemcpyDeviceToDevice, stream));
+    if (stats) QK_CUDA(cudaMemcpyAsync(stats, ctrl + 2, 5 * sizeof(int32_t), cudaMemcpyDeviceToDevice, stream));
     return QK_OK;
+}
+
+// ---- collect mode: all rows under given per-query thresholds, refined exactly, grouped by probe rank ------------
+extern "C" int qk_scan_collect(const qk_store_t* st, const float* queries, int64_t Q, int64_t q_pitch,
+                               const int32_t* probe_lists, int nprobe, int metric, int k, const uint32_t* threshold_keys,
+                               int64_t* out_ids, float* out_dist, int32_t* out_cnt, int32_t* out_overflow,
+                               void* workspace, size_t workspace_bytes, void* stream_v) {
+    QK_REQUIRE(probe_lists && threshold_keys && out_ids && out_dist && out_cnt && out_overflow, "null argument");
+    ScanExtras ex;
+    ex.preset_thresholds = threshold_keys;
+    ex.collect_ids = out_ids;
+    ex.collect_dist = out_dist;
+    ex.collect_cnt = out_cnt;
+    ex.collect_overflow = out_overflow;
+    return qk::scan_partitions_impl(st, queries, Q, q_pitch, probe_lists, nprobe, metric, k, nullptr, nullptr, nullptr,
+                                    workspace, workspace_bytes, nullptr, stream_v, ex);
 }
 
 // ---- two-level fixed-nprobe search in one call ------------------------------------------------------

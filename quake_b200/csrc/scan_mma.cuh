@@ -55,6 +55,7 @@ struct MmaDesc {  // published in shared memory by the producer warp for every w
     WorkItem w;
     int q[MMA_NQ];       // query index of every query slot (-1: unused slot)
     float limf[MMA_NQ];  // the queries' filter-score thresholds (float domain; +inf = none yet, -inf = unused slot)
+    float delta[MMA_NQ]; // top-1 mode: the margin added to a running minimum to make it a threshold (see ScanArgs::top1)
 };
 
 static size_t scan_mma_smem_bytes() {
@@ -259,6 +260,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) scan_mma_kernel(const ScanArgs
             }
             descs[id].q[lane] = q;
             descs[id].limf[lane] = q >= 0 ? key2lim(gthr) : -INFINITY;
+            descs[id].delta[lane] = (a.top1 && q >= 0) ? __ldg(a.qdelta + q) : 0.f;
             if (lane == 0) descs[id].w = m;
             __syncwarp();
             if (lane == 0) mbar_arrive(i_full + id);
@@ -506,6 +508,32 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) scan_mma_kernel(const ScanArgs
                 __syncwarp();
                 if (lane == 0) mbar_arrive(d_empty + db);
                 if (QK_DBG(a, 1)) continue;
+                if (a.top1 && !a.dense) {
+                    // top-1 mode (k = 1: the k-means assign, add()'s nearest-centroid search): the running minimum of a
+                    // query's scores plus a margin of a few filter error bounds IS a valid threshold -- every row that
+                    // can still be the exact nearest scores under it -- and it is known after the first tile instead of
+                    // after kc survivors. Per slot: warp-wide minimum of this tile's 32 rows (one REDUX), folded into
+                    // the item's limit and published with atomicMin when it improves it.
+                    const float* delta = descs[id].delta;
+                    uint32_t my_min = KEY_MAX;
+#pragma unroll
+                    for (int g = 0; g < MMA_NQ; ++g) {
+                        if (g >= npad) break;  // warp-uniform
+                        const float dot = __uint_as_float(v[g]);
+                        const float sc = kIP ? -dot : fmaf(-2.f, dot, nrm);
+                        const uint32_t key = r < tr ? f2key(sc) : KEY_MAX;
+                        const uint32_t wmin = __reduce_min_sync(0xffffffffu, key);
+                        if (lane == g) my_min = wmin;
+                    }
+                    if (lane < g_cnt && my_min != KEY_MAX) {
+                        const float cand = __fadd_ru(key2f(my_min), delta[lane]);
+                        if (cand < limf[lane]) {
+                            limf[lane] = cand;  // benign race between the warps of the item: every value written is valid
+                            atomicMin(a.gthr + dq[lane], f2key(cand));
+                        }
+                    }
+                    __syncwarp();
+                }
                 // ---- scores of this thread's row against the 32 query slots; bit g of pm: the score passes
                 uint32_t pm = 0;
 #pragma unroll
@@ -558,7 +586,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) scan_mma_kernel(const ScanArgs
                             if (slot < qcap) a.qbuf[(size_t)qs[i] * qcap + slot] = ((uint64_t)key[i] << 32) | arow;
                             // the fill passed a multiple of 64: ask a refresh warp for a new threshold (a busy
                             // mailbox just drops the request -- thresholds are an optimisation)
-                            if ((slot & 63) == 63 && slot + 1 >= kc && *my_box == 0ull)
+                            if ((slot & 63) == 63 && slot + 1 >= kc && !a.fixed_thr && !a.top1 && *my_box == 0ull)
                                 *my_box = ((unsigned long long)(qs[i] + 1) << 32) | (uint32_t)(slot + 1);
                         }
                     }

@@ -37,11 +37,13 @@ def _device() -> torch.device:
 
 
 # Filter precision policy of the PARTITION scan of a two-level index ("auto" | "2" | "3", env QK_FILTER): the
-# tensor-core filter may drop the a_lo term (2xTF32: ~13 % faster scan kernel at C2). Results stay exact either way --
-# the refine step proves every answer and re-scans a query exactly when the looser filter cannot separate its k-th
-# neighbour -- but re-scans are slow, so "auto" starts at 2 terms and falls back to 3 for good as soon as a search
-# reports more than 1 % of its queries re-scanned (checked from the statistics of the previous calls, no extra sync).
-# Coarse scans, flat indexes and the k-means assign always run 3xTF32 (their top-k margins are much tighter).
+# tensor-core filter may drop the a_lo term (2xTF32: a few % faster scan kernel). Results stay exact either way -- the
+# refine step proves every answer and re-scans a query exactly when the looser filter cannot separate its k-th
+# neighbour -- but re-scans are slow (one CTA walks all probed rows), so "auto" starts SAFE at 3 terms; every 3-term
+# scan also counts the queries whose proof would have failed under the 2-term bound, and once >= 256 queries have been
+# seen with at most 0.5 % such failures the store switches to 2 terms. A 2-term search that reports more than 1 % of
+# its queries re-scanned switches back for good. All of it from the asynchronously read statistics of earlier calls.
+# Coarse scans, flat indexes, APS and the k-means assign always run 3xTF32 (their top-k margins are much tighter).
 FILTER_POLICY = os.environ.get("QK_FILTER", "auto")
 LAST_SCAN_STATS = None  # set QK_SCAN_STATS=1: int32[4] device tensor of the last qk_scan_partitions call
 
@@ -61,18 +63,21 @@ def launch_count() -> int:
 
 
 class _FilterMonitor:
-    """Asynchronous read-back of a search's scan statistics (16 bytes through pinned memory + an event; never waited
-    for): how many queries of an earlier batch fell into the exact re-scan."""
+    """Asynchronous read-back of a search's scan statistics (32 bytes through pinned memory + an event; never waited
+    for): how many queries of an earlier batch fell into the exact re-scan / would have under the 2-term filter."""
 
     def __init__(self):
-        self.host = torch.zeros(4, dtype=torch.int32).pin_memory()
+        self.host = torch.zeros(8, dtype=torch.int32).pin_memory()
         self.event = None
         self.queries = 0
         self.calls = 0
+        self.seen = 0         # queries observed in 3-term mode ...
+        self.would_fail = 0   # ... and how many of them the 2-term bound would have re-scanned
+        self.locked = False   # a 2-term search re-scanned too much: 3 terms for good
 
     def submit(self, stats: torch.Tensor, queries: int) -> None:
         self.calls += 1
-        if self.event is not None or stats is None:
+        if self.event is not None or stats is None or self.locked:
             return  # one read-back in flight at a time
         if self.calls > 32 and (self.calls & 7):
             return  # steady state: every 8th call
@@ -82,11 +87,11 @@ class _FilterMonitor:
         self.queries = queries
 
     def poll(self):
-        """(queries re-scanned, queries) of a finished read-back, or None."""
+        """(queries re-scanned, would-fail-under-2-terms, queries) of a finished read-back, or None."""
         if self.event is None or not self.event.query():
             return None
         self.event = None
-        return int(self.host[0]), self.queries
+        return int(self.host[0]), int(self.host[4]), self.queries
 
 
 class _SearchPlan:
@@ -176,7 +181,7 @@ def scan_partitions(store: PartitionStore, xq: torch.Tensor, probe_slots: torch.
     stats = None
     if os.environ.get("QK_SCAN_STATS") == "1":
         global LAST_SCAN_STATS
-        stats = LAST_SCAN_STATS = torch.zeros(4, dtype=torch.int32, device=dev)
+        stats = LAST_SCAN_STATS = torch.zeros(8, dtype=torch.int32, device=dev)
     for b in range(0, Q, chunk):
         n = min(chunk, Q - b)
         check(lib.qk_scan_partitions(C.byref(st), ptr(xq[b:]), n, xq.stride(0),
@@ -343,23 +348,35 @@ class QuakeIndex:
         return cache[Q]
 
     def _apply_filter_policy(self) -> None:
-        """Filter precision of the partition scan (see FILTER_POLICY): two-level indexes start at 2xTF32 unless told
-        otherwise; everything else stays at 3xTF32."""
+        """Filter precision of the partition scan (see FILTER_POLICY): 3xTF32 unless forced to 2; "auto" relaxes a
+        two-level index to 2 terms on evidence (_filter_feedback)."""
         if self.store is None:
             return
         two_level = self.parent is not None and self.current_level == 0
-        self.store.set_filter_terms(2 if (two_level and FILTER_POLICY in ("auto", "2")) else 3)
+        self.store.set_filter_terms(2 if (two_level and FILTER_POLICY == "2") else 3)
 
     def _filter_feedback(self) -> None:
         mon = self.__dict__.get("_monitor")
-        if mon is None or self.store.filter_terms != 2 or FILTER_POLICY != "auto":
+        if mon is None or FILTER_POLICY != "auto" or mon.locked:
             return
         got = mon.poll()
-        if got is not None and got[0] > max(2, got[1] // 100):
-            # the 2-term filter cannot separate this data's neighbours often enough: exact results either way, but every
-            # failed proof is an exhaustive re-scan. 3xTF32 from now on (plans are re-captured: the store version moves).
-            self.store.set_filter_terms(3)
-            self.filter_fallback = got
+        if got is None:
+            return
+        rescanned, would_fail, queries = got
+        if self.store.filter_terms == 2:
+            if rescanned > max(2, queries // 100):
+                # the 2-term filter cannot separate this data's neighbours often enough: 3xTF32 for good (plans are
+                # re-captured: the store version moves)
+                self.store.set_filter_terms(3)
+                mon.locked = True
+                self.filter_fallback = got
+        else:
+            mon.seen += queries
+            mon.would_fail += would_fail
+            if mon.seen >= 256:
+                if mon.would_fail * 200 <= mon.seen:
+                    self.store.set_filter_terms(2)
+                mon.seen = mon.would_fail = 0
 
     def _reset_caches(self) -> None:
         """build() / load() install a new store: captured plans, probe tables and staging buffers of the old one go."""
@@ -406,7 +423,7 @@ class QuakeIndex:
         p_ids = torch.empty((Q, np_), dtype=torch.int64, device=dev)
         # statistics of the partition scan {queries re-scanned exactly, max / total candidates}: the filter precision
         # policy reads them back asynchronously (_FilterMonitor)
-        stats = torch.empty(4, dtype=torch.int32, device=dev)
+        stats = torch.empty(8, dtype=torch.int32, device=dev)
         self._last_stats = stats
         if os.environ.get("QK_SCAN_STATS") == "1":
             global LAST_SCAN_STATS
@@ -491,7 +508,7 @@ class QuakeIndex:
                 self._last_stats = None
                 ids, dist, p_ids = self._search_core(xq, sp)
                 stats = self._last_stats
-            if monitored and self.store.filter_terms == 2 and FILTER_POLICY == "auto":
+            if monitored and FILTER_POLICY == "auto":
                 self.__dict__.setdefault("_monitor", _FilterMonitor()).submit(stats, Q)
             parent_info.total_time_ns = int((time.perf_counter() - t1) * 1e9)
         if self.parent is not None:
