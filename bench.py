@@ -380,7 +380,8 @@ def run_b200(args):
     st4 = _qi.LAST_SCAN_STATS.cpu().tolist()
     os.environ.pop("QK_SCAN_STATS")
     scan_stats = {"queries_rescanned": st4[0], "max_appended_per_query": st4[1],
-                  "mean_appended_per_query": ((st4[3] << 32) | (st4[2] & 0xffffffff)) / W["Q"]}
+                  "mean_appended_per_query": ((st4[3] << 32) | (st4[2] & 0xffffffff)) / W["Q"],
+                  "threshold_refreshes": st4[6], "refresh_requests_dropped": st4[7]}
     for _ in range(args.warmup):
         idx._search_device(xq_d, sp)
     lib.qk_profile_begin(4 * args.steps + 8)

@@ -59,6 +59,24 @@ struct ScanExtras {
     float* collect_dist = nullptr;           // [Q x nprobe x k]
     int32_t* collect_cnt = nullptr;          // [Q x nprobe] entries per (query, rank), <= k, best first
     int32_t* collect_overflow = nullptr;     // [Q] 1 = the candidate buffer overflowed: this query's lists are unusable
+    // qk_search_ivf plumbing: the coarse scan's refine kernel expands its results straight into the partition scan's
+    // pair table (fused_expand, on the coarse call), the partition scan then skips its own expansion
+    // (pairs_preexpanded) and the workspace clears the caller already issued on a parallel branch (ws_precleared;
+    // pre_refine_event = a cudaEvent_t the coarse call's stream waits for before its refine kernel touches that table)
+    const struct FusedExpand* fused_expand = nullptr;
+    void* pre_refine_event = nullptr;
+    int pairs_preexpanded = 0;
+    int ws_precleared = 0;
+};
+struct FusedExpand {
+    int32_t* pair_seg;          // [Q x nprobe] of the NEXT scan
+    int32_t* seg_count;         // [S]
+    uint32_t* gthr;             // [Q]
+    const int32_t* id_to_slot;
+    int64_t table_size;
+    const int32_t* list_seg0;
+    const int32_t* list_nseg;
+    int num_lists, shard_rank, shard_world;
 };
 // probe_lists == NULL and probe_ids == NULL: flat mode -- the store has ONE list and every query scans it.
 int scan_partitions_impl(const qk_store_t* st, const float* queries, int64_t Q, int64_t q_pitch,

@@ -60,7 +60,7 @@ struct MergeArgs {
     const uint32_t* gthr;
     const uint64_t* qbuf;
     const int32_t* qcount;
-    int qcap;
+    int qcap, qstride;
     int32_t* flags;
     int32_t* ctrl;
     int P, kc, k;
@@ -79,7 +79,31 @@ struct MergeArgs {
     const uint32_t* dense;  // [Q x dense_rows] filter keys
     int dense_rows;
     long long dense_row0;
+    // fused pair expansion (qk_search_ivf): the ids this kernel emits are the partitions the NEXT scan probes; rank i of
+    // query q becomes pair slot (q, i) of that scan -- segment of the list (single-segment lists only), histogram, and
+    // the query's threshold reset -- instead of a separate expand_pairs launch re-reading the ids. x_pair_seg == NULL: off
+    int32_t* x_pair_seg;          // [Q x k]
+    int32_t* x_seg_count;         // [S] zeroed by the caller
+    uint32_t* x_gthr;             // [Q]
+    const int32_t* x_id_to_slot;  // dense partition id -> list slot table
+    int64_t x_table_size;
+    const int32_t* x_list_seg0;
+    const int32_t* x_list_nseg;
+    int x_num_lists, x_shard_rank, x_shard_world;
 };
+
+// the fused expansion of one emitted result (see MergeArgs::x_pair_seg)
+__device__ __forceinline__ void emit_expand(const MergeArgs& a, int64_t q, int i, int64_t id) {
+    if (!a.x_pair_seg) return;
+    int seg = -1;
+    if (id >= 0 && id < a.x_table_size && !(a.x_shard_world > 1 && (int)(id % a.x_shard_world) != a.x_shard_rank)) {
+        const int l = a.x_id_to_slot[id];
+        if (l >= 0 && l < a.x_num_lists && a.x_list_nseg[l] > 0) seg = a.x_list_seg0[l];
+    }
+    a.x_pair_seg[q * a.k + i] = seg;
+    if (seg >= 0) atomicAdd(&a.x_seg_count[seg], 1);
+    if (i == 0) a.x_gthr[q] = KEY_MAX;
+}
 
 struct RescanSmem {
     unsigned hist[256];
@@ -395,6 +419,7 @@ __device__ void exact_rescan_body(const MergeArgs& a, int64_t q, const float* qs
         a.out_ids[q * a.k + i] = id;
         a.out_dist[q * a.k + i] = dist;
         if (a.out_rows) a.out_rows[q * a.k + i] = row;
+        emit_expand(a, q, i, id);
     }
 }
 
@@ -543,6 +568,7 @@ __device__ void refine_and_emit(const MergeArgs& a, int64_t q, const uint64_t* c
         a.out_ids[q * a.k + i] = id;
         a.out_dist[q * a.k + i] = dist;
         if (a.out_rows) a.out_rows[q * a.k + i] = row;
+        emit_expand(a, q, i, id);
     }
 }
 
@@ -591,7 +617,7 @@ __global__ void __launch_bounds__(MERGE_THREADS, 5) merge_refine_kernel(const Me
 
     // ---- gather survivors: appended candidates whose filter key is within the final threshold
     const uint32_t gthr = a.gthr[q];
-    const int appended = a.qcount[q];
+    const int appended = a.qcount[(size_t)q * a.qstride];
     if (tid == 0) {  // statistics for qk_scan_partitions' `stats`
         atomicMax(&a.ctrl[3], appended);
         atomicAdd(reinterpret_cast<unsigned long long*>(a.ctrl + 4), (unsigned long long)appended);
@@ -601,15 +627,25 @@ __global__ void __launch_bounds__(MERGE_THREADS, 5) merge_refine_kernel(const Me
         const int n = appended < a.qcap ? appended : a.qcap;
         const uint64_t* c = a.qbuf + (size_t)q * a.qcap;
         uint32_t mn = 0xffffffffu, mx = 0u;
-        for (int i = tid; i < n; i += blockDim.x) {
-            const uint64_t v = c[i];
-            const uint32_t key = (uint32_t)(v >> 32);
-            if (key > gthr || key == KEY_MAX) continue;
-            mn = min(mn, key);
-            mx = max(mx, key);
-            const int pos = atomicAdd(&s_n, 1);
-            if (pos < a.sort_cap) sbuf[pos] = v;
-            else overflow = true;
+        // four loads in flight per thread (a few hundred entries per query: one at a time they were dependent L2 trips)
+        for (int base = 0; base < n; base += 4 * MERGE_THREADS) {
+            uint64_t v4[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = base + u * MERGE_THREADS + tid;
+                v4[u] = i < n ? __ldcs(reinterpret_cast<const unsigned long long*>(c) + i) : ~0ull;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint64_t v = v4[u];
+                const uint32_t key = (uint32_t)(v >> 32);
+                if (key > gthr || key == KEY_MAX) continue;
+                mn = min(mn, key);
+                mx = max(mx, key);
+                const int pos = atomicAdd(&s_n, 1);
+                if (pos < a.sort_cap) sbuf[pos] = v;
+                else overflow = true;
+            }
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -680,10 +716,38 @@ __global__ void __launch_bounds__(MERGE_THREADS, 5) dense_refine_kernel(const Me
     {
         // stage the query's keys; key range and the number of valid (non-NaN) scores on the way
         uint32_t mn = 0xffffffffu, mx = 0u, valid = 0;
-        for (int i = tid; i < rows; i += blockDim.x) {
-            const uint32_t key = src[i];
-            dkeys[i] = key;
+        auto note = [&](uint32_t key) {
             if (key != KEY_MAX) { mn = min(mn, key); mx = max(mx, key); ++valid; }
+        };
+        if ((rows & 3) == 0) {
+            // 16-byte loads, four in flight per thread (one at a time this loop was a chain of L2 round trips:
+            // 28 % of the kernel's stall samples, profiles/r02i_ncu_details_refine_seed_merge.txt)
+            const uint4* s4 = reinterpret_cast<const uint4*>(src);
+            uint4* d4 = reinterpret_cast<uint4*>(dkeys);
+            const int n4 = rows >> 2;
+            for (int base = 0; base < n4; base += 4 * MERGE_THREADS) {
+                uint4 v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int i = base + u * MERGE_THREADS + tid;
+                    v[u] = i < n4 ? __ldcs(s4 + i) : make_uint4(KEY_MAX, KEY_MAX, KEY_MAX, KEY_MAX);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int i = base + u * MERGE_THREADS + tid;
+                    if (i < n4) {
+                        d4[i] = v[u];
+                        note(v[u].x); note(v[u].y); note(v[u].z); note(v[u].w);
+                    }
+                }
+            }
+        } else {
+#pragma unroll 4
+            for (int i = tid; i < rows; i += MERGE_THREADS) {
+                const uint32_t key = src[i];
+                dkeys[i] = key;
+                note(key);
+            }
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -740,6 +804,7 @@ struct CollectArgs {
     int R, k;
     const uint64_t* qbuf;
     const int32_t* qcount;
+    int qstride;
     int qcap, cap, np;        // cap = candidates handled per query (<= COLLECT_CAP), np = next power of two
     int64_t* out_ids;         // [Q x R x k]
     float* out_dist;
@@ -759,7 +824,7 @@ __global__ void __launch_bounds__(MERGE_THREADS) collect_refine_kernel(const Col
     int* first = srows + a.R;                                          // [R] first sorted position of every rank
     const int64_t q = blockIdx.x;
     const int tid = threadIdx.x;
-    const int appended = a.qcount[q];
+    const int appended = a.qcount[(size_t)q * a.qstride];
     for (int j = tid; j < a.R; j += MERGE_THREADS) a.out_cnt[q * a.R + j] = 0;
     if (appended > a.cap) {
         if (tid == 0) a.overflow[q] = 1;

@@ -62,6 +62,7 @@ struct ScanPlan {
     size_t off_pair_seg, off_seg_count, off_seg_fill, off_seg_start, off_item_start, off_seg_pairs, off_items,
         off_ctrl, off_gthr, off_qdelta, off_flags, off_qcount, off_qbuf, total;
     int qcap;     // entries of the per-query candidate buffer
+    int qstride;  // ints between the fill counters of consecutive queries (see plan_qstride)
     int sample;   // rows sampled per query for the threshold seed (0: no seeding)
     int flat_seed;  // every query samples the same rows (single-list store): seed scores as one small GEMM
     size_t off_skeys;
@@ -81,6 +82,16 @@ static constexpr int SCAN_MAX_NQ = 4;   // query-chunk ring depth
 static constexpr size_t SCAN_SMEM_LIMIT = 227 * 1024;
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// The per-query fill counters take one returning atomicAdd per appended candidate (~500 k per batch at C2). L2 atomics
+// on one 128-byte line are serialised by its slice: with the counters packed (32 per line) all of them funnelled
+// through 32 lines. One counter per line (per 32-byte sector for very large batches, where the clear would cost more
+// than the contention).
+static int plan_qstride(int64_t Q) {
+    static const int env = getenv("QK_QSTRIDE") ? atoi(getenv("QK_QSTRIDE")) : 0;  // experiments
+    if (env > 0) return env;
+    return Q <= 16384 ? 32 : (Q <= 262144 ? 8 : 1);
+}
 
 static int candidate_count(int k) { return k + (k / 16 > 6 ? k / 16 : 6); }
 
@@ -171,7 +182,8 @@ static int make_plan(const qk_store_t* st, int64_t Q, int nprobe, int k, ScanPla
     p->off_seg_count = o;  o = align_up(o + (S + 1) * 4, 256);
     p->off_seg_fill = o;   o = align_up(o + (S + 1) * 4, 256);
     p->off_flags = o;      o = align_up(o + (size_t)Q * 4, 256);
-    p->off_qcount = o;     o = align_up(o + (size_t)Q * 4, 256);
+    p->qstride = plan_qstride(Q);
+    p->off_qcount = o;     o = align_up(o + (size_t)Q * p->qstride * 4, 256);
     p->off_ctrl = o;       o = align_up(o + 64, 256);
     p->off_seg_start = o;  o = align_up(o + (S + 1) * 4, 256);
     p->off_item_start = o; o = align_up(o + (S + 1) * 4, 256);
@@ -206,6 +218,8 @@ static int make_plan(const qk_store_t* st, int64_t Q, int nprobe, int k, ScanPla
             while (sample > 32 && sample / 2 >= p->kc && (size_t)Q * sample * p->dp * sizeof(float) > budget) sample >>= 1;
         }
         p->flat_seed = (st->num_lists == 1 && nprobe == 1) ? 1 : 0;
+        static const int env_sample = getenv("QK_SEED_SAMPLE") ? atoi(getenv("QK_SEED_SAMPLE")) : -1;  // experiments
+        if (env_sample >= 0 && st->num_lists > 1) sample = env_sample;
         if (sample < p->kc) sample = 0;
         // dense mode: [Q x rows] keys, at most 512 MB and at most 16384 rows (the select keeps a query's keys in smem).
         // Only a flat-mode call (no probe table) uses it; the workspace is sized for either.
@@ -442,8 +456,13 @@ __device__ __forceinline__ uint32_t radix_select(KeyAt key_at, int n, int kc, ui
 // The sampled rows are contiguous runs of the arena (one per probed list): they are fetched with TMA bulk copies into
 // shared memory, SEED_CHUNK rows at a time, so the kernel is a stream of a few large asynchronous copies per SM instead
 // of register-limited dependent loads (it was latency-bound: 39-63 us for 67 MB at C2).
-static int seed_chunk_rows(int dp, int sample) {  // rows staged per step: at most 32 KB (64 rows at d = 128)
-    int c = (32 * 1024) / (dp * 4);
+// 128 threads and 16 KB of staging per CTA: eight CTAs share an SM, so a batch of 1024 queries is ONE wave of 148 x 8
+// slots (with 256 threads / 32 KB it was 1.7 waves of four, each CTA mostly waiting for its own bulk copy: 41 us at C2;
+// now 25 us). Plain 16-byte loads into registers, eight rows in flight per warp, were slower (32 us).
+static constexpr int SEED_THREADS = 128;
+static constexpr int SEED_WARPS = SEED_THREADS / 32;
+static int seed_chunk_rows(int dp, int sample) {  // rows staged per step: at most 16 KB (32 rows at d = 128)
+    int c = (16 * 1024) / (dp * 4);
     if (c < 8) c = 8;
     return sample < c ? sample : c;
 }
@@ -451,7 +470,7 @@ static size_t seed_smem_bytes(int dp, int sample) {
     return (size_t)seed_chunk_rows(dp, sample) * dp * 4 + (size_t)dp * 4 + (size_t)sample * 8 + 16;
 }
 template <bool kIP>
-__global__ void __launch_bounds__(256) seed_thresholds_kernel(const float* __restrict__ vecs, int64_t pitch,
+__global__ void __launch_bounds__(SEED_THREADS, 8) seed_thresholds_kernel(const float* __restrict__ vecs, int64_t pitch,
                                                               const float* __restrict__ norms, int d, int dp,
                                                               const float* __restrict__ queries, int64_t q_pitch, int64_t Q,
                                                               const int32_t* __restrict__ pair_seg, int P,
@@ -467,9 +486,10 @@ __global__ void __launch_bounds__(256) seed_thresholds_kernel(const float* __res
     __shared__ int s_start[33];      // exclusive prefix of the sampled rows over the first 32 probes
     __shared__ long long s_r0[32];   // first arena row of each of them
     __shared__ __align__(8) uint64_t s_bar;
+    __shared__ uint32_t s_hist[256];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t q = blockIdx.x;
-    for (int i = tid; i < dp; i += 256) qs[i] = i < d ? queries[q * q_pitch + i] : 0.f;
+    for (int i = tid; i < dp; i += SEED_THREADS) qs[i] = i < d ? queries[q * q_pitch + i] : 0.f;
     if (warp == 0) {
         int nrows = 0;
         long long r0 = 0;
@@ -519,7 +539,7 @@ __global__ void __launch_bounds__(256) seed_thresholds_kernel(const float* __res
             // the rows' squared norms, one coalesced load per sampled row, in flight together with the first bulk copy
             // (read one by one inside the scoring loop they were a chain of dependent cache misses)
             if (!kIP) {
-                for (int i = tid; i < have; i += 256) {
+                for (int i = tid; i < have; i += SEED_THREADS) {
                     int j = 0;
                     while (j < 31 && i >= s_start[j + 1]) ++j;
                     nrm[i] = norms[s_r0[j] + (i - s_start[j])];
@@ -529,7 +549,7 @@ __global__ void __launch_bounds__(256) seed_thresholds_kernel(const float* __res
         }
         mbar_wait(&s_bar, phase);
         // one row per warp step: lane c holds 16-byte chunk c (conflict-free), reduced with shuffles
-        for (int i = warp; i < cn; i += 8) {
+        for (int i = warp; i < cn; i += SEED_WARPS) {
             const float4* rp = reinterpret_cast<const float4*>(rows + (size_t)i * dp);
             float acc = 0.f;
             for (int c = lane; c < dp4; c += 32) {
@@ -545,28 +565,14 @@ __global__ void __launch_bounds__(256) seed_thresholds_kernel(const float* __res
     }
     __syncthreads();
     if (warp != 0 || have < kc) return;  // fewer sampled rows than candidates wanted: no bound
-    // kc-th smallest key of the sample, by bisection on the key bits (keys in registers, 32 per lane at most)
-    uint32_t kreg[32];
-#pragma unroll
-    for (int s2 = 0; s2 < 32; ++s2) {
-        const int i = s2 * 32 + lane;
-        kreg[s2] = i < have ? keys[i] : KEY_MAX;
-    }
-    const int nslot = (have + 31) >> 5;
+    // kc-th smallest key of the sample: warp-level radix select over the keys in shared memory (the bisection on key
+    // bits this used to be -- 32 rounds of one ballot per 32 keys, by one warp -- was ~40 % of the kernel's samples)
     float qq = 0.f;
     for (int i = lane; i < dp; i += 32) qq = fmaf(qs[i], qs[i], qq);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) qq += __shfl_xor_sync(0xffffffffu, qq, o);
-    uint32_t lo = 0;
-#pragma unroll 1
-    for (int bit = 31; bit >= 0; --bit) {
-        const uint32_t cand = lo | (1u << bit);
-        int c = 0;
-#pragma unroll
-        for (int s2 = 0; s2 < 32; ++s2)
-            if (s2 < nslot) c += __popc(__ballot_sync(0xffffffffu, kreg[s2] < cand));
-        if (c < kc) lo = cand;
-    }
+    const uint32_t* kk = keys;
+    const uint32_t lo = radix_select([kk](int i) { return kk[i]; }, have, kc, s_hist, lane);
     if (lane == 0 && lo < KEY_MAX) {
         const float t = key2f(lo);
         const float margin = __fadd_ru(__fmul_ru(rel_margin, __fmul_ru(sqrtf(qq), max_row_norm)), fabsf(t) * 9.5367431640625e-07f);
@@ -714,6 +720,9 @@ struct ScanArgs {
     uint64_t* qbuf;    // [Q][qcap] candidates: key << 32 | arena row; unwritten slots are 0xff..ff
     int P, kc, gq, nq;
     int qcap;
+    int qstride;       // ints between consecutive queries' fill counters
+    int refresh_boxes, refresh_fresh;  // mailboxes per epilogue warp - 1 (0, 1 or 3); re-read the fill when serving
+    int refresh_step, refresh_window;  // tensor-core path: threshold refresh cadence (appends, power of two) / entries looked at
     uint32_t* dense;      // dense mode: [Q x dense_rows] filter keys of every (query, row); null otherwise
     long long dense_row0;
     int dense_rows;
@@ -1035,7 +1044,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) scan_kernel(const ScanArgs a,
                 if (lane == 0) mbar_arrive(kempty + grp * 2 + kb);
                 cur.nn = __popc(cur.m0) + __popc(cur.m1);
                 cur.base = 0;
-                if (cur.nn > 0) cur.base = atomicAdd(&a.qcount[my_q], cur.nn);
+                if (cur.nn > 0) cur.base = atomicAdd(&a.qcount[(size_t)my_q * a.qstride], cur.nn);
                 if (pend.live) flush(pend);
                 pend = cur;
                 if (g_now < my_lim) my_lim = g_now;
@@ -1145,6 +1154,7 @@ static int g_prof_cap = 0, g_prof_n = 0;
 struct SideStream {
     cudaStream_t stream = nullptr;
     cudaEvent_t fork = nullptr, join = nullptr;
+    cudaEvent_t fork2 = nullptr, join2 = nullptr;  // qk_search_ivf: workspace clears beside the coarse scan
 };
 static constexpr int QK_MAX_DEVICES = 64;
 static SideStream g_side[QK_MAX_DEVICES];
@@ -1159,6 +1169,8 @@ static int side_stream_for_current_device(SideStream** out) {
         QK_CUDA(cudaStreamCreateWithFlags(&ss.stream, cudaStreamNonBlocking));
         QK_CUDA(cudaEventCreateWithFlags(&ss.fork, cudaEventDisableTiming));
         QK_CUDA(cudaEventCreateWithFlags(&ss.join, cudaEventDisableTiming));
+        QK_CUDA(cudaEventCreateWithFlags(&ss.fork2, cudaEventDisableTiming));
+        QK_CUDA(cudaEventCreateWithFlags(&ss.join2, cudaEventDisableTiming));
     }
     *out = &ss;
     return QK_OK;
@@ -1258,6 +1270,14 @@ static int launch_scan(const ScanArgs& sa, const CUtensorMap& vmap, int metric, 
 
 using namespace qk;
 
+// The zero / +inf initialisation a scan needs of its workspace: seg_count, seg_fill, flags, qcount, ctrl are contiguous
+// (one memset); candidate slots start as +inf (a refresh may read a slot that was reserved but not written yet).
+static int clear_scan_workspace(const ScanPlan& p, char* ws, int64_t Q, cudaStream_t stream) {
+    QK_CUDA(cudaMemsetAsync(ws + p.off_seg_count, 0, p.off_seg_start - p.off_seg_count, stream));
+    if (!p.dense) QK_CUDA(cudaMemsetAsync(ws + p.off_qbuf, 0xff, (size_t)Q * p.qcap * 8, stream));
+    return QK_OK;
+}
+
 extern "C" size_t qk_scan_workspace_bytes(const qk_store_t* store, int64_t num_queries, int nprobe, int k) {
     ScanPlan p;
     if (!store || num_queries <= 0 || nprobe <= 0) return 0;
@@ -1328,9 +1348,7 @@ int qk::scan_partitions_impl(const qk_store_t* st, const float* queries, int64_t
     if (terms != 2) terms = 3;
     const double fgam = use_mma ? filter_gamma(terms) : 0.0;
 
-    // seg_count, seg_fill, flags, qcount, ctrl are contiguous: one memset; candidate slots start as +inf
-    QK_CUDA(cudaMemsetAsync(ws + p.off_seg_count, 0, p.off_seg_start - p.off_seg_count, stream));
-    if (!p.dense) QK_CUDA(cudaMemsetAsync(qbuf, 0xff, (size_t)Q * p.qcap * 8, stream));
+    if (!ex.ws_precleared && (rc = clear_scan_workspace(p, ws, Q, stream))) return rc;
     if (flat) {
         if (!p.dense) QK_CUDA(cudaMemsetAsync(gthr, 0xff, (size_t)Q * 4, stream));  // KEY_MAX: no threshold yet
     } else {
@@ -1338,7 +1356,9 @@ int qk::scan_partitions_impl(const qk_store_t* st, const float* queries, int64_t
         ps.slots = probe_lists; ps.ids = ex.probe_ids; ps.id_to_slot = ex.id_to_slot; ps.table_size = ex.table_size;
         ps.shard_rank = ex.shard_rank; ps.shard_world = ex.shard_world;
         const bool single = (p.P == nprobe);
-        if (single) {
+        if (ex.pairs_preexpanded) {
+            QK_REQUIRE(single && !collect, "pre-expanded pairs need single-segment lists");
+        } else if (single) {
             int64_t n = Q * nprobe;
             expand_pairs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(ps, Q, nprobe, p.P, st->list_seg0, st->list_nseg,
                                                                                   st->num_lists, pair_seg, seg_count, gthr, true, !collect);
@@ -1350,7 +1370,7 @@ int qk::scan_partitions_impl(const qk_store_t* st, const float* queries, int64_t
             expand_pairs_kernel<<<(unsigned)((Q + 127) / 128), 128, 0, stream>>>(ps, Q, nprobe, p.P, st->list_seg0, st->list_nseg,
                                                                                   st->num_lists, pair_seg, seg_count, gthr, false, !collect);
         }
-        QK_LAUNCHED();
+        if (!ex.pairs_preexpanded) QK_LAUNCHED();
         if (collect) QK_CUDA(cudaMemcpyAsync(gthr, ex.preset_thresholds, (size_t)Q * 4, cudaMemcpyDeviceToDevice, stream));
     }
     // The seeds only need the pair table; the grouping kernels (prefix, scatter) only the histogram: run them side by
@@ -1390,12 +1410,12 @@ int qk::scan_partitions_impl(const qk_store_t* st, const float* queries, int64_t
             const unsigned grid = (unsigned)Q;
             if ((rc = ip ? ensure_smem(seed_thresholds_kernel<true>, ssm) : ensure_smem(seed_thresholds_kernel<false>, ssm))) return rc;
             if (ip)
-                seed_thresholds_kernel<true><<<grid, 256, ssm, seed_stream>>>(st->vectors, st->pitch, st->row_norms, st->d, p.dp,
+                seed_thresholds_kernel<true><<<grid, SEED_THREADS, ssm, seed_stream>>>(st->vectors, st->pitch, st->row_norms, st->d, p.dp,
                                                                          queries, q_pitch, Q, pair_seg, p.P, st->seg_row0,
                                                                          st->seg_rows, p.kc, sample, seed_chunk_rows(p.dp, sample),
                                                                          st->max_row_norm, rel_margin, gthr);
             else
-                seed_thresholds_kernel<false><<<grid, 256, ssm, seed_stream>>>(st->vectors, st->pitch, st->row_norms, st->d, p.dp,
+                seed_thresholds_kernel<false><<<grid, SEED_THREADS, ssm, seed_stream>>>(st->vectors, st->pitch, st->row_norms, st->d, p.dp,
                                                                           queries, q_pitch, Q, pair_seg, p.P, st->seg_row0,
                                                                           st->seg_rows, p.kc, sample, seed_chunk_rows(p.dp, sample),
                                                                           st->max_row_norm, rel_margin, gthr);
@@ -1424,9 +1444,19 @@ int qk::scan_partitions_impl(const qk_store_t* st, const float* queries, int64_t
     sa.queries = queries; sa.q_pitch = q_pitch;
     sa.seg_pairs = seg_pairs; sa.items = items; sa.ctrl = ctrl;
     sa.gthr = gthr; sa.qcount = qcount; sa.qbuf = qbuf;
-    sa.P = p.P; sa.kc = p.kc; sa.gq = p.gq; sa.nq = p.nq; sa.qcap = p.qcap;
+    sa.P = p.P; sa.kc = p.kc; sa.gq = p.gq; sa.nq = p.nq; sa.qcap = p.qcap; sa.qstride = p.qstride;
     sa.Q = Q; sa.seg_row0 = st->seg_row0; sa.seg_rows = st->seg_rows;
     sa.terms = terms;
+    {
+        static const int env_step = getenv("QK_REFRESH_STEP") ? atoi(getenv("QK_REFRESH_STEP")) : 0;      // experiments
+        static const int env_win = getenv("QK_REFRESH_WINDOW") ? atoi(getenv("QK_REFRESH_WINDOW")) : 0;
+        sa.refresh_step = env_step > 0 ? env_step : 64;
+        sa.refresh_window = env_win > 0 ? env_win : 256;
+        static const int env_boxes = getenv("QK_REFRESH_BOXES") ? atoi(getenv("QK_REFRESH_BOXES")) : 0;
+        static const int env_fresh = getenv("QK_REFRESH_FRESH") ? atoi(getenv("QK_REFRESH_FRESH")) : 0;
+        sa.refresh_boxes = env_boxes == 4 ? 3 : (env_boxes == 2 ? 1 : 0);
+        sa.refresh_fresh = env_fresh;
+    }
     sa.fixed_thr = collect ? 1 : 0;
     sa.top1 = top1 ? 1 : 0;
     sa.qdelta = (const float*)(ws + p.off_qdelta);
@@ -1465,7 +1495,7 @@ int qk::scan_partitions_impl(const qk_store_t* st, const float* queries, int64_t
         memset(&ca, 0, sizeof(ca));
         ca.vecs = st->vectors; ca.pitch = st->pitch; ca.ids = st->ids; ca.d = st->d;
         ca.seg_row0 = st->seg_row0; ca.seg_rows = st->seg_rows; ca.queries = queries; ca.q_pitch = q_pitch;
-        ca.pair_seg = pair_seg; ca.R = nprobe; ca.k = k; ca.qbuf = qbuf; ca.qcount = qcount; ca.qcap = p.qcap;
+        ca.pair_seg = pair_seg; ca.R = nprobe; ca.k = k; ca.qbuf = qbuf; ca.qcount = qcount; ca.qcap = p.qcap; ca.qstride = p.qstride;
         ca.out_ids = ex.collect_ids; ca.out_dist = ex.collect_dist; ca.out_cnt = ex.collect_cnt; ca.overflow = ex.collect_overflow;
         int cap = p.qcap < COLLECT_CAP ? p.qcap : COLLECT_CAP;
         int np = 1;
@@ -1487,7 +1517,7 @@ int qk::scan_partitions_impl(const qk_store_t* st, const float* queries, int64_t
     ma.vecs = st->vectors; ma.pitch = st->pitch; ma.ids = st->ids; ma.d = st->d;
     ma.seg_row0 = st->seg_row0; ma.seg_rows = st->seg_rows; ma.queries = queries; ma.q_pitch = q_pitch;
     ma.pair_seg = pair_seg; ma.flat_nseg = flat ? S : 0;
-    ma.gthr = gthr; ma.qbuf = qbuf; ma.qcount = qcount; ma.qcap = p.qcap;
+    ma.gthr = gthr; ma.qbuf = qbuf; ma.qcount = qcount; ma.qcap = p.qcap; ma.qstride = p.qstride;
     ma.flags = flags; ma.ctrl = ctrl; ma.P = p.P; ma.kc = p.kc; ma.k = k;
     ma.max_row_norm = st->max_row_norm;
     ma.max_row_norm_dev = ex.max_row_norm_dev;
@@ -1498,6 +1528,14 @@ int qk::scan_partitions_impl(const qk_store_t* st, const float* queries, int64_t
     ma.out_ids = out_ids; ma.out_dist = out_dist; ma.out_rows = out_rows;
     ma.force_rescan = g_force_rescan;
     ma.rank_squared = ex.rank_squared;
+    if (ex.fused_expand) {
+        const FusedExpand& fx = *ex.fused_expand;
+        ma.x_pair_seg = fx.pair_seg; ma.x_seg_count = fx.seg_count; ma.x_gthr = fx.gthr;
+        ma.x_id_to_slot = fx.id_to_slot; ma.x_table_size = fx.table_size;
+        ma.x_list_seg0 = fx.list_seg0; ma.x_list_nseg = fx.list_nseg;
+        ma.x_num_lists = fx.num_lists; ma.x_shard_rank = fx.shard_rank; ma.x_shard_world = fx.shard_world;
+    }
+    if (ex.pre_refine_event) QK_CUDA(cudaStreamWaitEvent(stream, (cudaEvent_t)ex.pre_refine_event, 0));
     const int kcp = next_pow2(p.kc);
     if (p.dense) {
         ma.dense = sa.dense; ma.dense_rows = (int)st->flat_rows; ma.dense_row0 = st->flat_row0;
@@ -1525,7 +1563,7 @@ int qk::scan_partitions_impl(const qk_store_t* st, const float* queries, int64_t
         }
     }
     QK_LAUNCHED();
-    if (stats) QK_CUDA(cudaMemcpyAsync(stats, ctrl + 2, 5 * sizeof(int32_t), cudaMemcpyDeviceToDevice, stream));
+    if (stats) QK_CUDA(cudaMemcpyAsync(stats, ctrl + 2, 8 * sizeof(int32_t), cudaMemcpyDeviceToDevice, stream));
     return QK_OK;
 }
 
@@ -1548,7 +1586,7 @@ extern "C" int qk_scan_collect(const qk_store_t* st, const float* queries, int64
 // ---- two-level fixed-nprobe search in one call ------------------------------------------------------
 namespace {
 struct IvfLayout {
-    size_t off_pids, off_pdist, off_scan, coarse_bytes, part_bytes, total;
+    size_t off_pids, off_pdist, off_coarse, off_part, coarse_bytes, part_bytes, total;
     int np;  // partitions probed per query = min(nprobe, number of centroids)
 };
 int ivf_layout(const qk_store_t* parent, const qk_store_t* store, int64_t Q, int nprobe, int k, IvfLayout* L) {
@@ -1558,10 +1596,13 @@ int ivf_layout(const qk_store_t* parent, const qk_store_t* store, int64_t Q, int
     L->coarse_bytes = qk_scan_workspace_bytes(parent, Q, 1, L->np);
     L->part_bytes = store->num_segments > 0 ? qk_scan_workspace_bytes(store, Q, L->np, k) : 256;
     if (L->coarse_bytes == 0 || L->part_bytes == 0) return QK_ERR_INVALID_ARGUMENT;
+    // the two scans have their own regions: the partition scan's is cleared (and its pair table filled by the coarse
+    // scan's refine kernel) while the coarse scan still runs
     size_t o = 0;
-    L->off_pids = o;  o = align_up(o + (size_t)Q * L->np * 8, 256);
-    L->off_pdist = o; o = align_up(o + (size_t)Q * L->np * 4, 256);
-    L->off_scan = o;  o += L->coarse_bytes > L->part_bytes ? L->coarse_bytes : L->part_bytes;
+    L->off_pids = o;   o = align_up(o + (size_t)Q * L->np * 8, 256);
+    L->off_pdist = o;  o = align_up(o + (size_t)Q * L->np * 4, 256);
+    L->off_coarse = o; o = align_up(o + L->coarse_bytes, 256);
+    L->off_part = o;   o += L->part_bytes;
     L->total = o;
     return QK_OK;
 }
@@ -1595,18 +1636,45 @@ extern "C" int qk_search_ivf(const qk_store_t* parent, const qk_store_t* store, 
     char* ws = (char*)workspace;
     int64_t* p_ids = out_probe_ids ? out_probe_ids : (int64_t*)(ws + L.off_pids);
     float* p_dist = (float*)(ws + L.off_pdist);
-    // 1. coarse centroid scan (query_coordinator.cpp:644): top-np centroids per query, nearest first; flat mode
-    ScanExtras cx;
-    rc = scan_partitions_impl(parent, queries, Q, q_pitch, nullptr, 1, metric, L.np, p_ids, p_dist, nullptr, ws + L.off_scan,
-                              L.coarse_bytes, nullptr, stream, cx);
-    if (rc) return rc;
     if (store->num_segments == 0) {  // every list is empty: padded results (query_coordinator.cpp:589-601)
+        ScanExtras cx;
+        rc = scan_partitions_impl(parent, queries, Q, q_pitch, nullptr, 1, metric, L.np, p_ids, p_dist, nullptr,
+                                  ws + L.off_coarse, L.coarse_bytes, nullptr, stream, cx);
+        if (rc) return rc;
         const int64_t n = Q * k;
         fill_empty_result_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(
             n, out_ids, out_dist, metric == QK_METRIC_INNER_PRODUCT ? -INFINITY : INFINITY);
         QK_LAUNCHED();
         return QK_OK;
     }
+    // 0. the partition scan's workspace clears run on a parallel branch beside the coarse scan (16 MB of candidate
+    //    slots at C2: ~6 us that used to sit on the critical path)
+    ScanPlan pp;
+    if ((rc = make_plan(store, Q, L.np, k, &pp, /*allow_dense=*/false))) return rc;
+    char* pws = ws + L.off_part;
+    SideStream* side = nullptr;
+    if ((rc = side_stream_for_current_device(&side))) return rc;
+    QK_CUDA(cudaEventRecord(side->fork2, stream));
+    QK_CUDA(cudaStreamWaitEvent(side->stream, side->fork2, 0));
+    if ((rc = clear_scan_workspace(pp, pws, Q, side->stream))) return rc;
+    QK_CUDA(cudaEventRecord(side->join2, side->stream));
+    // 1. coarse centroid scan (query_coordinator.cpp:644): top-np centroids per query, nearest first; flat mode. With
+    //    single-segment lists its refine kernel also writes the partition scan's pair table (id -> slot map, shard
+    //    filter, per-segment histogram): no separate expansion launch
+    const bool fuse = (pp.P == L.np);
+    FusedExpand fx;
+    fx.pair_seg = (int32_t*)(pws + pp.off_pair_seg);
+    fx.seg_count = (int32_t*)(pws + pp.off_seg_count);
+    fx.gthr = (uint32_t*)(pws + pp.off_gthr);
+    fx.id_to_slot = id_to_slot; fx.table_size = table_size;
+    fx.list_seg0 = store->list_seg0; fx.list_nseg = store->list_nseg; fx.num_lists = store->num_lists;
+    fx.shard_rank = shard_rank; fx.shard_world = shard_world < 1 ? 1 : shard_world;
+    ScanExtras cx;
+    if (fuse) cx.fused_expand = &fx;
+    cx.pre_refine_event = side->join2;  // joins the clearing branch back into the stream
+    rc = scan_partitions_impl(parent, queries, Q, q_pitch, nullptr, 1, metric, L.np, p_ids, p_dist, nullptr, ws + L.off_coarse,
+                              L.coarse_bytes, nullptr, stream, cx);
+    if (rc) return rc;
     // 2. partition scan of the probed lists; the id -> slot map (and the shard filter) run inside the pair expansion
     ScanExtras px;
     px.probe_ids = p_ids;
@@ -1614,8 +1682,10 @@ extern "C" int qk_search_ivf(const qk_store_t* parent, const qk_store_t* store, 
     px.table_size = table_size;
     px.shard_rank = shard_rank;
     px.shard_world = shard_world < 1 ? 1 : shard_world;
-    return scan_partitions_impl(store, queries, Q, q_pitch, nullptr, L.np, metric, k, out_ids, out_dist, nullptr,
-                                ws + L.off_scan, L.part_bytes, stats, stream, px);
+    px.ws_precleared = 1;
+    px.pairs_preexpanded = fuse ? 1 : 0;
+    return scan_partitions_impl(store, queries, Q, q_pitch, nullptr, L.np, metric, k, out_ids, out_dist, nullptr, pws,
+                                L.part_bytes, stats, stream, px);
 }
 
 // ---- per-launch timing of the filter kernel ------------------------------------------------------

@@ -165,7 +165,7 @@ __device__ __forceinline__ float key2lim(uint32_t t) { return t == KEY_MAX ? INF
 template <bool kIP>
 __global__ void __launch_bounds__(MMA_THREADS, 1) scan_mma_kernel(const ScanArgs a, const __grid_constant__ CUtensorMap vmap) {
     constexpr int TM = MMA_TM, NB = MMA_NB, ND = MMA_ND;
-    static_assert(MMA_STAGES <= 16 && 768 + MMA_ND * sizeof(MmaDesc) <= MMA_SMEM_HEADER, "descriptor ring");
+    static_assert(MMA_STAGES <= 16 && 768 + MMA_ND * sizeof(MmaDesc) <= 3072 && 3072 + 32 * 8 <= MMA_SMEM_HEADER, "descriptor ring");
     extern __shared__ __align__(16) unsigned char smem_dyn[];
     unsigned char* smem_raw = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
@@ -180,7 +180,10 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) scan_mma_kernel(const ScanArgs
     uint64_t* d_empty = bars + 72;     // [NACC] 4 epilogue warps            -> MMA issuer
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + 640);
     volatile uint32_t* ep_done = reinterpret_cast<volatile uint32_t*>(smem_raw + 644);       // epilogue warps that left
-    volatile unsigned long long* mbox = reinterpret_cast<volatile unsigned long long*>(smem_raw + 704);  // [8] refresh requests
+    // [32] refresh requests: four mailboxes per epilogue warp (a lane posts into box lane & 3), so that a burst of
+    // requests -- the first lists of many queries, while the thresholds are still loose -- queues up instead of being
+    // dropped (with one box per warp more than half of the requests were)
+    volatile unsigned long long* mbox = reinterpret_cast<volatile unsigned long long*>(smem_raw + 3072);
     MmaDesc* descs = reinterpret_cast<MmaDesc*>(smem_raw + 768);    // [ND]
     unsigned char* As = smem_raw + MMA_SMEM_HEADER;                 // [NS][128 rows][128 B]
     unsigned char* Bs = As + (size_t)MMA_STAGES * MMA_BOX_BYTES;    // [NB][4 boxes][hi: 32 rows | lo: 32 rows][128 B]
@@ -204,7 +207,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) scan_mma_kernel(const ScanArgs
         for (int s = 0; s < MMA_NACC; ++s) { mbar_init(d_full + s, 1); mbar_init(d_empty + s, 4); }
         mbar_fence_init();
         *ep_done = 0;
-        for (int s = 0; s < 8; ++s) mbox[s] = 0ull;
+        for (int s = 0; s < 32; ++s) mbox[s] = 0ull;
     }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(MMA_TMEM_COLS));
@@ -460,7 +463,9 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) scan_mma_kernel(const ScanArgs
         const int eg = (warp - 6) >> 2;  // group: takes tiles with (T & 1) == eg
         const int q4 = warp & 3;
         const int qcap = a.qcap;
-        volatile unsigned long long* my_box = mbox + (warp - 6);
+        volatile unsigned long long* my_box = mbox + (warp - 6) * 4 + (lane & a.refresh_boxes);
+        const int rmask = a.refresh_step - 1;  // a refresh is requested whenever a query's fill passes a multiple of this
+        int dropped = 0;
         uint32_t T = 0;
         for (uint32_t n = 0;; ++n) {
             const int id = n % ND;
@@ -578,7 +583,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) scan_mma_kernel(const ScanArgs
                         }
                     }
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) base[i] = qs[i] >= 0 ? atomicAdd(&a.qcount[qs[i]], 1) : 0;
+                    for (int i = 0; i < 4; ++i) base[i] = qs[i] >= 0 ? atomicAdd(&a.qcount[(size_t)qs[i] * a.qstride], 1) : 0;
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         if (qs[i] >= 0) {
@@ -586,8 +591,10 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) scan_mma_kernel(const ScanArgs
                             if (slot < qcap) a.qbuf[(size_t)qs[i] * qcap + slot] = ((uint64_t)key[i] << 32) | arow;
                             // the fill passed a multiple of 64: ask a refresh warp for a new threshold (a busy
                             // mailbox just drops the request -- thresholds are an optimisation)
-                            if ((slot & 63) == 63 && slot + 1 >= kc && !a.fixed_thr && !a.top1 && *my_box == 0ull)
-                                *my_box = ((unsigned long long)(qs[i] + 1) << 32) | (uint32_t)(slot + 1);
+                            if ((slot & rmask) == rmask && slot + 1 >= kc && !a.fixed_thr && !a.top1) {
+                                if (*my_box == 0ull) *my_box = ((unsigned long long)(qs[i] + 1) << 32) | (uint32_t)(slot + 1);
+                                else ++dropped;
+                            }
                         }
                     }
                 }
@@ -601,54 +608,127 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) scan_mma_kernel(const ScanArgs
             __syncwarp();
             if (lane == 0) mbar_arrive(i_empty + id);
         }
+        dropped = __reduce_add_sync(0xffffffffu, dropped);
+        if (lane == 0 && dropped) atomicAdd(&a.ctrl[9], dropped);  // statistics: refresh requests that found the mailbox busy
         __syncwarp();
         if (lane == 0) atomicAdd(const_cast<uint32_t*>(ep_done), 1u);
     } else {
         // ===================================================================== threshold refresh (off the critical path)
+        // Up to 256 entries (8 keys per lane) are selected in registers: common prefix of the keys from a warp min / max,
+        // then one bit per round -- 8 compares and one REDUX -- with no shared memory, histogram or atomics. Two
+        // requests are taken per sweep so that their candidate loads (an L2 round trip each) overlap. This warp used
+        // to spend ~6 us per request on a 4-pass shared-memory radix select and more than half of the requests found
+        // their mailbox busy (stats[6], stats[7]); larger windows (kc > 64) still take that path.
         uint32_t* hist = hists;
         uint32_t* keys = rscratch;
         const int qcap = a.qcap;
+        int served = 0, rr = 0;
+        int ncap = 4 * kc > a.refresh_window ? 4 * kc : a.refresh_window;
+        if (ncap > MMA_REFRESH_CAP) ncap = MMA_REFRESH_CAP;
+        auto decode = [&](unsigned long long req, int& q, int& n) {
+            q = (int)(req >> 32) - 1;
+            int fill = (int)(uint32_t)req;
+            if (a.refresh_fresh) fill = __ldcg(a.qcount + (size_t)q * a.qstride);  // what the buffer holds NOW
+            if (fill > qcap) fill = qcap;
+            // the most recent entries carry the tightest keys; any subset yields a valid upper bound
+            n = fill < ncap ? fill : ncap;
+            return reinterpret_cast<const unsigned long long*>(a.qbuf) + (size_t)q * qcap + (fill - n);
+        };
+        auto load8 = [&](const unsigned long long* qb, int n, unsigned long long (&e)[8]) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int idx = j * 32 + lane;
+                e[j] = idx < n ? __ldcg(qb + idx) : ~0ull;
+            }
+        };
+        auto select8 = [&](const unsigned long long (&e)[8]) -> uint32_t {  // kc-th smallest key of <= 256 entries
+            uint32_t key[8], mn = KEY_MAX, mx = 0u;
+            int valid = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                key[j] = (uint32_t)(e[j] >> 32);
+                if (key[j] != KEY_MAX) { mn = min(mn, key[j]); mx = max(mx, key[j]); ++valid; }
+            }
+            mn = __reduce_min_sync(0xffffffffu, mn);
+            mx = __reduce_max_sync(0xffffffffu, mx);
+            valid = __reduce_add_sync(0xffffffffu, valid);
+            if (valid < kc) return KEY_MAX;  // slots reserved but not written yet count as +inf
+            const uint32_t diff = mn ^ mx;
+            if (diff == 0u) return mn;
+            const int top = 31 - __clz(diff);
+            uint32_t lo = mn & ~((2u << top) - 1u);  // the bits every valid key shares
+#pragma unroll 1
+            for (int bit = top; bit >= 0; --bit) {
+                const uint32_t cand = lo | (1u << bit);
+                int c = 0;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) c += key[j] < cand ? 1 : 0;
+                if (__reduce_add_sync(0xffffffffu, c) < kc) lo = cand;  // the kc-th smallest is >= cand
+            }
+            return lo;
+        };
         for (;;) {
-            bool did = false;
-            for (int i = 0; i < 8; ++i) {
-                volatile unsigned long long* mb = mbox + i;
-                const unsigned long long req = *mb;
-                if (req == 0ull) continue;  // warp-uniform: every lane read the same word
-                did = true;
-                const int q = (int)(req >> 32) - 1;
-                int fill = (int)(uint32_t)req;
-                if (fill > qcap) fill = qcap;
-                // the most recent entries carry the tightest keys; any subset yields a valid upper bound, and a
-                // short one keeps the refresh rate up when appends come fast
-                int ncap = 4 * kc > 256 ? 4 * kc : 256;
-                if (ncap > MMA_REFRESH_CAP) ncap = MMA_REFRESH_CAP;
-                const int n = fill < ncap ? fill : ncap;
-                const unsigned long long* qb = reinterpret_cast<const unsigned long long*>(a.qbuf) + (size_t)q * qcap + (fill - n);
-                for (int base = 0; base < n; base += 256) {
+            // up to two pending requests: lane l looks at mailbox l; round-robin start so that no box starves
+            const unsigned long long mine = mbox[lane];
+            const unsigned pend = __ballot_sync(0xffffffffu, mine != 0ull);
+            int ia = -1, ib = -1;
+            unsigned long long ra = 0ull, rb = 0ull;
+            if (pend) {
+                const unsigned rot = __funnelshift_r(pend, pend, rr);  // bit j of rot = box (j + rr) & 31
+                ia = (__ffs(rot) - 1 + rr) & 31;
+                const unsigned rot2 = rot & (rot - 1);
+                if (rot2) ib = (__ffs(rot2) - 1 + rr) & 31;
+                ra = __shfl_sync(0xffffffffu, mine, ia);
+                if (ib >= 0) rb = __shfl_sync(0xffffffffu, mine, ib);
+                rr = (ia + 1) & 31;
+            }
+            if (ia < 0) {
+                if (*ep_done >= 8u) break;
+                __nanosleep(100);
+                continue;
+            }
+            int qa, na, qb2 = 0, nb = 0;
+            const unsigned long long* pa = decode(ra, qa, na);
+            if (na > 256) {
+                // large window: shared-memory radix select
+                for (int base = 0; base < na; base += 256) {
                     unsigned long long e[8];
+                    load8(pa + base, na - base, e);
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         const int idx = base + j * 32 + lane;
-                        e[j] = idx < n ? __ldcg(qb + idx) : ~0ull;
-                    }
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const int idx = base + j * 32 + lane;
-                        if (idx < n) keys[idx] = (uint32_t)(e[j] >> 32);
+                        if (idx < na) keys[idx] = (uint32_t)(e[j] >> 32);
                     }
                 }
                 __syncwarp();
                 const uint32_t* kk = keys;
-                const uint32_t t = radix_select([kk](int i2) { return kk[i2]; }, n, kc, hist, lane);
-                if (t < KEY_MAX && lane == 0) atomicMin(a.gthr + q, t);
+                const uint32_t t = radix_select([kk](int i2) { return kk[i2]; }, na, kc, hist, lane);
+                if (t < KEY_MAX && lane == 0) atomicMin(a.gthr + qa, t);
                 __syncwarp();
-                if (lane == 0) *mb = 0ull;
+                if (lane == 0) mbox[ia] = 0ull;
+                ++served;
+                continue;
             }
-            if (!did) {
-                if (*ep_done >= 8u) break;
-                __nanosleep(200);
+            unsigned long long ea[8], eb[8];
+            load8(pa, na, ea);
+            if (ib >= 0) {
+                const unsigned long long* pb = decode(rb, qb2, nb);
+                load8(pb, nb, eb);
+            }
+            {
+                const uint32_t t = select8(ea);
+                if (t < KEY_MAX && lane == 0) atomicMin(a.gthr + qa, t);
+                if (lane == 0) mbox[ia] = 0ull;
+                ++served;
+            }
+            if (ib >= 0) {
+                const uint32_t t = select8(eb);
+                if (t < KEY_MAX && lane == 0) atomicMin(a.gthr + qb2, t);
+                if (lane == 0) mbox[ib] = 0ull;
+                ++served;
             }
         }
+        if (lane == 0 && served) atomicAdd(&a.ctrl[8], served);  // statistics: refreshes served
     }
     // ---- teardown: all tensor-memory traffic of this CTA has completed once every role has left its loop
     tc_fence_before();
