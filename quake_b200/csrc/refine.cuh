@@ -15,9 +15,15 @@
 
 namespace qk {
 
-static constexpr int MERGE_THREADS = 256;
+// 128 threads per query: with ~32 KB of shared memory seven CTAs share an SM, so a batch of 1024 queries is ONE wave of
+// 148 x 7 slots (with 256 threads it was 1.4 waves of five: the second wave ran at a third of the machine). Every loop
+// below strides by MERGE_THREADS / blockDim.x; nothing assumes a particular count beyond "a multiple of 32, <= 256".
+#ifndef QK_MERGE_THREADS
+#define QK_MERGE_THREADS 128
+#endif
+static constexpr int MERGE_THREADS = QK_MERGE_THREADS;
 static constexpr int MERGE_SORT_CAP = 4096;   // survivors gathered per query before the select (more => exact re-scan)
-static constexpr int MERGE_RANK_SORT_MAX = 256;  // candidate counts up to this are ordered by a one-pass rank sort
+static constexpr int MERGE_RANK_SORT_MAX = MERGE_THREADS;  // candidate counts up to this are ordered by a one-pass rank sort
 
 // ------------------------------------------------------------------------------------------------
 // block-wide bitonic sort of n (power of two) uint64 keys in shared memory (large k only)
@@ -160,11 +166,11 @@ __device__ int block_select_smallest(EntryAt entry_at, int n, int kc, uint32_t k
             if (in_bin) atomicAdd(&whist[warp * 256 + ((v >> sh) & ((1u << w) - 1u))], 1u);
         }
         __syncthreads();
-        if (tid < 256) {
+        for (int b = tid; b < 256; b += MERGE_THREADS) {
             unsigned t = 0;
 #pragma unroll
-            for (int ww = 0; ww < NW; ++ww) t += whist[ww * 256 + tid];
-            whist[tid] = t;  // column tid is only touched by this thread
+            for (int ww = 0; ww < NW; ++ww) t += whist[ww * 256 + b];
+            whist[b] = t;  // column b is only touched by this thread
         }
         __syncthreads();
         if (tid < 32) {  // lane l owns bins 8l .. 8l+7
@@ -273,7 +279,7 @@ __device__ void exact_rescan_body(const MergeArgs& a, int64_t q, const float* qs
     if (kk > 0) {
         // radix select of the kk-th smallest exact key, most significant byte first
         for (int pass = 3; pass >= 0; --pass) {
-            sm.hist[tid] = 0;
+            for (int b = tid; b < 256; b += blockDim.x) sm.hist[b] = 0;
             __syncthreads();
             const unsigned prefix = sm.prefix;
             for (int j = 0; j < nslots; ++j) {
@@ -315,7 +321,7 @@ __device__ void exact_rescan_body(const MergeArgs& a, int64_t q, const float* qs
             if (tid == 0) { sm.prefix64 = 0ull; sm.need = take_eq; }
             __syncthreads();
             for (int pass = 7; pass >= 0; --pass) {
-                sm.hist[tid] = 0;
+                for (int b = tid; b < 256; b += blockDim.x) sm.hist[b] = 0;
                 __syncthreads();
                 const uint64_t prefix = sm.prefix64;
                 for (int j = 0; j < nslots; ++j) {
@@ -366,7 +372,7 @@ __device__ void exact_rescan_body(const MergeArgs& a, int64_t q, const float* qs
                 int v = (lt ? 1 : 0) | (eq ? (1 << 16) : 0);
                 sm.scan[tid] = v;
                 __syncthreads();
-                for (int o = 1; o < 256; o <<= 1) {
+                for (int o = 1; o < (int)blockDim.x; o <<= 1) {
                     int t = (tid >= o) ? sm.scan[tid - o] : 0;
                     __syncthreads();
                     sm.scan[tid] += t;
@@ -388,7 +394,7 @@ __device__ void exact_rescan_body(const MergeArgs& a, int64_t q, const float* qs
                     rrow[slot] = (uint32_t)row;
                 }
                 __syncthreads();
-                if (tid == 255) {
+                if (tid == (int)blockDim.x - 1) {
                     sm.base_lt = blt + (incl & 0xffff);
                     sm.base_eq = beq + (incl >> 16);
                 }
@@ -466,7 +472,7 @@ __device__ void refine_and_emit(const MergeArgs& a, int64_t q, const uint64_t* c
         __syncthreads();
         if (kcp <= MERGE_RANK_SORT_MAX) {
             // one-pass rank sort: rank(i) = number of candidates ordered before i; P threads share one candidate
-            const int P = MERGE_THREADS / kcp;  // kcp is a power of two <= 256
+            const int P = MERGE_THREADS / kcp;  // kcp is a power of two <= MERGE_THREADS
             for (int i = tid; i < kcp; i += MERGE_THREADS) s.rank[i] = 0;
             __syncthreads();
             const int i = tid / P, part = tid - i * P;
@@ -591,14 +597,16 @@ __device__ __forceinline__ uint64_t* carve_refine(unsigned char* p, int d, int k
 // IVF stores: candidates from the per-query buffers the filter kernel appended to
 // ------------------------------------------------------------------------------------------------
 template <bool kIP>
-__global__ void __launch_bounds__(MERGE_THREADS, 5) merge_refine_kernel(const MergeArgs a) {
+__global__ void __launch_bounds__(MERGE_THREADS, MERGE_THREADS == 128 ? 8 : 5) merge_refine_kernel(const MergeArgs a) {
     extern __shared__ __align__(16) unsigned char msm[];
     uint64_t* sbuf = reinterpret_cast<uint64_t*>(msm);  // [sort_cap]
     const int kcp = next_pow2(a.kc);
     RefineSmem s;
     uint64_t* cbuf = carve_refine(msm + (size_t)a.sort_cap * 8, a.d, kcp, s);
-    __shared__ RescanSmem rs;
-    __shared__ unsigned s_whist[(MERGE_THREADS / 32) * 256];
+    // the exact re-scan only starts after the select is over: its scratch shares the histograms' storage
+    __shared__ __align__(16) unsigned s_whist[(MERGE_THREADS / 32) * 256 > (int)(sizeof(RescanSmem) / 4 + 1) ? (MERGE_THREADS / 32) * 256
+                                                                                                         : (int)(sizeof(RescanSmem) / 4 + 1)];
+    RescanSmem& rs = *reinterpret_cast<RescanSmem*>(s_whist);
     __shared__ uint64_t s_blist[SELECT_BOUNDARY_CAP];
     __shared__ int s_n, s_tot, s_flag;
     __shared__ unsigned s_sc[4], s_mm[2], s_T;
@@ -693,14 +701,16 @@ __global__ void __launch_bounds__(MERGE_THREADS, 5) merge_refine_kernel(const Me
 // the key of every (query, row); select the kc best here -- no thresholds, seeds, atomics or buffers in the filter
 // ------------------------------------------------------------------------------------------------
 template <bool kIP>
-__global__ void __launch_bounds__(MERGE_THREADS, 5) dense_refine_kernel(const MergeArgs a) {
+__global__ void __launch_bounds__(MERGE_THREADS, MERGE_THREADS == 128 ? 7 : 5) dense_refine_kernel(const MergeArgs a) {
     extern __shared__ __align__(16) unsigned char msm[];
     uint32_t* dkeys = reinterpret_cast<uint32_t*>(msm);  // [dense_rows rounded up to 2]
     const int kcp = next_pow2(a.kc);
     RefineSmem s;
     uint64_t* cbuf = carve_refine(msm + (size_t)((a.dense_rows + 1) & ~1) * 4, a.d, kcp, s);
-    __shared__ RescanSmem rs;
-    __shared__ unsigned s_whist[(MERGE_THREADS / 32) * 256];
+    // the exact re-scan only starts after the select is over: its scratch shares the histograms' storage
+    __shared__ __align__(16) unsigned s_whist[(MERGE_THREADS / 32) * 256 > (int)(sizeof(RescanSmem) / 4 + 1) ? (MERGE_THREADS / 32) * 256
+                                                                                                         : (int)(sizeof(RescanSmem) / 4 + 1)];
+    RescanSmem& rs = *reinterpret_cast<RescanSmem*>(s_whist);
     __shared__ uint64_t s_blist[SELECT_BOUNDARY_CAP];
     __shared__ int s_flag;
     __shared__ unsigned s_sc[4], s_mm[2], s_T, s_valid;

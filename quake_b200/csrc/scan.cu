@@ -1688,6 +1688,19 @@ extern "C" int qk_search_ivf(const qk_store_t* parent, const qk_store_t* store, 
                                 L.part_bytes, stats, stream, px);
 }
 
+#ifdef QK_STAGE_DEBUG
+// debug builds only (not part of the C ABI): per-role wait cycles of the tensor-core scan kernel, see scan_mma.cuh
+extern "C" int qk_debug_times(unsigned long long* out, int reset) {
+    if (out) QK_CUDA(cudaMemcpyFromSymbol(out, qk::g_dbg_times, sizeof(qk::g_dbg_times)));
+    if (reset) {
+        void* p = nullptr;
+        QK_CUDA(cudaGetSymbolAddress(&p, qk::g_dbg_times));
+        QK_CUDA(cudaMemset(p, 0, sizeof(qk::g_dbg_times)));
+    }
+    return QK_OK;
+}
+#endif
+
 // ---- per-launch timing of the filter kernel ------------------------------------------------------
 extern "C" int qk_profile_begin(int max_records) {
     QK_REQUIRE(max_records > 0 && max_records <= (1 << 20), "bad max_records");

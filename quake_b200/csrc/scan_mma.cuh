@@ -51,6 +51,20 @@ static constexpr int MMA_NACC = 4;            // accumulator buffers: the epilog
 static constexpr int MMA_TMEM_D = 0;          // MMA_NACC accumulator buffers x 64 columns (a.b_hi | a_hi.b_lo)
 static constexpr int MMA_TMEM_ALO = 256;      // MMA_STAGES a_lo boxes x 32 columns
 
+// -DQK_STAGE_DEBUG builds (scripts/gpu_roles.sh): cycles every role spends in its waits, accumulated per CTA in a
+// device array -- [launch kind: 0 partition scan, 1 flat / coarse][CTA][64 counters]
+#ifdef QK_STAGE_DEBUG
+__device__ unsigned long long g_dbg_times[2 * 148 * 64];
+#define QK_TDECL long long dbg_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}; const long long dbg_t00 = clock64();
+#define QK_TWAIT(slot, stmt) { const long long t0_ = clock64(); stmt; dbg_acc[slot] += clock64() - t0_; }
+#define QK_TFLUSH(base) { dbg_acc[0] = clock64() - dbg_t00; if (lane == 0 && blockIdx.x < 148) { \
+    for (int i_ = 0; i_ < 8; ++i_) atomicAdd(&g_dbg_times[((a.flat ? 148 : 0) + blockIdx.x) * 64 + (base) + i_], (unsigned long long)dbg_acc[i_]); } }
+#else
+#define QK_TDECL
+#define QK_TWAIT(slot, stmt) { stmt; }
+#define QK_TFLUSH(base) {}
+#endif
+
 struct MmaDesc {  // published in shared memory by the producer warp for every work item in flight
     WorkItem w;
     int q[MMA_NQ];       // query index of every query slot (-1: unused slot)
@@ -88,6 +102,44 @@ __device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64
         "{\n\t.reg .pred p, e;\n\telect.sync _|e, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"
         "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(tmem_d),
         "r"(tmem_a), "l"(db), "r"(idesc), "r"(acc)
+        : "memory");
+}
+// All four K-steps of one full row box (32 floats) in ONE asm block: a single election, the descriptors of the later
+// K-steps derived inside (a K-step advances both start addresses by 32 B = 2 descriptor units), no branch in between.
+// Issued one by one from C++ every MMA cost ~25 instructions (election, divergence check, five R2UR moves, 64-bit
+// descriptor adds, a bounds branch) and the issuing warps were the longest stage a tile went through.
+__device__ __forceinline__ void umma_box_ss4(uint32_t tmem_d, uint64_t da0, uint64_t db0, uint32_t idesc, uint32_t acc0) {
+    asm volatile(
+        "{\n\t.reg .pred p, e;\n\t.reg .b64 a1, a2, a3, b1, b2, b3;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "add.u64 a1, %1, 2;\n\tadd.u64 a2, %1, 4;\n\tadd.u64 a3, %1, 6;\n\t"
+        "add.u64 b1, %2, 2;\n\tadd.u64 b2, %2, 4;\n\tadd.u64 b3, %2, 6;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], a1, b1, %3, 1;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], a2, b2, %3, 1;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], a3, b3, %3, 1;\n\t}\n" ::"r"(tmem_d),
+        "l"(da0), "l"(db0), "r"(idesc), "r"(acc0)
+        : "memory");
+}
+// the same for the 3-term filter: a_hi . [b_hi | b_lo] (A from shared memory) and a_lo . b_hi (A from tensor memory, 8
+// columns per K-step) interleaved per K-step
+__device__ __forceinline__ void umma_box_ss4_ts4(uint32_t tmem_d, uint64_t da0, uint64_t db0, uint32_t talo, uint32_t idesc_hl,
+                                                 uint32_t idesc_h, uint32_t acc0) {
+    asm volatile(
+        "{\n\t.reg .pred p, e;\n\t.reg .b64 a1, a2, a3, b1, b2, b3;\n\t.reg .b32 t1, t2, t3;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\tsetp.ne.b32 p, %6, 0;\n\t"
+        "add.u64 a1, %1, 2;\n\tadd.u64 a2, %1, 4;\n\tadd.u64 a3, %1, 6;\n\t"
+        "add.u64 b1, %2, 2;\n\tadd.u64 b2, %2, 4;\n\tadd.u64 b3, %2, 6;\n\t"
+        "add.u32 t1, %3, 8;\n\tadd.u32 t2, %3, 16;\n\tadd.u32 t3, %3, 24;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %4, p;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], [%3], %2, %5, 1;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], a1, b1, %4, 1;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], [t1], b1, %5, 1;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], a2, b2, %4, 1;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], [t2], b2, %5, 1;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], a3, b3, %4, 1;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], [t3], b3, %5, 1;\n\t}\n" ::"r"(tmem_d),
+        "l"(da0), "l"(db0), "r"(talo), "r"(idesc_hl), "r"(idesc_h), "r"(acc0)
         : "memory");
 }
 // arrive on `bar` once every tcgen05 operation issued so far by the elected thread has completed
@@ -224,6 +276,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) scan_mma_kernel(const ScanArgs
         // index -> item -> query ids -> thresholds is consumed one iteration after it was issued, so none of them
         // is waited for. The descriptor of item n+1 is published BEFORE the row tiles of item n are issued, so
         // the split warps can prefetch its query chunk (B operand) while item n streams.
+        QK_TDECL
         const int n_items = a.flat ? a.flat_items : a.ctrl[1];
         auto fetch_index = [&]() {  // lane 0 holds the result; broadcast where it is consumed
             int it = 0;
@@ -250,10 +303,11 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) scan_mma_kernel(const ScanArgs
             return a.flat ? w.g_begin + lane : a.seg_pairs[w.g_begin + lane] / a.P;
         };
         auto fetch_gthr = [&](int q) { return q >= 0 ? __ldcg(a.gthr + q) : KEY_MAX; };
+        auto fetch_delta = [&](int q) { return (a.top1 && q >= 0) ? __ldg(a.qdelta + q) : 0.f; };
         // descriptor of item n; false when n is past the last item (the sentinel is published instead)
-        auto issue_desc_b = [&](uint32_t n, const WorkItem& m, int q, uint32_t gthr) {
+        auto issue_desc_b = [&](uint32_t n, const WorkItem& m, int q, uint32_t gthr, float delta) {
             const int id = n % ND;
-            mbar_wait(i_empty + id, ((n / ND) & 1u) ^ 1u);
+            QK_TWAIT(2, mbar_wait(i_empty + id, ((n / ND) & 1u) ^ 1u));
             if (m.seg < 0) {
                 if (lane == 0) {
                     descs[id].w.seg = -1;
@@ -263,61 +317,81 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) scan_mma_kernel(const ScanArgs
             }
             descs[id].q[lane] = q;
             descs[id].limf[lane] = q >= 0 ? key2lim(gthr) : -INFINITY;
-            descs[id].delta[lane] = (a.top1 && q >= 0) ? __ldg(a.qdelta + q) : 0.f;
+            descs[id].delta[lane] = delta;
             if (lane == 0) descs[id].w = m;
             __syncwarp();
             if (lane == 0) mbar_arrive(i_full + id);
             return true;
         };
+        // Metadata pipeline, one stage per loop iteration: index (atomic) -> item -> query ids -> thresholds. Every load
+        // is issued a whole iteration (one item's worth of TMA issue) before its result is used -- with the thresholds
+        // fetched in the same iteration as their use (as this loop used to) the producer stalled for a full L2/DRAM
+        // round trip per item, ~3 us of ~4, and the ring ran half empty (scripts/role_probe.py).
         WorkItem cur = fetch_item(__shfl_sync(0xffffffffu, fetch_index(), 0));
         WorkItem m1 = fetch_item(__shfl_sync(0xffffffffu, fetch_index(), 0));
         WorkItem m2 = fetch_item(__shfl_sync(0xffffffffu, fetch_index(), 0));
         WorkItem m3 = fetch_item(__shfl_sync(0xffffffffu, fetch_index(), 0));
-        int i4 = fetch_index();
-        int q1 = fetch_query(m1), q2 = fetch_query(m2);
-        uint32_t g1 = fetch_gthr(q1);
+        WorkItem m4 = fetch_item(__shfl_sync(0xffffffffu, fetch_index(), 0));
+        int i5 = fetch_index();
+        int q1 = fetch_query(m1), q2 = fetch_query(m2), q3 = fetch_query(m3);
+        uint32_t g1 = fetch_gthr(q1), g2 = fetch_gthr(q2);
+        float d1 = fetch_delta(q1), d2 = fetch_delta(q2);
         bool live;
         {
             const int q0 = fetch_query(cur);
-            live = issue_desc_b(0, cur, q0, fetch_gthr(q0));
+            live = issue_desc_b(0, cur, q0, fetch_gthr(q0), fetch_delta(q0));
         }
         uint32_t U = 0;
         for (uint32_t n = 0; live; ++n) {
-            const int i5 = fetch_index();  // consumed two iterations from now
-            const bool next_live = issue_desc_b(n + 1, m1, q1, g1);
+            const int i6 = fetch_index();  // consumed two iterations from now
+            bool next_live;
+            QK_TWAIT(4, next_live = issue_desc_b(n + 1, m1, q1, g1, d1));
             // ---- row tiles of item n
             const int ntiles = (cur.nrows + TM - 1) / TM;
             for (int tile = 0; tile < ntiles; ++tile) {
                 for (int b = 0; b < nbox; ++b, ++U) {
                     const int st = U % NS;
-                    mbar_wait(a_empty + st, ((U / NS) & 1u) ^ 1u);
-                    if (lane == 0) {
+                    QK_TWAIT(1, mbar_wait(a_empty + st, ((U / NS) & 1u) ^ 1u));
+                    QK_TWAIT(3, if (lane == 0) {
                         mbar_expect_tx(a_full + st, (uint32_t)MMA_BOX_BYTES);
                         tma_load_2d(As + (size_t)st * MMA_BOX_BYTES, &vmap, b * MMA_BOX, (int)(cur.row0 + (int64_t)tile * TM),
                                     a_full + st);
                     }
-                    __syncwarp();
+                    __syncwarp());
                 }
             }
-            // ---- rotate the metadata pipeline
+            // ---- rotate the metadata pipeline (every right-hand side was loaded at least one iteration ago)
+            QK_TWAIT(5,
             cur = m1;
-            m1 = m2; q1 = q2; g1 = fetch_gthr(q1);
-            m2 = m3; q2 = fetch_query(m2);
-            m3 = fetch_item(__shfl_sync(0xffffffffu, i4, 0));
-            i4 = i5;
-            live = next_live;
+            m1 = m2; q1 = q2; g1 = g2; d1 = d2;
+            m2 = m3; q2 = q3; g2 = fetch_gthr(q2); d2 = fetch_delta(q2);
+            m3 = m4; q3 = fetch_query(m3);
+            m4 = fetch_item(__shfl_sync(0xffffffffu, i5, 0));
+            i5 = i6;
+            live = next_live);
         }
+        QK_TFLUSH(0)
     } else if (warp == 1 || warp == 15) {
         // ===================================================================== MMA issuers
         // Issuer mi takes the tiles with (T & 1) == mi. tcgen05.commit only tracks the issuing thread's own MMAs: the
         // row boxes and the accumulator of a tile are released by the issuer that consumed them, the B slot of an item
         // by both (count 2).
-        const int mi = warp == 1 ? 0 : 1;
+        // Everything this role computes with is the same in all lanes; values that come out of shared memory or the
+        // thread index are broadcast from lane 0 (the compiler treats the result of such a shuffle as warp-uniform), so
+        // that the tile / ring counters and the MMA descriptors live in uniform registers. Without it every MMA was
+        // preceded by ~20 instructions of R2UR moves and divergence bookkeeping: the two issuers spent 65 of the
+        // kernel's 114 us issuing (scripts/role_probe.py), and a tile sat in the two-tile ring for that long.
+        const int mi = __shfl_sync(0xffffffffu, warp == 1 ? 0 : 1, 0);
+        const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
+        QK_TDECL
         uint32_t T = 0, U = 0;
         for (uint32_t n = 0;; ++n) {
             const int ib = n % NB, id = n % ND;
-            mbar_wait(i_full + id, (n / ND) & 1u);
-            const WorkItem d = descs[id].w;
+            QK_TWAIT(1, mbar_wait(i_full + id, (n / ND) & 1u));
+            WorkItem d;
+            d.seg = __shfl_sync(0xffffffffu, descs[id].w.seg, 0);
+            d.nrows = __shfl_sync(0xffffffffu, descs[id].w.nrows, 0);
+            d.g_cnt = __shfl_sync(0xffffffffu, descs[id].w.g_cnt, 0);
             if (d.seg < 0) break;
             __syncwarp();
             if (lane == 0) mbar_arrive(i_empty + id);  // only the descriptor header was needed
@@ -325,27 +399,31 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) scan_mma_kernel(const ScanArgs
             const int npad = (d.g_cnt <= 16 && !QK_DBG(a, 16)) ? 16 : 32;
             const uint32_t idesc_hl = umma_idesc_tf32(MMA_TM, 2 * npad);  // a_hi . [b_hi | b_lo]
             const uint32_t idesc_h = umma_idesc_tf32(MMA_TM, npad);       // a_lo . b_hi
-            mbar_wait(b_ready + ib, (n / NB) & 1u);
+            QK_TWAIT(2, mbar_wait(b_ready + ib, (n / NB) & 1u));
             const uint32_t bs = smem_u32(Bs + (size_t)ib * 4 * MMA_BBOX_BYTES);
             const int ntiles = (d.nrows + TM - 1) / TM;
             for (int tile = 0; tile < ntiles; ++tile, ++T) {
                 const int db = T % MMA_NACC;
                 if ((int)(T & 1u) != mi) { U += nbox; continue; }
-                mbar_wait(d_empty + db, ((T / MMA_NACC) & 1u) ^ 1u);
-                const uint32_t tmem_d = tmem + MMA_TMEM_D + db * (2 * MMA_NQ);
+                QK_TWAIT(3, mbar_wait(d_empty + db, ((T / MMA_NACC) & 1u) ^ 1u));
+                const uint32_t tmem_d = tmem_u + MMA_TMEM_D + db * (2 * MMA_NQ);
                 for (int b = 0; b < nbox; ++b, ++U) {
                     const int st = U % NS;
                     const uint64_t da0 = umma_desc_sw128(smem_u32(As + (size_t)st * MMA_BOX_BYTES));
                     const uint64_t db0 = umma_desc_sw128(bs + b * MMA_BBOX_BYTES);
-                    const uint32_t talo = tmem + MMA_TMEM_ALO + st * MMA_BOX;
+                    const uint32_t talo = tmem_u + MMA_TMEM_ALO + st * MMA_BOX;
                     const int ksteps = min(4, (dp - b * MMA_BOX + 7) >> 3);
                     if (a.terms == 2) {
                         // 2xTF32: a_hi . (b_hi + b_lo) only -- no a_lo term, nothing to wait for but the TMA data
-                        mbar_wait(a_full + st, (U / NS) & 1u);
+                        QK_TWAIT(4, mbar_wait(a_full + st, (U / NS) & 1u));
                         tc_fence_after();
+                        if (ksteps == 4) {
+                            umma_box_ss4(tmem_d, da0, db0, idesc_hl, b ? 1u : 0u);
+                        } else {
 #pragma unroll
-                        for (int kk = 0; kk < 4; ++kk)
-                            if (kk < ksteps) umma_ss(tmem_d, da0 + 2 * kk, db0 + 2 * kk, idesc_hl, (b | kk) ? 1u : 0u);
+                            for (int kk = 0; kk < 4; ++kk)
+                                if (kk < ksteps) umma_ss(tmem_d, da0 + 2 * kk, db0 + 2 * kk, idesc_hl, (b | kk) ? 1u : 0u);
+                        }
                     } else if (QK_DBG(a, 8)) {
                         // the a_hi products only need the TMA data: they run while the split warps still derive a_lo
                         mbar_wait(a_full + st, (U / NS) & 1u);
@@ -360,13 +438,17 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) scan_mma_kernel(const ScanArgs
                             if (kk < ksteps) umma_ts(tmem_d, talo + kk * 8, db0 + 2 * kk, idesc_h, 1u);
                     } else {
                         // the split warps waited for the TMA data of this box themselves: a_lo ready => a_hi ready
-                        mbar_wait(alo_full + st, (U / NS) & 1u);
+                        QK_TWAIT(4, mbar_wait(alo_full + st, (U / NS) & 1u));
                         tc_fence_after();
+                        if (ksteps == 4 && !(QK_DBG(a, 2))) {
+                            umma_box_ss4_ts4(tmem_d, da0, db0, talo, idesc_hl, idesc_h, b ? 1u : 0u);
+                        } else {
 #pragma unroll
-                        for (int kk = 0; kk < 4; ++kk) {
-                            if (kk < ksteps && !(QK_DBG(a, 2))) {  // a K-step advances both start addresses by 32 B (2 descriptor units)
-                                umma_ss(tmem_d, da0 + 2 * kk, db0 + 2 * kk, idesc_hl, (b | kk) ? 1u : 0u);
-                                umma_ts(tmem_d, talo + kk * 8, db0 + 2 * kk, idesc_h, 1u);
+                            for (int kk = 0; kk < 4; ++kk) {
+                                if (kk < ksteps && !(QK_DBG(a, 2))) {  // a K-step advances both start addresses by 32 B (2 descriptor units)
+                                    umma_ss(tmem_d, da0 + 2 * kk, db0 + 2 * kk, idesc_hl, (b | kk) ? 1u : 0u);
+                                    umma_ts(tmem_d, talo + kk * 8, db0 + 2 * kk, idesc_h, 1u);
+                                }
                             }
                         }
                     }
@@ -376,6 +458,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) scan_mma_kernel(const ScanArgs
             }
             umma_commit(b_empty + ib);
         }
+        QK_TFLUSH(mi ? 16 : 8)
     } else if (warp < 6) {
         // ===================================================================== split warps
         // Besides a_lo, these 128 threads build the B operand of every item: thread (warp w, lane c) owns the
@@ -390,9 +473,10 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) scan_mma_kernel(const ScanArgs
         const bool c_used = lane < nbox * 8;  // chunk column inside the boxes the MMA reads
         uint32_t U = 0;
         float4 bq[8];
+        QK_TDECL
         auto prefetch_b = [&](uint32_t n, WorkItem& w) {  // reads descriptor n, issues the loads, releases it
             const int id = n % ND;
-            mbar_wait(i_full + id, (n / ND) & 1u);
+            QK_TWAIT(1, mbar_wait(i_full + id, (n / ND) & 1u));
             w = descs[id].w;
             if (w.seg >= 0) {
 #pragma unroll
@@ -411,7 +495,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) scan_mma_kernel(const ScanArgs
         for (uint32_t n = 0;; ++n) {
             if (d.seg < 0) break;
             const int ib = n % NB;
-            mbar_wait(b_empty + ib, ((n / NB) & 1u) ^ 1u);  // the MMAs of item n - NB have completed
+            QK_TWAIT(2, mbar_wait(b_empty + ib, ((n / NB) & 1u) ^ 1u));  // the MMAs of item n - NB have completed
             if (c_used) {
                 unsigned char* bs = Bs + (size_t)ib * 4 * MMA_BBOX_BYTES + (size_t)(lane >> 3) * MMA_BBOX_BYTES;
                 const int npad = (d.g_cnt <= 16 && !QK_DBG(a, 16)) ? 16 : 32;
@@ -439,7 +523,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) scan_mma_kernel(const ScanArgs
             for (int tile = 0; tile < ntiles; ++tile) {
                 for (int b = 0; b < nbox; ++b, ++U) {
                     const int st = U % NS;
-                    mbar_wait(a_full + st, (U / NS) & 1u);
+                    QK_TWAIT(3, mbar_wait(a_full + st, (U / NS) & 1u));
                     const unsigned char* rowp = As + (size_t)st * MMA_BOX_BYTES + r * 128;
                     uint32_t v[32];
                     if (!(QK_DBG(a, 4)))
@@ -458,6 +542,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) scan_mma_kernel(const ScanArgs
                 }
             }
         }
+        if (warp == 2) QK_TFLUSH(24)
     } else if (warp < 14) {
         // ===================================================================== epilogue + selection
         const int eg = (warp - 6) >> 2;  // group: takes tiles with (T & 1) == eg
@@ -466,10 +551,11 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) scan_mma_kernel(const ScanArgs
         volatile unsigned long long* my_box = mbox + (warp - 6) * 4 + (lane & a.refresh_boxes);
         const int rmask = a.refresh_step - 1;  // a refresh is requested whenever a query's fill passes a multiple of this
         int dropped = 0;
+        QK_TDECL
         uint32_t T = 0;
         for (uint32_t n = 0;; ++n) {
             const int id = n % ND;
-            mbar_wait(i_full + id, (n / ND) & 1u);
+            QK_TWAIT(1, mbar_wait(i_full + id, (n / ND) & 1u));
             const WorkItem d = descs[id].w;
             if (d.seg < 0) break;
             const int g_cnt = d.g_cnt;
@@ -488,8 +574,11 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) scan_mma_kernel(const ScanArgs
                 float nrm = 0.f;
                 if (!kIP && r < tr) nrm = __ldg(a.norms + d.row0 + (int64_t)tile * TM + r);
                 const int db = T % MMA_NACC;  // group eg sees the buffers with db & 1 == eg
-                mbar_wait(d_full + db, (T / MMA_NACC) & 1u);
+                QK_TWAIT(2, mbar_wait(d_full + db, (T / MMA_NACC) & 1u));
                 tc_fence_after();
+#ifdef QK_STAGE_DEBUG
+                const long long t_tile0 = clock64();
+#endif
                 // dot = (a_hi + a_lo) . b_hi [columns 0 .. npad-1] + a_hi . b_lo [columns npad .. 2 npad - 1]
                 uint32_t v[32];
                 {
@@ -562,6 +651,9 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) scan_mma_kernel(const ScanArgs
                         for (int g = 0; g < MMA_NQ; ++g)
                             if (g < g_cnt) a.dense[(size_t)dq[g] * a.dense_rows + lrow] = f2key(__uint_as_float(v[g]));
                     }
+#ifdef QK_STAGE_DEBUG
+                    dbg_acc[3] += clock64() - t_tile0;
+#endif
                     continue;
                 }
                 pm &= gvalid;
@@ -604,10 +696,15 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) scan_mma_kernel(const ScanArgs
                     const float f = key2lim(g_now);
                     if (f < limf[lane]) limf[lane] = f;
                 }
+#ifdef QK_STAGE_DEBUG
+                dbg_acc[3] += clock64() - t_tile0;
+#endif
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(i_empty + id);
         }
+        if (warp == 6) QK_TFLUSH(32)
+        if (warp == 10) QK_TFLUSH(40)
         dropped = __reduce_add_sync(0xffffffffu, dropped);
         if (lane == 0 && dropped) atomicAdd(&a.ctrl[9], dropped);  // statistics: refresh requests that found the mailbox busy
         __syncwarp();

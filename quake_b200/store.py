@@ -460,10 +460,12 @@ class PartitionStore:
             return 256
         if self.nlist > 16 or self.list_size.size == 0:
             return _MAX_SEGMENT_ROWS
+        if os.environ.get("QK_FLAT_SEG_LEN"):  # experiments: few-list stores only (the coarse scan)
+            return int(os.environ["QK_FLAT_SEG_LEN"])
         chunks = max(1, (num_queries + 31) // 32) * min(self.nlist, nprobe)
         longest = max(int(self.list_size.max()), 1)
         seg_len = _MAX_SEGMENT_ROWS
-        while seg_len > 256 and chunks * ((longest + seg_len - 1) // seg_len) < 222:  # ~1.5 items per SM (measured best)
+        while seg_len > 256 and chunks * ((longest + seg_len - 1) // seg_len) < 444:  # ~3 items per SM (coarse scan of C2: 30 us at 3.5 items per SM, 42 us at 1.7)
             seg_len //= 2
         return seg_len
 
