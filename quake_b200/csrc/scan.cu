@@ -721,6 +721,7 @@ struct ScanArgs {
     int P, kc, gq, nq;
     int qcap;
     int qstride;       // ints between consecutive queries' fill counters
+    int refresh_first;                 // an extra, early refresh request when a query's fill reaches this (0: none)
     int refresh_boxes, refresh_fresh;  // mailboxes per epilogue warp - 1 (0, 1 or 3); re-read the fill when serving
     int refresh_step, refresh_window;  // tensor-core path: threshold refresh cadence (appends, power of two) / entries looked at
     uint32_t* dense;      // dense mode: [Q x dense_rows] filter keys of every (query, row); null otherwise
@@ -1243,17 +1244,18 @@ static int ensure_smem_impl(const void* kern, size_t bytes) {
 template <typename K>
 static int ensure_smem(K kern, size_t bytes) { return ensure_smem_impl((const void*)kern, bytes); }
 
-static int launch_scan(const ScanArgs& sa, const CUtensorMap& vmap, int metric, size_t smem, bool mma, cudaStream_t stream) {
+static int launch_scan(const ScanArgs& sa, const CUtensorMap& vmap, const CUtensorMap& vmap_sub, int metric, size_t smem, bool mma,
+                       cudaStream_t stream) {
     const int grid = sm_count();
     int rc;
     if (mma) {
         const size_t msmem = scan_mma_smem_bytes();
         if (metric == QK_METRIC_INNER_PRODUCT) {
             if ((rc = ensure_smem(scan_mma_kernel<true>, msmem))) return rc;
-            scan_mma_kernel<true><<<grid, MMA_THREADS, msmem, stream>>>(sa, vmap);
+            scan_mma_kernel<true><<<grid, MMA_THREADS, msmem, stream>>>(sa, vmap, vmap_sub);
         } else {
             if ((rc = ensure_smem(scan_mma_kernel<false>, msmem))) return rc;
-            scan_mma_kernel<false><<<grid, MMA_THREADS, msmem, stream>>>(sa, vmap);
+            scan_mma_kernel<false><<<grid, MMA_THREADS, msmem, stream>>>(sa, vmap, vmap_sub);
         }
     } else if (metric == QK_METRIC_INNER_PRODUCT) {
         if ((rc = ensure_smem(scan_kernel<true>, smem))) return rc;
@@ -1456,6 +1458,8 @@ int qk::scan_partitions_impl(const qk_store_t* st, const float* queries, int64_t
         static const int env_fresh = getenv("QK_REFRESH_FRESH") ? atoi(getenv("QK_REFRESH_FRESH")) : 0;
         sa.refresh_boxes = env_boxes == 4 ? 3 : (env_boxes == 2 ? 1 : 0);
         sa.refresh_fresh = env_fresh;
+        static const int env_first = getenv("QK_REFRESH_FIRST") ? atoi(getenv("QK_REFRESH_FIRST")) : 0;
+        sa.refresh_first = env_first;
     }
     sa.fixed_thr = collect ? 1 : 0;
     sa.top1 = top1 ? 1 : 0;
@@ -1480,13 +1484,15 @@ int qk::scan_partitions_impl(const qk_store_t* st, const float* queries, int64_t
     // forces the latter (tests cross-check the two).
     rc = make_row_tensor_map(st, use_mma ? MMA_TM : SCAN_TV, &vmap);
     if (rc) return rc;
+    CUtensorMap vmap_sub = vmap;  // tensor-core path: a half-height box for the short last tile of a list
+    if (use_mma && (rc = make_row_tensor_map(st, MMA_SUB_ROWS, &vmap_sub))) return rc;
     ProfileRecord* rec = nullptr;
     if (g_prof && g_prof_n < g_prof_cap) {
         rec = &g_prof[g_prof_n++];
         rec->queries = Q; rec->nprobe = nprobe; rec->k = k; rec->used = 1;
         QK_CUDA(cudaEventRecord(rec->start, stream));
     }
-    rc = launch_scan(sa, vmap, metric, p.smem, use_mma, stream);
+    rc = launch_scan(sa, vmap, vmap_sub, metric, p.smem, use_mma, stream);
     if (rc) return rc;
     if (rec) QK_CUDA(cudaEventRecord(rec->stop, stream));
 

@@ -40,6 +40,7 @@ static constexpr int MMA_NQ = 32;             // query slots per item (UMMA N)
 static constexpr int MMA_BOX = 32;            // floats per TMA box row (128 B, one swizzle atom row)
 static constexpr int MMA_STAGES = 8;          // ring of A boxes, 16 KB each (two whole 128-row tiles at d = 128)
 static constexpr int MMA_BOX_BYTES = MMA_TM * 128;
+static constexpr int MMA_SUB_ROWS = 64;       // rows of the half-height box a list's short last tile is loaded with
 static constexpr int MMA_NB = 2;              // B-operand slots (query chunk hi + lo, 32 KB each)
 static constexpr int MMA_ND = 5;              // work-item descriptor slots (the selection warps lag the MMAs)
 static constexpr int MMA_BBOX_BYTES = 2 * MMA_NQ * 128;  // 8 KB: (32 queries hi + 32 queries lo) x 32 floats
@@ -215,7 +216,8 @@ __device__ __forceinline__ uint32_t pick32(const uint32_t (&v)[32], int g) {
 __device__ __forceinline__ float key2lim(uint32_t t) { return t == KEY_MAX ? INFINITY : key2f(t); }
 
 template <bool kIP>
-__global__ void __launch_bounds__(MMA_THREADS, 1) scan_mma_kernel(const ScanArgs a, const __grid_constant__ CUtensorMap vmap) {
+__global__ void __launch_bounds__(MMA_THREADS, 1) scan_mma_kernel(const ScanArgs a, const __grid_constant__ CUtensorMap vmap,
+                                                                const __grid_constant__ CUtensorMap vmap_sub) {
     constexpr int TM = MMA_TM, NB = MMA_NB, ND = MMA_ND;
     static_assert(MMA_STAGES <= 16 && 768 + MMA_ND * sizeof(MmaDesc) <= 3072 && 3072 + 32 * 8 <= MMA_SMEM_HEADER, "descriptor ring");
     extern __shared__ __align__(16) unsigned char smem_dyn[];
@@ -347,18 +349,31 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) scan_mma_kernel(const ScanArgs
             bool next_live;
             QK_TWAIT(4, next_live = issue_desc_b(n + 1, m1, q1, g1, d1));
             // ---- row tiles of item n
+            // lane b issues box b of the tile: the (up to four) slot waits and TMA issues of a tile run side by side
+            // instead of one after the other (~160 cycles each: the producer was busy, not blocked, most of the time)
             const int ntiles = (cur.nrows + TM - 1) / TM;
-            for (int tile = 0; tile < ntiles; ++tile) {
-                for (int b = 0; b < nbox; ++b, ++U) {
-                    const int st = U % NS;
-                    QK_TWAIT(1, mbar_wait(a_empty + st, ((U / NS) & 1u) ^ 1u));
-                    QK_TWAIT(3, if (lane == 0) {
+            for (int tile = 0; tile < ntiles; ++tile, U += nbox) {
+                QK_TWAIT(1, if (lane < nbox) {
+                    const uint32_t Ub = U + lane;
+                    const int st = Ub % NS;
+                    mbar_wait(a_empty + st, ((Ub / NS) & 1u) ^ 1u);
+                    const int tr = cur.nrows - tile * TM;  // rows of this tile that belong to the list
+                    unsigned char* dst = As + (size_t)st * MMA_BOX_BYTES;
+                    const int y0 = (int)(cur.row0 + (int64_t)tile * TM);
+                    if (tr > MMA_SUB_ROWS) {
                         mbar_expect_tx(a_full + st, (uint32_t)MMA_BOX_BYTES);
-                        tma_load_2d(As + (size_t)st * MMA_BOX_BYTES, &vmap, b * MMA_BOX, (int)(cur.row0 + (int64_t)tile * TM),
-                                    a_full + st);
+                        tma_load_2d(dst, &vmap, lane * MMA_BOX, y0, a_full + st);
+                    } else {
+                        // a short last tile of a list: ONE half-height box. The rows after it keep whatever an earlier
+                        // tile left in the slot (finite data, or anything at all in the first round: every row's scores
+                        // depend on that row alone, and the epilogue masks them); loading them would re-read the head
+                        // of the next list. (Finer sub-boxes -- 32 rows, up to three per slot -- cut the DRAM traffic
+                        // further but cost more in TMA issues than they saved: 134.7 vs 131.6 us at C2.)
+                        mbar_expect_tx(a_full + st, (uint32_t)(MMA_SUB_ROWS * 128));
+                        tma_load_2d(dst, &vmap_sub, lane * MMA_BOX, y0, a_full + st);
                     }
-                    __syncwarp());
                 }
+                __syncwarp());
             }
             // ---- rotate the metadata pipeline (every right-hand side was loaded at least one iteration ago)
             QK_TWAIT(5,
@@ -599,6 +614,13 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) scan_mma_kernel(const ScanArgs
                     }
                 }
                 tc_fence_before();
+                // fold in what every SM has learnt about the queries meanwhile (read before the wait above) BEFORE this
+                // tile is scored; every warp does it for itself -- all values ever written are valid upper bounds, so
+                // the races between the warps of an item are benign
+                if (my_q >= 0 && !a.dense) {
+                    const float f = key2lim(g_now);
+                    if (f < limf[lane]) limf[lane] = f;
+                }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(d_empty + db);
                 if (QK_DBG(a, 1)) continue;
@@ -683,18 +705,12 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) scan_mma_kernel(const ScanArgs
                             if (slot < qcap) a.qbuf[(size_t)qs[i] * qcap + slot] = ((uint64_t)key[i] << 32) | arow;
                             // the fill passed a multiple of 64: ask a refresh warp for a new threshold (a busy
                             // mailbox just drops the request -- thresholds are an optimisation)
-                            if ((slot & rmask) == rmask && slot + 1 >= kc && !a.fixed_thr && !a.top1) {
+                            if (((slot & rmask) == rmask || slot + 1 == a.refresh_first) && slot + 1 >= kc && !a.fixed_thr && !a.top1) {
                                 if (*my_box == 0ull) *my_box = ((unsigned long long)(qs[i] + 1) << 32) | (uint32_t)(slot + 1);
                                 else ++dropped;
                             }
                         }
                     }
-                }
-                // fold in the global thresholds read at the top of the tile (a benign race between the two groups:
-                // every value ever written is a valid upper bound)
-                if (q4 == 0 && my_q >= 0) {
-                    const float f = key2lim(g_now);
-                    if (f < limf[lane]) limf[lane] = f;
                 }
 #ifdef QK_STAGE_DEBUG
                 dbg_acc[3] += clock64() - t_tile0;
