@@ -18,6 +18,7 @@ from ._lib import check, ptr
 _FIRST_ROUND = 2   # probe ranks scanned in the first round (pseudo-queries with a full top-k each)
 _MAX_ROUND = 128   # ... doubling every round while most queries are still active
 _MAX_PSEUDO = 1 << 17  # pseudo-queries (query, rank) per scan call
+_MAX_COLLECT_ENTRIES = 1 << 26  # (query, rank, k) result entries of one collect round (12 B each: 768 MB)
 
 _beta_tables: dict = {}
 _TRACE = os.environ.get("QK_APS_TRACE") == "1"
@@ -143,8 +144,14 @@ def adaptive_scan(index, xq: torch.Tensor, cand_rows: torch.Tensor, slots: torch
         if n_still == 0:
             break
         # every round streams the probed lists again: while most queries are still going, bigger rounds cost less than
-        # the ranks a finishing query over-scans; once most have stopped, keep the round size
+        # the ranks a finishing query over-scans; once most have stopped, keep the round size. Once a round touches most
+        # of the index anyway (active queries x ranks >= half the lists: a pass over all of HBM whatever the round
+        # size), the passes are what costs, not the ranks: the scanned prefix then grows five-fold per round (C3:
+        # rounds 14..69 and 70..326 instead of five doubling rounds, each a full pass over the 5 GB index).
         if 2 * n_still > Qa:
             R = min(2 * R, _MAX_ROUND)
+            if collect_ok and 2 * n_still * R >= store.nlist:
+                dense_r = min(4 * p, max(1, _MAX_COLLECT_ENTRIES // (n_still * k)))
+                R = max(R, dense_r)
         active = torch.nonzero(done == 0).reshape(-1).to(torch.int32)
     return run_ids, run_dist, scanned

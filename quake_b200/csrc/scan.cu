@@ -221,11 +221,11 @@ static int make_plan(const qk_store_t* st, int64_t Q, int nprobe, int k, ScanPla
         static const int env_sample = getenv("QK_SEED_SAMPLE") ? atoi(getenv("QK_SEED_SAMPLE")) : -1;  // experiments
         if (env_sample >= 0 && st->num_lists > 1) sample = env_sample;
         if (sample < p->kc) sample = 0;
-        // dense mode: [Q x rows] keys, at most 512 MB and at most 16384 rows (the select keeps a query's keys in smem).
+        // dense mode: [Q x rows] keys, at most 512 MB and at most 32768 rows (the select keeps a query's keys in smem).
         // Only a flat-mode call (no probe table) uses it; the workspace is sized for either.
         static const bool no_dense = getenv("QK_NO_DENSE") != nullptr;
         const bool dense_ok = p->flat_seed && g_scan_variant == 0 && p->dp <= 128 && Q <= 8192 && st->flat_rows >= p->kc &&
-                              st->flat_rows <= 16384 && (size_t)Q * (size_t)st->flat_rows * 4 <= ((size_t)512 << 20) && !no_dense;
+                              st->flat_rows <= 32768 && (size_t)Q * (size_t)st->flat_rows * 4 <= ((size_t)512 << 20) && !no_dense;
         p->dense = (dense_ok && allow_dense) ? 1 : 0;
         p->sample = p->dense ? 0 : sample;
         p->off_skeys = o;

@@ -5,7 +5,7 @@ sys.path.insert(0, ROOT)
 import torch
 import quake_b200 as qb
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 5_000_000
-nlist = n // 610
+nlist = 16384 if n == 10_000_000 else n // 610  # C3: 10M vectors, nlist 16384
 torch.manual_seed(1234)
 x = torch.randn(n, 128); x /= x.norm(dim=1, keepdim=True)
 torch.manual_seed(4321)
@@ -27,3 +27,24 @@ for mode in ("1", "0"):
         ref_ids = r.ids.clone()
     else:
         print("ids equal between modes:", bool(torch.equal(ref_ids, r.ids)))
+
+# where the time goes outside the rounds: the candidate search in the parent (k = 2 % of the centroids)
+from quake_b200 import clustering
+os.environ["QK_APS_COLLECT"] = "1"
+xq = clustering.pad_rows(q, idx.store.device)
+psp = qb.SearchParams(); psp.batched_scan = True; psp.recall_target = 0.9
+psp.k = max(int(idx.nlist() * 0.02), 1)
+for _ in range(2):
+    idx.parent._search_device(xq, psp, want_rows=True)
+torch.cuda.synchronize(); t0 = time.perf_counter()
+for _ in range(5):
+    idx.parent._search_device(xq, psp, want_rows=True)
+torch.cuda.synchronize()
+print(f"candidate search in the parent (k = {psp.k}): {(time.perf_counter() - t0) / 5 * 1e3:.2f} ms", flush=True)
+for _ in range(2):
+    idx._search_device(xq, sp)
+torch.cuda.synchronize(); t0 = time.perf_counter()
+for _ in range(5):
+    idx._search_device(xq, sp)
+torch.cuda.synchronize()
+print(f"whole APS search, device-resident queries: {(time.perf_counter() - t0) / 5 * 1e3:.2f} ms", flush=True)
