@@ -495,6 +495,7 @@ def run_b200(args):
             traffic = json.load(open(os.path.join(ROOT, "profiles", "scan_kernel_traffic.json"))).get("dram_bytes_per_launch")
         except Exception:
             pass
+        terms = int(idx.store.filter_terms)
         line = {
             "metric": METRIC, "value": world * W["Q"] / (dev_ms * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms, "higher_is_better": True,
@@ -507,6 +508,9 @@ def run_b200(args):
             "roofline": {"bound": "hbm", "kernel": "scan_mma_kernel (partition-scan filter, tcgen05)", "achieved": achieved,
                          "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None, "traffic": traffic,
                          "traffic_source": "profiles/scan_kernel_traffic.json (one ncu --set full capture of this command)",
+                         "traffic_over_algorithmic": round(traffic / alg_bytes, 4) if traffic and alg_bytes else None,
+                         "filter": f"{terms}xTF32 tensor-core filter (3 = a_hi.b_hi + a_lo.b_hi + a_hi.b_lo, 2 = no a_lo term; chosen "
+                                   "on evidence by the index, results exact either way: refine + proof + exact re-scan)",
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
                          "per_query_list_bytes_per_launch": pair_bytes, "kernel_ms": scan_ms_avg,
                          "kernel_share_of_step": scan_ms_avg / dev_ms if dev_ms else None,

@@ -315,10 +315,24 @@ class QuakeIndex:
                     stage.clear()
                 stage[key] = (torch.empty(key, dtype=torch.int64).pin_memory(), torch.empty(key, dtype=torch.float32).pin_memory())
             h_ids, h_dist = stage[key]
-            h_ids.copy_(ids, non_blocking=True)
-            h_dist.copy_(dist, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-            res.ids, res.distances = h_ids.clone(), h_dist.clone()
+            n8 = ids.numel() * 8
+            if (ids.is_contiguous() and dist.is_contiguous() and ids.dtype == torch.int64
+                    and dist.data_ptr() == ids.data_ptr() + n8):
+                # one allocation on the device (_search_ivf), one on the host: a single D2H copy
+                if key not in stage.setdefault("_blocks", {}):
+                    hb = torch.empty(n8 + dist.numel() * 4, dtype=torch.uint8).pin_memory()
+                    stage["_blocks"][key] = {"block": hb, "ids": hb[:n8].view(torch.int64).view(ids.shape),
+                                             "dist": hb[n8:].view(torch.float32).view(dist.shape)}
+                hb = stage["_blocks"][key]
+                dblock = torch.as_strided(ids.view(torch.uint8).reshape(-1), (n8 + dist.numel() * 4,), (1,))
+                hb["block"].copy_(dblock, non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+                res.ids, res.distances = hb["ids"].clone(), hb["dist"].clone()
+            else:
+                h_ids.copy_(ids, non_blocking=True)
+                h_dist.copy_(dist, non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+                res.ids, res.distances = h_ids.clone(), h_dist.clone()
         else:
             res.ids = ids.to(out_dev, copy=True)
             res.distances = dist.to(out_dev, copy=True)
@@ -418,8 +432,10 @@ class QuakeIndex:
         if wsb == 0:
             check(1)
         ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
-        out_ids = torch.empty((Q, k), dtype=torch.int64, device=dev)
-        out_dist = torch.empty((Q, k), dtype=torch.float32, device=dev)
+        # ids and distances share one allocation: search() brings both to the host with ONE copy
+        block = torch.empty(Q * k * 12, dtype=torch.uint8, device=dev)
+        out_ids = block[: Q * k * 8].view(torch.int64).view(Q, k)
+        out_dist = block[Q * k * 8:].view(torch.float32).view(Q, k)
         p_ids = torch.empty((Q, np_), dtype=torch.int64, device=dev)
         # statistics of the partition scan {queries re-scanned exactly, max / total candidates}: the filter precision
         # policy reads them back asynchronously (_FilterMonitor)

@@ -74,7 +74,7 @@ def test_segment_len_heuristic():
     assert ivf.segment_len(1024, 64) == 4096          # many short lists: leave them whole
     assert ivf.segment_len(4, 8) == 256               # tiny batch: spread the work
     coarse = _host_store([4096])
-    assert coarse.segment_len(1024, 1) == 512         # the C2 coarse scan: 32 chunks x 8 segments
+    assert coarse.segment_len(1024, 1) == 256         # the C2 coarse scan: 32 chunks x 16 segments (~3.5 items per SM)
     big = _host_store([65536])
     assert big.segment_len(1024, 1) >= 2048           # already plenty of items
     assert coarse.segment_len(32768, 1) == 4096       # k-means assign batches: chunks alone fill the GPU
