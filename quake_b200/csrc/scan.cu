@@ -461,13 +461,13 @@ __device__ __forceinline__ uint32_t radix_select(KeyAt key_at, int n, int kc, ui
 // now 25 us). Plain 16-byte loads into registers, eight rows in flight per warp, were slower (32 us).
 static constexpr int SEED_THREADS = 128;
 static constexpr int SEED_WARPS = SEED_THREADS / 32;
-static int seed_chunk_rows(int dp, int sample) {  // rows staged per step: at most 16 KB (32 rows at d = 128)
-    int c = (16 * 1024) / (dp * 4);
-    if (c < 8) c = 8;
+static int seed_chunk_rows(int dp, int sample) {  // rows per staging buffer: at most 8 KB (16 rows at d = 128); two buffers
+    int c = (8 * 1024) / (dp * 4);
+    if (c < 4) c = 4;
     return sample < c ? sample : c;
 }
 static size_t seed_smem_bytes(int dp, int sample) {
-    return (size_t)seed_chunk_rows(dp, sample) * dp * 4 + (size_t)dp * 4 + (size_t)sample * 8 + 16;
+    return (size_t)2 * seed_chunk_rows(dp, sample) * dp * 4 + (size_t)dp * 4 + (size_t)sample * 8 + 16;
 }
 template <bool kIP>
 __global__ void __launch_bounds__(SEED_THREADS, 8) seed_thresholds_kernel(const float* __restrict__ vecs, int64_t pitch,
@@ -479,13 +479,13 @@ __global__ void __launch_bounds__(SEED_THREADS, 8) seed_thresholds_kernel(const 
                                                               int chunk_rows, float max_row_norm, float rel_margin,
                                                               uint32_t* __restrict__ gthr) {
     extern __shared__ __align__(128) unsigned char seed_raw[];
-    float* rows = reinterpret_cast<float*>(seed_raw);                 // [chunk_rows][dp]
-    float* qs = rows + (size_t)chunk_rows * dp;                       // [dp]
+    float* rows = reinterpret_cast<float*>(seed_raw);                 // [2][chunk_rows][dp]: double-buffered staging
+    float* qs = rows + (size_t)2 * chunk_rows * dp;                   // [dp]
     uint32_t* keys = reinterpret_cast<uint32_t*>(qs + dp);            // [sample]
     float* nrm = reinterpret_cast<float*>(keys + sample);             // [sample] squared norms of the sampled rows
     __shared__ int s_start[33];      // exclusive prefix of the sampled rows over the first 32 probes
     __shared__ long long s_r0[32];   // first arena row of each of them
-    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ __align__(8) uint64_t s_bar[2];
     __shared__ uint32_t s_hist[256];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t q = blockIdx.x;
@@ -507,7 +507,8 @@ __global__ void __launch_bounds__(SEED_THREADS, 8) seed_thresholds_kernel(const 
         s_r0[lane] = r0;
         if (lane == 31) s_start[32] = incl;
         if (lane == 0) {
-            mbar_init(&s_bar, 1);
+            mbar_init(&s_bar[0], 1);
+            mbar_init(&s_bar[1], 1);
             mbar_fence_init();
         }
     }
@@ -515,45 +516,49 @@ __global__ void __launch_bounds__(SEED_THREADS, 8) seed_thresholds_kernel(const 
     const int have = min(s_start[32], sample);
     const int dp4 = dp >> 2;
     const uint32_t row_bytes = (uint32_t)dp * 4u;
-    uint32_t phase = 0;
-    for (int base = 0; base < have; base += chunk_rows, phase ^= 1u) {
-        const int cn = min(chunk_rows, have - base);
-
-        if (warp == 0) {
-            // rows [base, base + cn) of the sample: one bulk copy per probed list they touch (contiguous when the arena
-            // has no row padding), else one per row
-            if (lane == 0) mbar_expect_tx(&s_bar, (uint32_t)cn * row_bytes);
-            __syncwarp();
-            const int lo = max(s_start[lane], base), hi = min(s_start[lane + 1], base + cn);
-            if (hi > lo) {
-                const float* src = vecs + (s_r0[lane] + (lo - s_start[lane])) * pitch;
-                float* dst = rows + (size_t)(lo - base) * dp;
-                if (pitch == dp) {
-                    bulk_g2s(dst, src, (uint32_t)(hi - lo) * row_bytes, &s_bar);
-                } else {
-                    for (int r = 0; r < hi - lo; ++r) bulk_g2s(dst + (size_t)r * dp, src + (size_t)r * pitch, row_bytes, &s_bar);
-                }
+    const int nchunks = (have + chunk_rows - 1) / chunk_rows;
+    // chunk c = rows [c * chunk_rows, ...) of the sample -> buffer c & 1: one bulk copy per probed list they touch
+    // (contiguous when the arena has no row padding), else one per row. Issued by warp 0 one chunk ahead of the scoring.
+    auto issue = [&](int c) {
+        if (warp != 0) return;
+        const int base = c * chunk_rows, cn = min(chunk_rows, have - base);
+        uint64_t* bar = &s_bar[c & 1];
+        float* buf = rows + (size_t)(c & 1) * chunk_rows * dp;
+        if (lane == 0) mbar_expect_tx(bar, (uint32_t)cn * row_bytes);
+        __syncwarp();
+        const int lo = max(s_start[lane], base), hi = min(s_start[lane + 1], base + cn);
+        if (hi > lo) {
+            const float* src = vecs + (s_r0[lane] + (lo - s_start[lane])) * pitch;
+            float* dst = buf + (size_t)(lo - base) * dp;
+            if (pitch == dp) {
+                bulk_g2s(dst, src, (uint32_t)(hi - lo) * row_bytes, bar);
+            } else {
+                for (int r = 0; r < hi - lo; ++r) bulk_g2s(dst + (size_t)r * dp, src + (size_t)r * pitch, row_bytes, bar);
             }
         }
-        if (base == 0) {
-            // the rows' squared norms, one coalesced load per sampled row, in flight together with the first bulk copy
-            // (read one by one inside the scoring loop they were a chain of dependent cache misses)
-            if (!kIP) {
-                for (int i = tid; i < have; i += SEED_THREADS) {
-                    int j = 0;
-                    while (j < 31 && i >= s_start[j + 1]) ++j;
-                    nrm[i] = norms[s_r0[j] + (i - s_start[j])];
-                }
-            }
-            __syncthreads();
+    };
+    if (nchunks > 0) issue(0);
+    // the rows' squared norms, one coalesced load per sampled row, in flight together with the first bulk copy
+    // (read one by one inside the scoring loop they were a chain of dependent cache misses)
+    if (!kIP) {
+        for (int i = tid; i < have; i += SEED_THREADS) {
+            int j = 0;
+            while (j < 31 && i >= s_start[j + 1]) ++j;
+            nrm[i] = norms[s_r0[j] + (i - s_start[j])];
         }
-        mbar_wait(&s_bar, phase);
+    }
+    __syncthreads();
+    for (int c = 0; c < nchunks; ++c) {
+        if (c + 1 < nchunks) issue(c + 1);  // its buffer was released by the barrier that ended iteration c - 1
+        const int base = c * chunk_rows, cn = min(chunk_rows, have - base);
+        const float* buf = rows + (size_t)(c & 1) * chunk_rows * dp;
+        mbar_wait(&s_bar[c & 1], (uint32_t)(c >> 1) & 1u);
         // one row per warp step: lane c holds 16-byte chunk c (conflict-free), reduced with shuffles
         for (int i = warp; i < cn; i += SEED_WARPS) {
-            const float4* rp = reinterpret_cast<const float4*>(rows + (size_t)i * dp);
+            const float4* rp = reinterpret_cast<const float4*>(buf + (size_t)i * dp);
             float acc = 0.f;
-            for (int c = lane; c < dp4; c += 32) {
-                const float4 x = rp[c], y = reinterpret_cast<const float4*>(qs)[c];
+            for (int cc = lane; cc < dp4; cc += 32) {
+                const float4 x = rp[cc], y = reinterpret_cast<const float4*>(qs)[cc];
                 acc = fmaf(x.x, y.x, acc); acc = fmaf(x.y, y.y, acc);
                 acc = fmaf(x.z, y.z, acc); acc = fmaf(x.w, y.w, acc);
             }
@@ -561,7 +566,7 @@ __global__ void __launch_bounds__(SEED_THREADS, 8) seed_thresholds_kernel(const 
             for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
             if (lane == 0) keys[base + i] = f2key(kIP ? -acc : fmaf(-2.f, acc, nrm[base + i]));
         }
-        __syncthreads();  // the staging buffer is refilled by the next chunk
+        __syncthreads();  // the buffer is refilled by the chunk after next
     }
     __syncthreads();
     if (warp != 0 || have < kc) return;  // fewer sampled rows than candidates wanted: no bound

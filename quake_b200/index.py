@@ -317,7 +317,8 @@ class QuakeIndex:
             h_ids, h_dist = stage[key]
             n8 = ids.numel() * 8
             if (ids.is_contiguous() and dist.is_contiguous() and ids.dtype == torch.int64
-                    and dist.data_ptr() == ids.data_ptr() + n8):
+                    and dist.data_ptr() == ids.data_ptr() + n8
+                    and ids.untyped_storage().data_ptr() == dist.untyped_storage().data_ptr()):
                 # one allocation on the device (_search_ivf), one on the host: a single D2H copy
                 if key not in stage.setdefault("_blocks", {}):
                     hb = torch.empty(n8 + dist.numel() * 4, dtype=torch.uint8).pin_memory()

@@ -1,2 +1,2 @@
-timeout 900 python -m pytest tests/test_gpu_index.py tests/test_gpu_configs.py -m gpu -x -q 2>&1 | tail -3
-QK_APS_TRACE=1 timeout 600 python scripts/aps_probe.py 10000000 2>&1 | grep -v "pseudo active 1024 -> 1024 ([0-9.]* ms)$" | tail -22
+timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -3
+timeout 900 python scripts/run_configs.py c3 --tag r02a 2>&1 | tail -2
