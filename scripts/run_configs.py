@@ -84,7 +84,8 @@ def c1(args):
         rsp = quake_ref.SearchParams(); rsp.k, rsp.nprobe = 10, 10
         sp = qb.SearchParams(); sp.k, sp.nprobe = 10, 10
         want = ref.search(q, rsp)
-        idx.search(q, sp)  # captures the search plan for this batch size
+        for _ in range(8):  # captures the search plan for this batch size; lets the filter-precision policy settle (it may
+            idx.search(q, sp)  # re-capture the plan once after its first 256 queries)
         got, t = timed(lambda: idx.search(q, sp), reps=20)
         _, tref = timed(lambda: ref.search(q, rsp), reps=3)
         out[f"Q{Q}"] = {"ids_equal_reference": bool(torch.equal(got.ids, want.ids)),
