@@ -112,7 +112,9 @@ int qk_scan_partitions(const qk_store_t* store,
  * lists -> top-k. `parent` must be a single-list store whose ids are the partition ids. shard_world > 1 scans only the
  * partitions with id % shard_world == shard_rank (lists sharded over GPUs, partition_manager.cpp:599-602): the result
  * is then this shard's PARTIAL top-k. out_probe_ids: optional [Q x min(nprobe, nlist)] int64, the probed partition
- * ids in rank order (the hit window of the maintenance policy reads them). */
+ * ids as a SET -- exactly the reference's nprobe nearest centroids (membership is settled in exact arithmetic wherever
+ * the filter's error bound leaves a doubt), the nearest by filter score first, the rest in no guaranteed order: the
+ * partition scan does not depend on it and the hit window of the maintenance policy counts per partition. */
 size_t qk_search_ivf_workspace_bytes(const qk_store_t* parent, const qk_store_t* store, int64_t num_queries,
                                      int nprobe, int k);
 int qk_search_ivf(const qk_store_t* parent, const qk_store_t* store,

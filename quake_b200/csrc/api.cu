@@ -19,6 +19,11 @@ int cuda_fail(cudaError_t e, const char* what) {
 }
 static std::atomic<long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+int pdl_mask() {
+    // default off: measured at C2 (round 2, graph replay) the step is the same with and without it, 238-242 us
+    static const int mask = getenv("QK_PDL") ? atoi(getenv("QK_PDL")) : 0;
+    return mask;
+}
 long long launches() { return g_launches.load(std::memory_order_relaxed); }
 int sm_count() {
     static int n[64] = {0};  // per device ordinal

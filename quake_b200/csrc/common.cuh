@@ -5,6 +5,7 @@
 #include <stdint.h>
 #include <math.h>
 #include <stdio.h>
+#include <string.h>
 #include "../../include/quake_b200.h"
 
 #if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
@@ -42,6 +43,32 @@ void count_launch();
         QK_CUDA(cudaGetLastError());           \
     } while (0)
 
+// Programmatic dependent launch (sm_90+): a kernel launched with launch_pdl() may start -- block scheduling, prologue --
+// while the previous kernel of its stream is still draining; it must call pdl_wait() before it touches anything that
+// kernel (or any earlier one) wrote. A primary that calls pdl_launch_dependents() early lets the dependent's CTAs become
+// resident as soon as every primary CTA has got that far. Inside a stream capture these become programmatic graph edges.
+// Both device calls are no-ops in a kernel launched the ordinary way. QK_PDL is a mask of the launch sites that use it
+// (1: grouping kernels after the coarse refine, 2: refine kernel after the partition scan; default 0 = none: no
+// measurable gain at C2, kept as an experiment switch).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+int pdl_mask();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(int site, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = (pdl_mask() & site) ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 // qk_scan_partitions with more knobs (library-internal callers: k-means assign, qk_search_ivf)
 struct ScanExtras {
     int rank_squared = 0;                    // l2: order results by the squared distance (k-means assign: faiss's Top1
@@ -51,6 +78,7 @@ struct ScanExtras {
     const int32_t* id_to_slot = nullptr;     // ... mapped through this dense table
     int64_t table_size = 0;
     int shard_rank = 0, shard_world = 1;     // shard_world > 1: scan only the partitions with id % world == rank
+    int set_mode = 0;                        // dense mode only: the k best as a set (refine.cuh: set_select_and_emit)
     // collect mode (APS rounds, qk_scan_collect): the per-query filter thresholds are GIVEN (device keys, [Q]) and
     // stay fixed -- every row at or below them is kept -- and instead of a top-k the survivors are refined exactly and
     // handed out grouped by the probe rank of their list

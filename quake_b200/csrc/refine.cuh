@@ -96,6 +96,9 @@ struct MergeArgs {
     const int32_t* x_list_seg0;
     const int32_t* x_list_nseg;
     int x_num_lists, x_shard_rank, x_shard_world;
+    // set mode (dense_refine_kernel, qk_search_ivf's coarse scan): the caller only needs WHICH k rows are the best, not
+    // their order or exact distances -- see set_select_and_emit
+    int set_mode;
 };
 
 // the fused expansion of one emitted result (see MergeArgs::x_pair_seg)
@@ -109,6 +112,25 @@ __device__ __forceinline__ void emit_expand(const MergeArgs& a, int64_t q, int i
     a.x_pair_seg[q * a.k + i] = seg;
     if (seg >= 0) atomicAdd(&a.x_seg_count[seg], 1);
     if (i == 0) a.x_gthr[q] = KEY_MAX;
+}
+
+// |q|^2 in double for the proof's bounds: warp 0, four partial sums per lane and a shuffle tree (one thread adding d
+// terms in sequence was a ~0.5 us chain at d = 128 that the CTA's first barrier waited for). Any accurate value will do:
+// the bound it enters carries relative slack of 2^-17 and more.
+__device__ __forceinline__ void block_query_sqnorm(const float* qs, int d, double* out) {
+    if (threadIdx.x < 32) {
+        double t0 = 0.0, t1 = 0.0;
+        int i = threadIdx.x;
+        for (; i + 32 < d; i += 64) {
+            t0 += (double)qs[i] * (double)qs[i];
+            t1 += (double)qs[i + 32] * (double)qs[i + 32];
+        }
+        if (i < d) t0 += (double)qs[i] * (double)qs[i];
+        double t = t0 + t1;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (threadIdx.x == 0) *out = t;
+    }
 }
 
 struct RescanSmem {
@@ -578,6 +600,151 @@ __device__ void refine_and_emit(const MergeArgs& a, int64_t q, const uint64_t* c
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Set mode: the k best rows as a SET (fixed-nprobe coarse scan: the partition scan that follows does not care in which
+// order a query's lists were probed, query_coordinator.cpp:628-645 only hands the ids on). Membership is decided from
+// the filter scores wherever the filter's error bound allows it and by exact arithmetic only where it does not:
+//   * the m > k candidates (everything else has a filter key >= a_key) are ranked by filter key; s_lo / s_hi = the
+//     k-th / (k+1)-th smallest score
+//   * [lo(s), hi(s)] bounds the value the REFERENCE orders by (sqrt'ed l2 distance in its summation order, or -ip) of
+//     any row whose filter score is s -- the same error model as the proof in refine_and_emit, used in both directions
+//   * a candidate with hi(s) < lo(s_hi) beats every row ranked k+1 or worse: a sure member; one with lo(s) > hi(s_lo)
+//     loses to k rows: surely out; the rows outside the candidate set must all be surely out (else: return false and
+//     the ordinary path runs). What remains -- typically the two or three candidates around the boundary, none at all
+//     for most queries -- is refined exactly and ordered by (distance, id) like the ordinary path does
+// Emits exactly k ids, best filter score first (the seed kernel samples a query's first list), with distances derived
+// from the filter score (approximate; nobody reads them). Saves the exact evaluation of ~k candidates and the
+// (distance, id) rank sort: a third of dense_refine_kernel's instructions at nprobe 64.
+// Returns false (nothing emitted) when the bounds do not settle it; all threads take the same decision.
+// ------------------------------------------------------------------------------------------------
+template <bool kIP>
+__device__ __forceinline__ void exact_value_bounds(float sc, double qn, double qnorm, double U, double fgam, int d, bool squared,
+                                                   float* lo, float* hi) {
+    const double eps = 5.960464477539063e-08;  // 2^-24
+    const double gam = (d + 8) * eps;
+    const double e2 = (d / 8 + 12) * eps;
+    if (!kIP) {
+        const double e1 = gam * U * U + 2.0 * (gam + fgam) * qnorm * U + 4.0 * eps * fabs((double)sc);
+        const float lbf = __double2float_rd((qn * (1.0 - gam) + (double)sc - e1) * (1.0 - e2));
+        const float ubf = __double2float_ru((qn * (1.0 + gam) + (double)sc + e1) * (1.0 + e2));
+        *lo = lbf > 0.f ? (squared ? lbf : __fsqrt_rn(lbf)) : 0.f;
+        *hi = ubf > 0.f ? (squared ? ubf : __fsqrt_rn(ubf)) : 0.f;
+        if (!(ubf == ubf) || !(lbf == lbf)) { *lo = 0.f; *hi = INFINITY; }  // NaN: nothing is settled
+    } else {
+        const double err = (gam + fgam + e2) * qnorm * U + 4.0 * eps * fabs((double)sc);
+        *lo = __double2float_rd((double)sc - err);
+        *hi = __double2float_ru((double)sc + err);
+        if (!(*lo == *lo) || !(*hi == *hi)) { *lo = -INFINITY; *hi = INFINITY; }
+    }
+}
+
+template <bool kIP>
+__device__ bool set_select_and_emit(const MergeArgs& a, int64_t q, const uint64_t* cand, int m, uint32_t a_key, bool have_rejects,
+                                    const RefineSmem& s, double qn2) {
+    __shared__ int s_nm, s_na;
+    __shared__ int s_wsum[MERGE_THREADS / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int k = a.k;
+    // 1. rank by filter key (ties by position): order[r] = candidate at rank r
+    for (int i = tid; i < m; i += MERGE_THREADS) {
+        const uint32_t ki = (uint32_t)(cand[i] >> 32);
+        int r = 0;
+        for (int j = 0; j < m; ++j) {
+            const uint32_t kj = (uint32_t)(cand[j] >> 32);
+            r += (kj < ki || (kj == ki && j < i)) ? 1 : 0;
+        }
+        s.order[r] = (uint32_t)i;
+    }
+    if (tid == 0) { s_nm = 0; s_na = 0; }
+    __syncthreads();
+    // 2. classify (every thread evaluates the same boundary bounds: the decision is uniform without a broadcast)
+    const double U = (double)(a.max_row_norm_dev ? *a.max_row_norm_dev : a.max_row_norm);
+    const double qnorm = sqrt(qn2);
+    const bool sq = a.rank_squared != 0;
+    float lo_klo, hi_klo, lo_khi, hi_khi;
+    exact_value_bounds<kIP>(key2f((uint32_t)(cand[s.order[k - 1]] >> 32)), qn2, qnorm, U, a.filter_gam, a.d, sq, &lo_klo, &hi_klo);
+    exact_value_bounds<kIP>(key2f((uint32_t)(cand[s.order[k]] >> 32)), qn2, qnorm, U, a.filter_gam, a.d, sq, &lo_khi, &hi_khi);
+    if (have_rejects) {
+        float lo_r, hi_r;
+        exact_value_bounds<kIP>(key2f(a_key), qn2, qnorm, U, a.filter_gam, a.d, sq, &lo_r, &hi_r);
+        if (!(lo_r > hi_klo)) return false;  // a row outside the candidate set might belong to the k best
+    }
+    for (int r = tid; r < m; r += MERGE_THREADS) {
+        float lo_i, hi_i;
+        exact_value_bounds<kIP>(key2f((uint32_t)(cand[s.order[r]] >> 32)), qn2, qnorm, U, a.filter_gam, a.d, sq, &lo_i, &hi_i);
+        int cls = 2;                       // undecided
+        if (hi_i < lo_khi) cls = 1;        // beats every row ranked k+1 or worse
+        else if (lo_i > hi_klo) cls = 0;   // loses to the k rows ranked k or better
+        if (cls == 1) atomicAdd(&s_nm, 1);
+        else if (cls == 2) s.rrow[atomicAdd(&s_na, 1)] = (uint32_t)r;
+        s.rank[r] = cls;
+    }
+    __syncthreads();
+    const int na = s_na, need = k - s_nm;
+    if (need < 0 || need > na) return false;  // cannot happen with monotone bounds; the ordinary path sorts it out
+    // 3. the undecided candidates: exact values, (distance, id) order, the `need` best are members
+    if (need > 0 && need < na) {
+        for (int base = 0; base < na; base += MERGE_THREADS / 8) {
+            const int x = base + (tid >> 3), j = tid & 7;
+            if (x < na) {  // uniform inside every 8-lane group
+                const uint32_t row = (uint32_t)cand[s.order[s.rrow[x]]];
+                const float dist = ref_pair_distance_g8<kIP>(s.qs, a.vecs + (int64_t)row * a.pitch, a.d, j);
+                if (j == 0) {
+                    s.rkey[x] = (uint64_t)f2key(kIP ? -dist : (sq ? dist : __fsqrt_rn(dist))) << 32;
+                    s.rid[x] = a.ids ? a.ids[row] : (int64_t)row;
+                }
+            }
+        }
+        __syncthreads();
+        for (int x = tid; x < na; x += MERGE_THREADS) {
+            const uint32_t dx = (uint32_t)(s.rkey[x] >> 32);
+            const int64_t idx = s.rid[x];
+            int before = 0;
+            for (int y = 0; y < na; ++y) {
+                const uint32_t dy = (uint32_t)(s.rkey[y] >> 32);
+                const int64_t idy = s.rid[y];
+                before += (dy < dx || (dy == dx && (idy < idx || (idy == idx && y < x)))) ? 1 : 0;
+            }
+            s.rank[s.rrow[x]] = before < need ? 1 : 0;
+        }
+    } else {
+        for (int x = tid; x < na; x += MERGE_THREADS) s.rank[s.rrow[x]] = need > 0 ? 1 : 0;
+    }
+    __syncthreads();
+    // 4. emit the members in filter-rank order
+    int carry = 0;
+    for (int base = 0; base < m; base += MERGE_THREADS) {
+        const int r = base + tid;
+        const bool member = r < m && s.rank[r] == 1;
+        const unsigned bal = __ballot_sync(0xffffffffu, member);
+        if (lane == 0) s_wsum[warp] = __popc(bal);
+        __syncthreads();
+        int off = carry, tot = 0;
+#pragma unroll
+        for (int w = 0; w < MERGE_THREADS / 32; ++w) {
+            const int c = s_wsum[w];
+            if (w < warp) off += c;
+            tot += c;
+        }
+        if (member) {
+            const int slot = off + __popc(bal & ((1u << lane) - 1u));
+            const uint64_t e = cand[s.order[r]];
+            const uint32_t row = (uint32_t)e;
+            const float sc = key2f((uint32_t)(e >> 32));
+            const int64_t id = a.ids ? a.ids[row] : (int64_t)row;
+            const float d2 = fmaxf((float)qn2 + sc, 0.f);
+            a.out_ids[q * k + slot] = id;
+            a.out_dist[q * k + slot] = kIP ? -sc : (sq ? d2 : sqrtf(d2));
+            if (a.out_rows) a.out_rows[q * k + slot] = row;
+            emit_expand(a, q, slot, id);
+        }
+        carry += tot;
+        __syncthreads();
+    }
+    if (tid == 0) a.flags[q] = 0;
+    return true;
+}
+
 // shared-memory carve-up common to both kernels: [front buffer][cbuf kcp u64][qs][rkey][rid][rrow][order][rank]
 __host__ __device__ inline size_t refine_tail_bytes(int d, int kcp) {
     return (size_t)kcp * 8 + (size_t)((d + 3) & ~3) * 4 + 8 + (size_t)kcp * (8 + 8 + 4 + 4 + 4);
@@ -615,13 +782,10 @@ __global__ void __launch_bounds__(MERGE_THREADS, MERGE_THREADS == 128 ? 8 : 5) m
     const int64_t q = blockIdx.x;
     const int tid = threadIdx.x;
     if (tid == 0) { s_n = 0; s_tot = 0; s_mm[0] = 0xffffffffu; s_mm[1] = 0u; }
+    pdl_wait();  // launched as a programmatic dependent of the filter kernel: nothing of its output is read above
     for (int i = tid; i < a.d; i += blockDim.x) s.qs[i] = a.queries[q * a.q_pitch + i];
     __syncthreads();
-    if (tid == 0) {
-        double t = 0.0;
-        for (int i = 0; i < a.d; ++i) t += (double)s.qs[i] * (double)s.qs[i];
-        s_qn = t;
-    }
+    block_query_sqnorm(s.qs, a.d, &s_qn);
 
     // ---- gather survivors: appended candidates whose filter key is within the final threshold
     const uint32_t gthr = a.gthr[q];
@@ -720,6 +884,7 @@ __global__ void __launch_bounds__(MERGE_THREADS, MERGE_THREADS == 128 ? 7 : 5) d
     const int tid = threadIdx.x;
     const int rows = a.dense_rows;
     const uint32_t* src = a.dense + (size_t)q * rows;
+    pdl_launch_dependents();  // the grouping kernel may become resident (it waits for this grid's completion itself)
     if (tid == 0) { s_mm[0] = 0xffffffffu; s_mm[1] = 0u; s_valid = 0u; }
     for (int i = tid; i < a.d; i += blockDim.x) s.qs[i] = a.queries[q * a.q_pitch + i];
     __syncthreads();
@@ -767,11 +932,7 @@ __global__ void __launch_bounds__(MERGE_THREADS, MERGE_THREADS == 128 ? 7 : 5) d
         }
         if ((tid & 31) == 0 && valid) { atomicMin(&s_mm[0], mn); atomicMax(&s_mm[1], mx); atomicAdd(&s_valid, valid); }
     }
-    if (tid == 0) {
-        double t = 0.0;
-        for (int i = 0; i < a.d; ++i) t += (double)s.qs[i] * (double)s.qs[i];
-        s_qn = t;
-    }
+    block_query_sqnorm(s.qs, a.d, &s_qn);
     __syncthreads();
     bool rescan = a.force_rescan != 0;
     int m = 0;
@@ -791,6 +952,7 @@ __global__ void __launch_bounds__(MERGE_THREADS, MERGE_THREADS == 128 ? 7 : 5) d
         atomicMax(&a.ctrl[3], m);
         atomicAdd(reinterpret_cast<unsigned long long*>(a.ctrl + 4), (unsigned long long)m);
     }
+    if (a.set_mode && !rescan && m > a.k && set_select_and_emit<kIP>(a, q, cbuf, m, s_T, /*have_rejects=*/rows > m, s, s_qn)) return;
     refine_and_emit<kIP>(a, q, cbuf, m, s_T, /*have_rejects=*/rows > m, rescan, s, s_qn, rs, &s_flag);
 }
 

@@ -313,6 +313,8 @@ __global__ void __launch_bounds__(1024) prefix_segments_kernel(const int32_t* __
     __shared__ int2 carry;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) carry = make_int2(0, 0);
+    pdl_launch_dependents();
+    pdl_wait();
     __syncthreads();
     for (int base = 0; base < S; base += 1024) {
         int s = base + tid;
@@ -366,6 +368,7 @@ __global__ void scatter_pairs_kernel(const int32_t* __restrict__ pair_seg, int64
                                      int32_t* __restrict__ seg_pairs, const int32_t* __restrict__ item_start,
                                      const int64_t* __restrict__ seg_row0, const int32_t* __restrict__ seg_rows, int gq,
                                      WorkItem* __restrict__ items) {
+    pdl_wait();
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < QP) {
         int seg = pair_seg[i];
@@ -456,18 +459,23 @@ __device__ __forceinline__ uint32_t radix_select(KeyAt key_at, int n, int kc, ui
 // The sampled rows are contiguous runs of the arena (one per probed list): they are fetched with TMA bulk copies into
 // shared memory, SEED_CHUNK rows at a time, so the kernel is a stream of a few large asynchronous copies per SM instead
 // of register-limited dependent loads (it was latency-bound: 39-63 us for 67 MB at C2).
-// 128 threads and 16 KB of staging per CTA: eight CTAs share an SM, so a batch of 1024 queries is ONE wave of 148 x 8
-// slots (with 256 threads / 32 KB it was 1.7 waves of four, each CTA mostly waiting for its own bulk copy: 41 us at C2;
-// now 25 us). Plain 16-byte loads into registers, eight rows in flight per warp, were slower (32 us).
+// 128 threads and 24 KB of staging per CTA (three 8 KB buffers: two bulk copies in flight behind the chunk being
+// scored): eight CTAs share an SM, so a batch of 1024 queries is ONE wave of 148 x 8 slots (with 256 threads / 32 KB it
+// was 1.7 waves of four, each CTA mostly waiting for its own bulk copy: 41 us at C2). Plain 16-byte loads into
+// registers, eight rows in flight per warp, were slower (32 us).
+// Scoring: EIGHT LANES PER ROW, four rows per warp step -- lane (r, j) sums the 16-byte pieces j, j + 8, ... of row r
+// (a quarter-warp reads 128 contiguous bytes: conflict-free) and three shuffles finish the row; one row per warp step
+// with a five-shuffle reduction spent three times the instructions and the kernel was issue-bound (56 % issue-active).
 static constexpr int SEED_THREADS = 128;
 static constexpr int SEED_WARPS = SEED_THREADS / 32;
-static int seed_chunk_rows(int dp, int sample) {  // rows per staging buffer: at most 8 KB (16 rows at d = 128); two buffers
+static constexpr int SEED_NBUF = 3;
+static int seed_chunk_rows(int dp, int sample) {  // rows per staging buffer: at most 8 KB (16 rows at d = 128)
     int c = (8 * 1024) / (dp * 4);
     if (c < 4) c = 4;
     return sample < c ? sample : c;
 }
 static size_t seed_smem_bytes(int dp, int sample) {
-    return (size_t)2 * seed_chunk_rows(dp, sample) * dp * 4 + (size_t)dp * 4 + (size_t)sample * 8 + 16;
+    return (size_t)SEED_NBUF * seed_chunk_rows(dp, sample) * dp * 4 + (size_t)dp * 4 + (size_t)sample * 8 + 16;
 }
 template <bool kIP>
 __global__ void __launch_bounds__(SEED_THREADS, 8) seed_thresholds_kernel(const float* __restrict__ vecs, int64_t pitch,
@@ -479,13 +487,13 @@ __global__ void __launch_bounds__(SEED_THREADS, 8) seed_thresholds_kernel(const 
                                                               int chunk_rows, float max_row_norm, float rel_margin,
                                                               uint32_t* __restrict__ gthr) {
     extern __shared__ __align__(128) unsigned char seed_raw[];
-    float* rows = reinterpret_cast<float*>(seed_raw);                 // [2][chunk_rows][dp]: double-buffered staging
-    float* qs = rows + (size_t)2 * chunk_rows * dp;                   // [dp]
+    float* rows = reinterpret_cast<float*>(seed_raw);                 // [SEED_NBUF][chunk_rows][dp]: staging ring
+    float* qs = rows + (size_t)SEED_NBUF * chunk_rows * dp;           // [dp]
     uint32_t* keys = reinterpret_cast<uint32_t*>(qs + dp);            // [sample]
     float* nrm = reinterpret_cast<float*>(keys + sample);             // [sample] squared norms of the sampled rows
     __shared__ int s_start[33];      // exclusive prefix of the sampled rows over the first 32 probes
     __shared__ long long s_r0[32];   // first arena row of each of them
-    __shared__ __align__(8) uint64_t s_bar[2];
+    __shared__ __align__(8) uint64_t s_bar[SEED_NBUF];
     __shared__ uint32_t s_hist[256];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t q = blockIdx.x;
@@ -507,8 +515,8 @@ __global__ void __launch_bounds__(SEED_THREADS, 8) seed_thresholds_kernel(const 
         s_r0[lane] = r0;
         if (lane == 31) s_start[32] = incl;
         if (lane == 0) {
-            mbar_init(&s_bar[0], 1);
-            mbar_init(&s_bar[1], 1);
+#pragma unroll
+            for (int b = 0; b < SEED_NBUF; ++b) mbar_init(&s_bar[b], 1);
             mbar_fence_init();
         }
     }
@@ -517,13 +525,14 @@ __global__ void __launch_bounds__(SEED_THREADS, 8) seed_thresholds_kernel(const 
     const int dp4 = dp >> 2;
     const uint32_t row_bytes = (uint32_t)dp * 4u;
     const int nchunks = (have + chunk_rows - 1) / chunk_rows;
-    // chunk c = rows [c * chunk_rows, ...) of the sample -> buffer c & 1: one bulk copy per probed list they touch
-    // (contiguous when the arena has no row padding), else one per row. Issued by warp 0 one chunk ahead of the scoring.
+    // chunk c = rows [c * chunk_rows, ...) of the sample -> buffer c % SEED_NBUF: one bulk copy per probed list they
+    // touch (contiguous when the arena has no row padding), else one per row. Issued by warp 0, SEED_NBUF - 1 chunks
+    // ahead of the scoring.
     auto issue = [&](int c) {
         if (warp != 0) return;
         const int base = c * chunk_rows, cn = min(chunk_rows, have - base);
-        uint64_t* bar = &s_bar[c & 1];
-        float* buf = rows + (size_t)(c & 1) * chunk_rows * dp;
+        uint64_t* bar = &s_bar[c % SEED_NBUF];
+        float* buf = rows + (size_t)(c % SEED_NBUF) * chunk_rows * dp;
         if (lane == 0) mbar_expect_tx(bar, (uint32_t)cn * row_bytes);
         __syncwarp();
         const int lo = max(s_start[lane], base), hi = min(s_start[lane + 1], base + cn);
@@ -537,8 +546,10 @@ __global__ void __launch_bounds__(SEED_THREADS, 8) seed_thresholds_kernel(const 
             }
         }
     };
-    if (nchunks > 0) issue(0);
-    // the rows' squared norms, one coalesced load per sampled row, in flight together with the first bulk copy
+#pragma unroll
+    for (int c = 0; c < SEED_NBUF - 1; ++c)
+        if (c < nchunks) issue(c);
+    // the rows' squared norms, one coalesced load per sampled row, in flight together with the first bulk copies
     // (read one by one inside the scoring loop they were a chain of dependent cache misses)
     if (!kIP) {
         for (int i = tid; i < have; i += SEED_THREADS) {
@@ -548,25 +559,31 @@ __global__ void __launch_bounds__(SEED_THREADS, 8) seed_thresholds_kernel(const 
         }
     }
     __syncthreads();
+    const int sub = lane >> 3, j8 = lane & 7;  // row of the warp's group of four, 16-byte piece within the row
     for (int c = 0; c < nchunks; ++c) {
-        if (c + 1 < nchunks) issue(c + 1);  // its buffer was released by the barrier that ended iteration c - 1
+        // the buffer of chunk c + SEED_NBUF - 1 held chunk c - 1: released by the barrier that ended iteration c - 1
+        if (c + SEED_NBUF - 1 < nchunks) issue(c + SEED_NBUF - 1);
         const int base = c * chunk_rows, cn = min(chunk_rows, have - base);
-        const float* buf = rows + (size_t)(c & 1) * chunk_rows * dp;
-        mbar_wait(&s_bar[c & 1], (uint32_t)(c >> 1) & 1u);
-        // one row per warp step: lane c holds 16-byte chunk c (conflict-free), reduced with shuffles
-        for (int i = warp; i < cn; i += SEED_WARPS) {
-            const float4* rp = reinterpret_cast<const float4*>(buf + (size_t)i * dp);
-            float acc = 0.f;
-            for (int cc = lane; cc < dp4; cc += 32) {
+        const float* buf = rows + (size_t)(c % SEED_NBUF) * chunk_rows * dp;
+        mbar_wait(&s_bar[c % SEED_NBUF], (uint32_t)(c / SEED_NBUF) & 1u);
+        for (int i0 = warp * 4; i0 < cn; i0 += SEED_WARPS * 4) {
+            const int i = i0 + sub;
+            const bool live = i < cn;
+            const float4* rp = reinterpret_cast<const float4*>(buf + (size_t)(live ? i : i0) * dp);
+            float a0 = 0.f, a1 = 0.f;
+#pragma unroll 4
+            for (int cc = j8; cc < dp4; cc += 8) {
                 const float4 x = rp[cc], y = reinterpret_cast<const float4*>(qs)[cc];
-                acc = fmaf(x.x, y.x, acc); acc = fmaf(x.y, y.y, acc);
-                acc = fmaf(x.z, y.z, acc); acc = fmaf(x.w, y.w, acc);
+                a0 = fmaf(x.x, y.x, a0); a1 = fmaf(x.y, y.y, a1);
+                a0 = fmaf(x.z, y.z, a0); a1 = fmaf(x.w, y.w, a1);
             }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-            if (lane == 0) keys[base + i] = f2key(kIP ? -acc : fmaf(-2.f, acc, nrm[base + i]));
+            float acc = a0 + a1;
+            acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+            acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+            acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+            if (live && j8 == 0) keys[base + i] = f2key(kIP ? -acc : fmaf(-2.f, acc, nrm[base + i]));
         }
-        __syncthreads();  // the buffer is refilled by the chunk after next
+        __syncthreads();  // the buffer is refilled SEED_NBUF - 1 chunks later
     }
     __syncthreads();
     if (warp != 0 || have < kc) return;  // fewer sampled rows than candidates wanted: no bound
@@ -1433,12 +1450,13 @@ int qk::scan_partitions_impl(const qk_store_t* st, const float* queries, int64_t
     ScanArgs sa;
     memset(&sa, 0, sizeof(sa));
     if (!flat) {
-        prefix_segments_kernel<<<1, 1024, 0, stream>>>(seg_count, S, p.gq, seg_start, item_start, ctrl);
+        const int64_t n = QP > S ? QP : S;
+        QK_CUDA(launch_pdl(1, prefix_segments_kernel, dim3(1), dim3(1024), 0, stream, (const int32_t*)seg_count, S, p.gq, seg_start,
+                           item_start, ctrl));
         QK_LAUNCHED();
-        int64_t n = QP > S ? QP : S;
-        scatter_pairs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(pair_seg, QP, S, seg_start, seg_fill,
-                                                                               seg_pairs, item_start, st->seg_row0,
-                                                                               st->seg_rows, p.gq, items);
+        QK_CUDA(launch_pdl(1, scatter_pairs_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, stream,
+                           (const int32_t*)pair_seg, QP, S, (const int32_t*)seg_start, seg_fill, seg_pairs,
+                           (const int32_t*)item_start, st->seg_row0, st->seg_rows, p.gq, items));
         QK_LAUNCHED();
     } else {
         sa.flat = 1;
@@ -1539,6 +1557,7 @@ int qk::scan_partitions_impl(const qk_store_t* st, const float* queries, int64_t
     ma.out_ids = out_ids; ma.out_dist = out_dist; ma.out_rows = out_rows;
     ma.force_rescan = g_force_rescan;
     ma.rank_squared = ex.rank_squared;
+    ma.set_mode = (ex.set_mode && p.dense) ? 1 : 0;
     if (ex.fused_expand) {
         const FusedExpand& fx = *ex.fused_expand;
         ma.x_pair_seg = fx.pair_seg; ma.x_seg_count = fx.seg_count; ma.x_gthr = fx.gthr;
@@ -1567,10 +1586,10 @@ int qk::scan_partitions_impl(const qk_store_t* st, const float* queries, int64_t
         const size_t msmem = (size_t)sort_cap * 8 + refine_tail_bytes(st->d, kcp);
         if (ip) {
             if ((rc = ensure_smem(merge_refine_kernel<true>, msmem))) return rc;
-            merge_refine_kernel<true><<<(unsigned)Q, MERGE_THREADS, msmem, stream>>>(ma);
+            QK_CUDA(launch_pdl(2, merge_refine_kernel<true>, dim3((unsigned)Q), dim3(MERGE_THREADS), msmem, stream, ma));
         } else {
             if ((rc = ensure_smem(merge_refine_kernel<false>, msmem))) return rc;
-            merge_refine_kernel<false><<<(unsigned)Q, MERGE_THREADS, msmem, stream>>>(ma);
+            QK_CUDA(launch_pdl(2, merge_refine_kernel<false>, dim3((unsigned)Q), dim3(MERGE_THREADS), msmem, stream, ma));
         }
     }
     QK_LAUNCHED();
@@ -1682,6 +1701,10 @@ extern "C" int qk_search_ivf(const qk_store_t* parent, const qk_store_t* store, 
     fx.shard_rank = shard_rank; fx.shard_world = shard_world < 1 ? 1 : shard_world;
     ScanExtras cx;
     if (fuse) cx.fused_expand = &fx;
+    // the partition scan does not depend on the order of a query's probes: the coarse scan only has to settle WHICH np
+    // centroids are the nearest (out_probe_ids: nearest by filter score first, the rest in no guaranteed order)
+    static const bool no_set_mode = getenv("QK_SET_MODE") && atoi(getenv("QK_SET_MODE")) == 0;
+    cx.set_mode = no_set_mode ? 0 : 1;
     cx.pre_refine_event = side->join2;  // joins the clearing branch back into the stream
     rc = scan_partitions_impl(parent, queries, Q, q_pitch, nullptr, 1, metric, L.np, p_ids, p_dist, nullptr, ws + L.off_coarse,
                               L.coarse_bytes, nullptr, stream, cx);

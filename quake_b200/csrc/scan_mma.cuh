@@ -247,6 +247,9 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) scan_mma_kernel(const ScanArgs
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int dp = a.dp, kc = a.kc;
     const int nbox = (dp + MMA_BOX - 1) / MMA_BOX;  // 1..4
+    // the refine kernel (a programmatic dependent, common.cuh) may be scheduled as this grid's CTAs leave; it waits for
+    // the grid's completion itself before it reads a candidate
+    pdl_launch_dependents();
     // Ring slots in use: a multiple of two tiles' worth of boxes (8, 8, 6, 8 for 1..4 boxes per tile), so that each of
     // the two MMA issuers (alternate tiles) meets every slot it uses in EVERY round. With 3 boxes per tile on 8 slots an
     // issuer would skip rounds of a slot; its parity wait could then be satisfied by the completion of an older round
