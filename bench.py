@@ -635,14 +635,16 @@ def build_section(qb, x, W, dev, binfo, build_s):
     N, K, d = W["N"], W["nlist"], W["d"]
     xd = clustering.pad_rows(x, dev)
     cents = xd[torch.randperm(N, device=dev)[:K]].clone()
+    filt = clustering.AssignFilter(dev)  # the precision policy of a training run (2xTF32 unless points get re-scanned)
     for _ in range(2):  # warm-up of all three stages (first launches load the kernels)
-        a = clustering.assign_points(xd, d, cents, _lib.QK_METRIC_L2)
+        a = clustering.assign_points(xd, d, cents, _lib.QK_METRIC_L2, filt=filt)
+        filt.review()
         counts, offsets, order = clustering.partition_by_assignment(a, K)
         sums = clustering.centroid_sums(xd, d, order, offsets, K)
     e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
     torch.cuda.synchronize()
     e[0].record()
-    a = clustering.assign_points(xd, d, cents, _lib.QK_METRIC_L2)
+    a = clustering.assign_points(xd, d, cents, _lib.QK_METRIC_L2, filt=filt)
     e[1].record()
     counts, offsets, order = clustering.partition_by_assignment(a, K)
     e[2].record()
@@ -656,7 +658,8 @@ def build_section(qb, x, W, dev, binfo, build_s):
     hbm = float(peaks.get("hbm_gbs", 6650.0))
     return {"build_s": round(build_s, 3), "train_time_us": getattr(binfo, "train_time_us", None),
             "assign": {"ms": round(t_assign, 3), "tflops": round(flop / (t_assign * 1e-3) / 1e12, 2),
-                       "note": "3xTF32 tensor-core filter + exact refine of the winner (k = 1); flop = 2*N*K*d",
+                       "note": f"{filt.terms}xTF32 tensor-core filter + exact refine of the winner (k = 1); flop = 2*N*K*d",
+                       "points_rescanned_exactly": int(filt.stats[0].item()),
                        "frac_of_bf16_dense_peak": round(flop / (t_assign * 1e-3) / 1e12 / tf_peak, 4) if tf_peak else None},
             "update": {"sort_ms": round(t_sort, 3), "sums_ms": round(t_sum, 3), "largest_list": int(counts.max()),
                        "note": "first Lloyd iteration (random initial centroids): list sizes are skewed, the per-centroid "

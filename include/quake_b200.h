@@ -231,6 +231,18 @@ int qk_kmeans_assign(const float* points, int64_t n, int64_t point_pitch, int d,
                      const float* centroids, int64_t num_centroids, int64_t centroid_pitch,
                      int metric, int32_t* out_assign, float* out_distances,
                      void* workspace, size_t workspace_bytes, void* stream);
+/* The same with the tensor-core filter's precision chosen by the caller: filter_terms 3 = 3xTF32 (what
+ * qk_kmeans_assign uses), 2 = 2xTF32 (no a_lo term: 1.3x faster at K = 4096 .. 16384, d = 128). The assignment is the
+ * same either way -- the winner is evaluated in exact arithmetic and a point whose proof fails is re-scanned
+ * exhaustively -- but a looser filter sends more points to that slow re-scan on data whose nearest centroids are
+ * closer together than its error bound. out_stats (optional, device int32[2], zeroed by the caller): [0] += points
+ * re-scanned exactly, [1] = max candidates of one point -- the evidence the host's precision policy reads
+ * (quake_b200/clustering.py: start with 2 terms, fall back to 3 for the rest of a training run once more than 0.5 % of
+ * a call's points were re-scanned). Same workspace as qk_kmeans_assign. */
+int qk_kmeans_assign_filtered(const float* points, int64_t n, int64_t point_pitch, int d,
+                              const float* centroids, int64_t num_centroids, int64_t centroid_pitch,
+                              int metric, int filter_terms, int32_t* out_assign, float* out_distances,
+                              int32_t* out_stats, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Replaces faiss compute_centroids (third_party/faiss/faiss/Clustering.cpp:123-192) and the scalar
  * accumulation loop of kmeans_refine_partitions (clustering.cpp:162-175): per-centroid sum of

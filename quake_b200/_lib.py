@@ -96,6 +96,10 @@ PROTOTYPES = {
         C.c_int,
         [vp, C.c_int64, C.c_int64, C.c_int, vp, C.c_int64, C.c_int64, C.c_int, vp, vp, vp, C.c_size_t, vp],
     ),
+    "qk_kmeans_assign_filtered": (
+        C.c_int,
+        [vp, C.c_int64, C.c_int64, C.c_int, vp, C.c_int64, C.c_int64, C.c_int, C.c_int, vp, vp, vp, vp, C.c_size_t, vp],
+    ),
     "qk_kmeans_accumulate": (C.c_int, [vp, C.c_int64, C.c_int, vp, vp, C.c_int64, vp, C.c_int64, vp]),
     "qk_partition_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int64]),
     "qk_partition_by_assignment": (C.c_int, [vp, C.c_int64, C.c_int64, vp, vp, vp, vp, C.c_size_t, vp]),

@@ -43,8 +43,38 @@ def rand_perm_prefix(n: int, seed: int, m: int) -> np.ndarray:
     return out
 
 
-def assign_points(x: torch.Tensor, d: int, centroids: torch.Tensor, metric: int, want_dist: bool = False):
-    """Nearest centroid of every row of x ([n, pitch] device) -> int32 [n] (and distances)."""
+ASSIGN_FILTER_POLICY = "auto"  # "auto": 2xTF32 until the evidence says otherwise; "3": always 3xTF32; "2": always 2xTF32
+_ASSIGN_RESCAN_LIMIT = 0.005   # fraction of a call's points sent to the exact re-scan before a run falls back to 3 terms
+
+
+class AssignFilter:
+    """Filter precision of the k-means assign over one training / refit run (include/quake_b200.h:
+    qk_kmeans_assign_filtered). The assignment itself is exact either way; this only decides how fast it is found."""
+
+    def __init__(self, device):
+        import os
+        policy = os.environ.get("QK_ASSIGN_FILTER", ASSIGN_FILTER_POLICY)
+        self.fixed = policy in ("2", "3")
+        self.terms = 3 if policy == "3" else 2
+        self.stats = torch.zeros(2, dtype=torch.int32, device=device)
+        self.points = 0
+
+    def review(self) -> None:
+        """Reads the evidence of the calls since the last review (one small D2H copy: call it where the host
+        synchronises anyway) and falls back to 3 terms for good when too many points were re-scanned."""
+        if self.fixed or self.terms == 3 or self.points == 0:
+            return
+        rescanned = int(self.stats[0].item())
+        if rescanned > max(8, int(_ASSIGN_RESCAN_LIMIT * self.points)):
+            self.terms = 3
+        self.stats.zero_()
+        self.points = 0
+
+
+def assign_points(x: torch.Tensor, d: int, centroids: torch.Tensor, metric: int, want_dist: bool = False,
+                  filt: AssignFilter | None = None):
+    """Nearest centroid of every row of x ([n, pitch] device) -> int32 [n] (and distances). `filt`: the run's
+    filter-precision state (None: 3xTF32)."""
     lib = _lib.load()
     _lib.require_device()
     n, K = int(x.shape[0]), int(centroids.shape[0])
@@ -54,8 +84,12 @@ def assign_points(x: torch.Tensor, d: int, centroids: torch.Tensor, metric: int,
     if wsb == 0:
         check(1)
     ws = torch.empty(wsb, dtype=torch.uint8, device=x.device)
-    check(lib.qk_kmeans_assign(ptr(x), n, x.stride(0), d, ptr(centroids), K, centroids.stride(0), metric, ptr(out),
-                               ptr(dist), ptr(ws), wsb, _stream()))
+    terms = filt.terms if filt is not None else 3
+    stats = filt.stats if filt is not None else None
+    check(lib.qk_kmeans_assign_filtered(ptr(x), n, x.stride(0), d, ptr(centroids), K, centroids.stride(0), metric, terms,
+                                        ptr(out), ptr(dist), ptr(stats), ptr(ws), wsb, _stream()))
+    if filt is not None:
+        filt.points += n
     return (out, dist) if want_dist else out
 
 
@@ -83,7 +117,7 @@ def centroid_sums(x: torch.Tensor, d: int, order: torch.Tensor, offsets: torch.T
     return sums
 
 
-def train_centroids(x: torch.Tensor, d: int, K: int, metric: int, niter: int) -> torch.Tensor:
+def train_centroids(x: torch.Tensor, d: int, K: int, metric: int, niter: int, filt: AssignFilter | None = None) -> torch.Tensor:
     """faiss::Clustering::train (Clustering.cpp:255-539) with default ClusteringParameters:
     subsample to K*256 points (seed 1234), initial centroids = first K of rand_perm(seed + 1),
     niter x [assign; mean update; split empty clusters]."""
@@ -100,13 +134,15 @@ def train_centroids(x: torch.Tensor, d: int, K: int, metric: int, niter: int) ->
         return x[:K].clone()
     perm = rand_perm_prefix(nx, FAISS_SEED + 1, K)
     centroids = xt[torch.from_numpy(perm).to(x.device)].clone()
+    filt = filt if filt is not None else AssignFilter(x.device)
     for _ in range(niter):
-        assign = assign_points(xt, d, centroids, metric)
+        assign = assign_points(xt, d, centroids, metric, filt=filt)
         counts, offsets, order = partition_by_assignment(assign, K)
         sums = centroid_sums(xt, d, order, offsets, K)
         hassign = counts.to(torch.float32)
         inv = torch.where(hassign > 0, 1.0 / hassign, torch.zeros_like(hassign))
         centroids = sums * inv[:, None]
+        filt.review()  # beside the synchronisation below
         if bool((counts == 0).any()):
             c_h = centroids.cpu().contiguous()
             h_h = hassign.cpu().contiguous()
@@ -126,7 +162,8 @@ def kmeans(x: torch.Tensor, d: int, K: int, metric: int, niter: int):
     n = int(x.shape[0])
     if metric == _lib.QK_METRIC_INNER_PRODUCT:
         check(lib.qk_normalize_rows(ptr(x), n, x.stride(0), d, _stream()))
-    trained = train_centroids(x, d, K, metric, niter)
+    filt = AssignFilter(x.device)
+    trained = train_centroids(x, d, K, metric, niter, filt)
     centroids = trained
     if metric == _lib.QK_METRIC_INNER_PRODUCT:
         centroids = trained.clone()
@@ -134,7 +171,7 @@ def kmeans(x: torch.Tensor, d: int, K: int, metric: int, niter: int):
     # the final assignment searches the faiss index, which still holds the centroids of the last
     # iteration -- un-normalised for ip (clustering.cpp:65 uses index_ptr, not the normalised copy
     # that is returned); argmax <x, c> and argmax <x, c/|c|> can differ, so keep the reference's choice.
-    assign = assign_points(x, d, trained, metric)
+    assign = assign_points(x, d, trained, metric, filt=filt)
     counts, offsets, order = partition_by_assignment(assign, K)
     return centroids, counts, offsets, order
 
@@ -155,7 +192,9 @@ def kmeans_refine(centroids: torch.Tensor, d: int, vecs: torch.Tensor, ids: torc
     counts = torch.zeros(K, dtype=torch.int64, device=vecs.device)
     identity = torch.arange(n, dtype=torch.int64, device=vecs.device)
     offsets = None
+    filt = AssignFilter(vecs.device)
     for it in range(iters):
+        filt.review()
         if it > 0:
             sums = centroid_sums(vecs, d, identity, offsets, K)
             # 0/0 = NaN for an emptied cluster, as in the reference (clustering.cpp:122-124)
@@ -163,7 +202,7 @@ def kmeans_refine(centroids: torch.Tensor, d: int, vecs: torch.Tensor, ids: torc
         if n == 0:
             offsets = torch.zeros(K + 1, dtype=torch.int64, device=vecs.device)
             continue
-        assign = assign_points(vecs, d, centroids, metric)
+        assign = assign_points(vecs, d, centroids, metric, filt=filt)
         counts, offsets, order = partition_by_assignment(assign, K)
         vecs = vecs[order]
         ids = ids[order]

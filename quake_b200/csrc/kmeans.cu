@@ -501,7 +501,7 @@ extern "C" int qk_merge_topk(const float* part_distances, const int64_t* part_id
 namespace {
 struct AssignLayout {
     size_t off_seg_row0, off_seg_rows, off_list_seg0, off_list_nseg, off_probe, off_rows, off_dist, off_ids, off_norm,
-        off_cnorms, off_scan, scan_bytes, total;
+        off_cnorms, off_stats, off_scan, scan_bytes, total;
     int nseg;
 };
 int64_t assign_batch(int64_t n) { return n < 65536 ? n : 65536; }
@@ -531,6 +531,7 @@ int assign_layout(int64_t n, int64_t K, int d, AssignLayout* L) {
     L->off_dist = take((size_t)B * 4);
     L->off_norm = take(4);
     L->off_cnorms = take((size_t)K * 4);
+    L->off_stats = take(64);
     L->off_scan = take(L->scan_bytes);
     L->total = o;
     return QK_OK;
@@ -555,10 +556,27 @@ extern "C" size_t qk_kmeans_assign_workspace_bytes(int64_t n, int64_t K, int d) 
     return L.total;
 }
 
+namespace {
+// out[0] += queries the batch re-scanned exactly, out[1] = max(out[1], most candidates of one query)
+__global__ void assign_stats_kernel(const int32_t* __restrict__ batch_stats, int32_t* __restrict__ out) {
+    out[0] += batch_stats[0];
+    out[1] = max(out[1], batch_stats[1]);
+}
+}  // namespace
+
 extern "C" int qk_kmeans_assign(const float* points, int64_t n, int64_t point_pitch, int d, const float* centroids,
                                 int64_t K, int64_t centroid_pitch, int metric, int32_t* out_assign,
                                 float* out_distances, void* workspace, size_t workspace_bytes, void* stream_v) {
+    return qk_kmeans_assign_filtered(points, n, point_pitch, d, centroids, K, centroid_pitch, metric, 3, out_assign,
+                                     out_distances, nullptr, workspace, workspace_bytes, stream_v);
+}
+
+extern "C" int qk_kmeans_assign_filtered(const float* points, int64_t n, int64_t point_pitch, int d, const float* centroids,
+                                         int64_t K, int64_t centroid_pitch, int metric, int filter_terms, int32_t* out_assign,
+                                         float* out_distances, int32_t* out_stats, void* workspace, size_t workspace_bytes,
+                                         void* stream_v) {
     cudaStream_t stream = (cudaStream_t)stream_v;
+    QK_REQUIRE(filter_terms == 2 || filter_terms == 3, "filter_terms must be 2 or 3");
     QK_REQUIRE(points && centroids && out_assign && n > 0 && K > 0 && d > 0, "bad argument");
     AssignLayout L;
     int rc = assign_layout(n, K, d, &L);
@@ -603,6 +621,7 @@ extern "C" int qk_kmeans_assign(const float* points, int64_t n, int64_t point_pi
     st.seg_row0 = seg_row0;
     st.seg_rows = seg_rows;
     st.max_row_norm = 0.f;  // the bound stays on the device (ScanExtras::max_row_norm_dev): no host synchronisation
+    st.filter_terms = filter_terms;
     st.row_norms = cnorms;
     st.num_rows = K;
     st.flat_row0 = 0;
@@ -614,9 +633,14 @@ extern "C" int qk_kmeans_assign(const float* points, int64_t n, int64_t point_pi
         ex.rank_squared = 1;
         ex.max_row_norm_dev = norm;
         // flat mode (no probe table): every point scans the whole centroid list
+        int32_t* batch_stats = out_stats ? (int32_t*)(ws + L.off_stats) : nullptr;
         rc = scan_partitions_impl(&st, points + b * point_pitch, cnt, point_pitch, nullptr, 1, metric, 1, ids, dist, rows,
-                                  ws + L.off_scan, L.scan_bytes, nullptr, stream, ex);
+                                  ws + L.off_scan, L.scan_bytes, batch_stats, stream, ex);
         if (rc) return rc;
+        if (out_stats) {
+            assign_stats_kernel<<<1, 1, 0, stream>>>(batch_stats, out_stats);
+            QK_LAUNCHED();
+        }
         assign_finish_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, stream>>>(rows, dist, cnt, out_assign + b,
                                                                                 out_distances ? out_distances + b : nullptr);
         QK_LAUNCHED();

@@ -184,7 +184,7 @@ class ShardedQuakeIndex:
             centroids = trained.clone()
             check(_lib.load().qk_normalize_rows(ptr(centroids), K, centroids.stride(0), d, _stream()))
         # ---- 2. assignment of the local slice (against the un-normalised trained centroids, like kmeans())
-        assign = clustering.assign_points(xd, d, trained, self.metric).to(torch.int64)
+        assign = clustering.assign_points(xd, d, trained, self.metric, filt=clustering.AssignFilter(dev)).to(torch.int64)
         # ---- 3. exchange: rows sorted by (owner, partition), one all-to-all for vectors, ids, partition ids
         owner = owner_of(assign, self.world)
         order = torch.argsort(owner * K + assign, stable=True)

@@ -1,8 +1,6 @@
 #!/usr/bin/env bash
 set -u
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_index.py tests/test_gpu_scan.py -m gpu -x -q 2>&1 | tail -3
-bash scripts/gpu_ab.sh carve+ncu nocarve:QK_CARVEOUT=0 carve2 nocarve2:QK_CARVEOUT=0
-QK_BENCH_CUPROF=1 timeout 600 ncu --profile-from-start off --set full --clock-control none --import-source on \
-  -k regex:"dense_refine|merge_refine" -c 2 -f -o gpurun_out/prof_rest_d2 python bench.py --steps 1 --warmup 3 --no-cpu-baseline --quick > gpurun_out/ncu_rest_d2.log 2>&1
-tail -2 gpurun_out/ncu_rest_d2.log
+timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -6
+python scripts/assign_speed.py 1000000 4096 2>&1 | tail -1
+timeout 600 python bench.py --no-cpu-baseline --steps 20 --warmup 5 2>/dev/null | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(d.get('build')); print(d['ms_per_step'], d['config'].get('build_s'), d.get('build_s'))"

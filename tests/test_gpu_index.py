@@ -202,6 +202,41 @@ def test_kmeans_assign_update_match_oracle(metric):
 
 
 @pytest.mark.parametrize("metric", ["l2", "ip"])
+def test_kmeans_assign_filter_precision_policy(metric):
+    """qk_kmeans_assign_filtered: the 2xTF32 filter returns the assignment of the 3xTF32 one (the winner is decided in
+    exact arithmetic either way); many copies of one centroid make the proof fail for every point nearest to it --
+    those points take the exact re-scan (lowest index still wins) and the run's policy falls back to three terms."""
+    from quake_b200 import clustering, _lib
+    dev = torch.device("cuda", 0)
+    g = torch.Generator().manual_seed(33)
+    n, K, d = 20000, 256, 64
+    x = torch.randn(n, d, generator=g)
+    c = torch.randn(K, d, generator=g)
+    m = _lib.QK_METRIC_INNER_PRODUCT if metric == "ip" else _lib.QK_METRIC_L2
+    xd, cd = clustering.pad_rows(x, dev), clustering.pad_rows(c, dev)
+    filt = clustering.AssignFilter(dev)
+    assert filt.terms == 2
+    a2 = clustering.assign_points(xd, d, cd, m, filt=filt)
+    a3 = clustering.assign_points(xd, d, cd, m)
+    want = orc.assign(x.numpy(), c.numpy(), metric)
+    assert np.array_equal(a2.cpu().numpy(), want) and np.array_equal(a3.cpu().numpy(), want)
+    filt.review()
+    assert filt.terms == 2  # nothing (or next to nothing) was re-scanned on this data
+    # seventeen copies each of centroids 5, 6 and 7: more tied rows than the refine keeps candidates, for > 0.5 % of the points
+    c[16:32], c[32:48], c[48:64] = c[5], c[6], c[7]
+    cd = clustering.pad_rows(c, dev)
+    a2 = clustering.assign_points(xd, d, cd, m, filt=filt)
+    want = orc.assign(x.numpy(), c.numpy(), metric)
+    assert np.array_equal(a2.cpu().numpy(), want)
+    tied = int(((a2 >= 5) & (a2 <= 7)).sum())
+    assert not ((a2 >= 16) & (a2 < 64)).any() and tied > 0.005 * n
+    rescanned = int(filt.stats[0].item())
+    assert rescanned >= tied
+    filt.review()
+    assert filt.terms == 3
+
+
+@pytest.mark.parametrize("metric", ["l2", "ip"])
 @pytest.mark.parametrize("iters", [0, 3])
 def test_kmeans_refine_matches_reference_golden(metric, iters):
     """kmeans_refine_partitions (clustering.cpp:99-182) vs the reference's own output."""
