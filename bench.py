@@ -428,6 +428,12 @@ def run_b200(args):
     e1.record()
     barrier()
     probe_ms = e0.elapsed_time(e1)
+    if world > 1:
+        # every rank must run the SAME number of timed regions: each one is bracketed by collectives, and a rank that
+        # derived one repeat fewer from its own probe would leave the others waiting in a barrier for ever
+        pm = torch.tensor([probe_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(pm, op=dist.ReduceOp.MAX)
+        probe_ms = float(pm.item())
     repeats = int(min(60, max(3, -(-MIN_TIMED_MS // max(probe_ms, 1e-3)))))
     l0 = _qi.launch_count()
     dev_runs = []
@@ -479,7 +485,10 @@ def run_b200(args):
             del x
             log("waiting for the sharded section")
             barrier()
-            extra["sharded"] = sharded_section(qb, world, rank, dev, args)
+            try:
+                extra["sharded"] = sharded_section(qb, world, rank, dev, args)
+            except Exception as e:  # an error every rank hits alike (e.g. out of memory): keep the headline line
+                extra["sharded"] = {"error": f"{type(e).__name__}: {e}"[:300]}
 
     if rank == 0:
         peaks = {}
