@@ -428,13 +428,7 @@ def run_b200(args):
     e1.record()
     barrier()
     probe_ms = e0.elapsed_time(e1)
-    if world > 1:
-        # every rank must run the SAME number of timed regions: each one is bracketed by collectives, and a rank that
-        # derived one repeat fewer from its own probe would leave the others waiting in a barrier for ever
-        pm = torch.tensor([probe_ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(pm, op=dist.ReduceOp.MAX)
-        probe_ms = float(pm.item())
-    repeats = int(min(60, max(3, -(-MIN_TIMED_MS // max(probe_ms, 1e-3)))))
+    repeats = agreed_repeats(probe_ms, world, dev)
     l0 = _qi.launch_count()
     dev_runs = []
     for _ in range(repeats):
@@ -537,6 +531,20 @@ def run_b200(args):
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+def agreed_repeats(probe_ms: float, world: int, device) -> int:
+    """How many times the K-step region is repeated so that >= MIN_TIMED_MS of GPU work is timed -- THE SAME NUMBER ON
+    EVERY RANK: each region is bracketed by collectives, and a rank that derived one repeat fewer from its own probe
+    time would leave the others waiting in a barrier for ever (the 8-GPU run of round 2 hung exactly there). The probe
+    time is all-reduced (max) first; the result is a function of that one number only."""
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        pm = torch.tensor([float(probe_ms)], dtype=torch.float64, device=device)
+        dist.all_reduce(pm, op=dist.ReduceOp.MAX)
+        probe_ms = float(pm.item())
+    return int(min(60, max(3, -(-MIN_TIMED_MS // max(probe_ms, 1e-3)))))
 
 
 def recall_at_k(ids, gt):
