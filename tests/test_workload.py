@@ -65,3 +65,67 @@ def test_generate_and_replay_roundtrip(tmp_path):
     assert recalls and min(recalls) > 0.9
     assert (tmp_path / "out" / "quake_b200_results.json").exists()
     assert ev.summary["avg_query_recall"] == pytest.approx(float(np.mean(recalls)))
+
+
+# ------------------------------------------------------------------ pinned against the reference's own generator
+def _golden_workload():
+    import os
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    return np.load(os.path.join(here, "workload.npz")), json.load(open(os.path.join(here, "workload.json")))
+
+
+def _golden_dataset(seed, n, nq, d):
+    # the dataset of tests/golden/make_golden_workload.py
+    g = torch.Generator().manual_seed(seed)
+    centers = torch.randn(12, d, generator=g) * 4.0
+    base = centers[torch.randint(0, 12, (n,), generator=g)] + torch.randn(n, d, generator=g)
+    queries = centers[torch.randint(0, 12, (nq,), generator=g)] + torch.randn(nq, d, generator=g)
+    return base, queries
+
+
+class _RecordedClustering:
+    """Stands in for the clustered index: the reference's own centroids (the generator only asks for those)."""
+
+    def __init__(self, centroids):
+        self._c = centroids
+
+    def centroids(self):
+        return self._c
+
+
+@pytest.mark.parametrize("case", ["skewed", "uniform"])
+def test_generator_draws_the_reference_stream(case, tmp_path):
+    """The operation stream of DynamicWorkloadGenerator equals the one the REFERENCE's generator drew on the same
+    inputs (tests/golden/workload.{npz,json}, written by make_golden_workload.py from
+    /root/reference/src/python/workload_generator.py): operation types (np.random.choice), sampled ids of every
+    operation and of the initial resident set (torch.randperm / randint inside the samplers, in the reference's call
+    order), resident-set sizes, and the ground-truth neighbours of every query batch. The reference's clustering
+    (assignments, centroids, and the state its k-means left torch's global generator in) is injected, so the test needs
+    no GPU."""
+    z, meta = _golden_workload()
+    m = meta[case]
+    base, queries = _golden_dataset(*m["dataset"])
+
+    class Gen(wl.DynamicWorkloadGenerator):
+        def initialize_clustered_index(self):
+            self.assignments = torch.from_numpy(z[f"{case}_assignments"])
+            # the reference's C++ k-means draws from torch's global generator: the state it left is part of the recording
+            torch.set_rng_state(torch.from_numpy(z[f"{case}_rng_after_clustering"]))
+            return _RecordedClustering(torch.from_numpy(z[f"{case}_centroids"]))
+
+    gen = Gen(tmp_path / "w", base, queries=queries, **m["kwargs"])
+    book = gen.generate_workload()
+    assert book["summary"] == m["summary"]
+    assert book["parameters"] == m["parameters"]
+    assert torch.equal(torch.load(tmp_path / "w" / "initial_indices.pt"), torch.from_numpy(z[f"{case}_initial"]))
+    ops = book["operations"]
+    assert [ops[i]["type"] for i in sorted(ops)] == m["types"]
+    assert [ops[i]["sample_size"] for i in sorted(ops)] == m["sizes"]
+    assert [ops[i]["n_resident"] for i in sorted(ops)] == z[f"{case}_n_resident"].tolist()
+    offs = z[f"{case}_op_offsets"]
+    for j, i in enumerate(sorted(ops)):
+        ids = torch.load(tmp_path / "w" / "operations" / f"{i}.pt")
+        assert ids.tolist() == z[f"{case}_op_ids"][offs[j]:offs[j + 1]].tolist(), f"operation {i}"
+        if ops[i]["type"] == "query":
+            gt = torch.load(tmp_path / "w" / "operations" / f"{i}_gt_ids.pt")
+            assert torch.equal(gt[:, :10], torch.from_numpy(z[f"{case}_gt_{i}"])), f"ground truth of operation {i}"
