@@ -130,12 +130,20 @@ class QuakeWrapper:
     def save(self, filename):
         self.index.save(str(filename))
 
-    def load(self, filename, n_workers: int = 0, **_ignored):
+    def load(self, filename, n_workers: int = 0, use_numa: bool = False, verbose: bool = False, verify_numa: bool = False,
+             same_core: bool = True, use_centroid_workers: bool = False, use_adaptive_n_probe: bool = False):
+        """index_wrappers/quake.py:166-187. The worker / NUMA switches of the reference's CPU engine are accepted and
+        have no meaning here (as in the reference's own wrapper, which only prints them)."""
         self.index = QuakeIndex()
         self.index.load(str(filename), n_workers)
 
     def centroids(self) -> torch.Tensor:
         return self.index.parent.get(self.index.parent.get_ids())
+
+    def cluster_ids(self) -> torch.Tensor:
+        """index_wrappers/quake.py:198-204 forwards to ``index.cluster_assignments()``, which the reference's bindings
+        (wrap.cpp:57-186) do not define; kept for the surface, with the same outcome."""
+        return self.index.cluster_assignments()
 
     def metric(self) -> str:
         return "ip" if self.index.metric == 0 else "l2"
